@@ -1,0 +1,557 @@
+/*
+ * vafgpu_api.cu -- the C ABI of include/vafgpu.h: contexts, pinned staging blocks, one
+ * stream per block for copy/compute overlap, round-robin over the devices, one NCCL
+ * all-reduce of the counters at the end.  Host logic only; the kernels are in
+ * vafgpu_kernels.cu.
+ */
+#include "../../include/vafgpu.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> /* types only; the library is loaded at run time when it is needed */
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "vafgpu_kernels.cuh"
+#include "vafgpu_tables.hpp"
+
+using namespace vafgpu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Block {
+	char *h = nullptr;        /* pinned host staging */
+	uint8_t *d = nullptr;     /* device copy         */
+	cudaStream_t stream = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; /* copy start, copy end, kernel end */
+	bool in_flight = false;
+	size_t used = 0;
+};
+
+struct Device {
+	int ordinal = 0;
+	int n_sm = 0;
+	uint32_t *d_filter = nullptr;
+	vg_slot_t *d_slots = nullptr;
+	uint64_t *d_rkeys = nullptr;
+	uint32_t *d_rvals = nullptr;
+	uint32_t *d_counts = nullptr;
+	unsigned long long *d_stats = nullptr;
+	cudaStream_t main_stream = nullptr;
+	std::vector<Block> blocks;
+	ncclComm_t comm = nullptr;
+};
+
+struct Nccl {
+	void *lib = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+	                          cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+} // namespace
+
+struct vafgpu_ctx {
+	int k = 0;
+	unsigned flags = 0;
+	uint32_t n_patterns = 0;
+	size_t n_counts = 0; /* 2 * n_patterns, at least 2 */
+	size_t block_bytes = 0;
+	Plan plan;
+	uint32_t filter_words = 0, slot_bits = 0, rbits = 0;
+	std::vector<Device> devs;
+	Nccl nccl;
+	/* producer state */
+	Block *cur = nullptr;
+	int cur_dev = 0;
+	uint64_t seq = 0; /* blocks handed out so far: round-robin over devices, then buffers */
+	std::vector<char> scratch;
+	vafgpu_stats st{};
+	std::string err;
+};
+
+namespace {
+
+int fail(vafgpu_ctx *c, int code, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (c) c->err = buf;
+	else g_create_error = buf;
+	return code;
+}
+
+#define CU(c, call)                                                                              \
+	do {                                                                                         \
+		cudaError_t e_ = (call);                                                                 \
+		if (e_ != cudaSuccess)                                                                   \
+			return fail(c, VAFGPU_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+/* the byte rules of the reference encoder, applied while copying (see vafgpu.h) */
+const char kNibbleRule[16 + 1] = "NANCTTNGNNNNNNNN"; /* vaf-counter.c:272-275 */
+
+struct StrictRule {
+	char t[256];
+	StrictRule()
+	{
+		memset(t, 'N', sizeof t);
+		t[0] = 'A', t[1] = 'C', t[2] = 'G', t[3] = 'T'; /* vaf-counter.c:74 */
+		t['A'] = t['a'] = 'A';
+		t['C'] = t['c'] = 'C';
+		t['G'] = t['g'] = 'G';
+		t['T'] = t['t'] = t['U'] = t['u'] = 'T';
+	}
+};
+const StrictRule kStrictRule;
+
+void account(vafgpu_ctx *c, Block &b)
+{
+	float ms = 0;
+	if (cudaEventElapsedTime(&ms, b.e0, b.e1) == cudaSuccess) c->st.h2d_ms += ms;
+	if (cudaEventElapsedTime(&ms, b.e1, b.e2) == cudaSuccess) c->st.kernel_ms += ms;
+}
+
+int wait_block(vafgpu_ctx *c, Block &b)
+{
+	if (!b.in_flight) return VAFGPU_OK;
+	CU(c, cudaEventSynchronize(b.e2));
+	account(c, b);
+	b.in_flight = false;
+	return VAFGPU_OK;
+}
+
+int acquire(vafgpu_ctx *c)
+{
+	const size_t nd = c->devs.size();
+	const int di = (int)(c->seq % nd);
+	Device &d = c->devs[di];
+	Block &b = d.blocks[(c->seq / nd) % d.blocks.size()];
+	++c->seq;
+	int rc = wait_block(c, b);
+	if (rc) return rc;
+	b.used = 0;
+	c->cur = &b;
+	c->cur_dev = di;
+	return VAFGPU_OK;
+}
+
+ScanArgs scan_args(const vafgpu_ctx *c, const Device &d, const uint8_t *bytes, size_t n, uint32_t *counts)
+{
+	ScanArgs a{};
+	a.bytes = bytes;
+	a.n_bytes = n;
+	a.counts = counts ? counts : d.d_counts;
+	a.stats = d.d_stats;
+	a.k = c->k;
+	a.stride = c->plan.stride;
+	a.len = c->plan.len;
+	a.filter = d.d_filter;
+	a.filter_words = c->filter_words;
+	a.slots = d.d_slots;
+	a.slot_bits = c->slot_bits;
+	a.rkeys = d.d_rkeys;
+	a.rvals = d.d_rvals;
+	a.rbits = c->rbits;
+	return a;
+}
+
+cudaError_t launch(const vafgpu_ctx *c, const Device &d, const ScanArgs &a, cudaStream_t s)
+{
+	return (c->flags & VAFGPU_F_REFERENCE_RECIPE) ? launch_recipe_scan(a, d.n_sm, s)
+	                                              : launch_anchor_scan(a, d.n_sm, s);
+}
+
+/* copy the current block to its device and scan it there, all on the block's stream */
+int submit_current(vafgpu_ctx *c)
+{
+	Block *b = c->cur;
+	if (!b) return VAFGPU_OK;
+	c->cur = nullptr;
+	if (b->used == 0) return VAFGPU_OK;
+	Device &d = c->devs[c->cur_dev];
+	size_t n = (b->used + 15) & ~(size_t)15;
+	memset(b->h + b->used, '\n', n - b->used);
+	CU(c, cudaSetDevice(d.ordinal));
+	CU(c, cudaEventRecord(b->e0, b->stream));
+	CU(c, cudaMemcpyAsync(b->d, b->h, n, cudaMemcpyHostToDevice, b->stream));
+	CU(c, cudaEventRecord(b->e1, b->stream));
+	CU(c, launch(c, d, scan_args(c, d, b->d, n, nullptr), b->stream));
+	CU(c, cudaEventRecord(b->e2, b->stream));
+	b->in_flight = true;
+	c->st.n_blocks++;
+	c->st.n_bytes += n;
+	return VAFGPU_OK;
+}
+
+/* room for `need` more bytes in the current block, submitting / acquiring as required */
+int ensure_room(vafgpu_ctx *c, size_t need)
+{
+	if (c->cur && c->cur->used + need > c->block_bytes) {
+		int rc = submit_current(c);
+		if (rc) return rc;
+	}
+	if (!c->cur) return acquire(c);
+	return VAFGPU_OK;
+}
+
+int load_nccl(vafgpu_ctx *c)
+{
+	Nccl &n = c->nccl;
+	if (n.lib) return VAFGPU_OK;
+	n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!n.lib) n.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!n.lib) return fail(c, VAFGPU_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                          \
+	*(void **)(&n.field) = dlsym(n.lib, name);                                    \
+	if (!n.field) return fail(c, VAFGPU_ENCCL, "libnccl lacks %s", name);
+	SYM(CommInitAll, "ncclCommInitAll")
+	SYM(CommDestroy, "ncclCommDestroy")
+	SYM(AllReduce, "ncclAllReduce")
+	SYM(GroupStart, "ncclGroupStart")
+	SYM(GroupEnd, "ncclGroupEnd")
+	SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+	return VAFGPU_OK;
+}
+
+void destroy_device(Device &d)
+{
+	cudaSetDevice(d.ordinal);
+	for (Block &b : d.blocks) {
+		if (b.stream) cudaStreamSynchronize(b.stream);
+		if (b.h) cudaFreeHost(b.h);
+		if (b.d) cudaFree(b.d);
+		if (b.e0) cudaEventDestroy(b.e0);
+		if (b.e1) cudaEventDestroy(b.e1);
+		if (b.e2) cudaEventDestroy(b.e2);
+		if (b.stream) cudaStreamDestroy(b.stream);
+	}
+	if (d.main_stream) cudaStreamDestroy(d.main_stream);
+	cudaFree(d.d_filter);
+	cudaFree(d.d_slots);
+	cudaFree(d.d_rkeys);
+	cudaFree(d.d_rvals);
+	cudaFree(d.d_counts);
+	cudaFree(d.d_stats);
+}
+
+} // namespace
+
+extern "C" {
+
+const char *vafgpu_version(void) { return "vafgpu 0.1 (sm_100a)"; }
+
+int vafgpu_plan(int k, int *stride, int *len)
+{
+	if (k < 1 || k > 31) return VAFGPU_EINVAL;
+	Plan p = make_plan(k);
+	if (stride) *stride = p.stride;
+	if (len) *len = p.len;
+	return VAFGPU_OK;
+}
+
+void vafgpu_canonicalise_read(const char *seq, size_t len, char *out, int simd_rule)
+{
+	const size_t body = simd_rule ? (len & ~(size_t)15) : 0; /* vaf-counter.c:278 */
+	size_t i = 0;
+	for (; i < body; ++i) out[i] = kNibbleRule[(unsigned char)seq[i] & 15];
+	for (; i < len; ++i) out[i] = kStrictRule.t[(unsigned char)seq[i]]; /* vaf-counter.c:288-290 */
+}
+
+const char *vafgpu_strerror(const vafgpu_ctx *ctx)
+{
+	return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t *vals, uint32_t n_entries,
+                  uint32_t n_patterns, size_t block_bytes, int n_buffers, int n_devices, unsigned flags)
+{
+	if (!out) return fail(nullptr, VAFGPU_EINVAL, "ctx is NULL");
+	*out = nullptr;
+	if (k < 1 || k > 31) return fail(nullptr, VAFGPU_EINVAL, "k = %d is outside 1..31", k);
+	if (n_entries && (!keys || !vals)) return fail(nullptr, VAFGPU_EINVAL, "keys/vals are NULL");
+	if (n_patterns > 0x3FFFFFFFu) return fail(nullptr, VAFGPU_EINVAL, "too many patterns (%u)", n_patterns);
+	const uint64_t kmask = (1ULL << 2 * k) - 1;
+	for (uint32_t i = 0; i < n_entries; ++i) {
+		if (keys[i] > kmask) return fail(nullptr, VAFGPU_EINVAL, "key %u does not fit 2k bits", i);
+		if (vals[i] >= 2ull * n_patterns) return fail(nullptr, VAFGPU_EINVAL, "value %u names pattern %u of %u", i, vals[i] >> 1, n_patterns);
+	}
+	int visible = 0;
+	cudaError_t ce = cudaGetDeviceCount(&visible);
+	if (ce != cudaSuccess || visible < 1)
+		return fail(nullptr, VAFGPU_ENOGPU, "no CUDA device: %s", ce == cudaSuccess ? "count is 0" : cudaGetErrorString(ce));
+	if (n_devices <= 0 || n_devices > visible) n_devices = visible;
+	if (block_bytes == 0) block_bytes = (size_t)16 << 20;
+	if (block_bytes < 4096) block_bytes = 4096;
+	if (block_bytes > ((size_t)1 << 34)) return fail(nullptr, VAFGPU_EINVAL, "block_bytes too large");
+	if (n_buffers <= 0) n_buffers = 3;
+
+	vafgpu_ctx *c = new (std::nothrow) vafgpu_ctx;
+	if (!c) return fail(nullptr, VAFGPU_ENOMEM, "out of memory");
+	c->k = k;
+	c->flags = flags;
+	c->n_patterns = n_patterns;
+	c->n_counts = (size_t)2 * (n_patterns ? n_patterns : 1);
+	c->block_bytes = block_bytes;
+
+	RecipeTable rt;
+	AnchorTables at;
+	build_recipe_table(k, keys, vals, n_entries, n_patterns, rt);
+	build_anchor_tables(k, keys, vals, n_entries, at);
+	c->plan = at.plan;
+	c->filter_words = (uint32_t)at.filter.size();
+	c->slot_bits = at.slot_bits;
+	c->rbits = rt.bits;
+
+	int rc = VAFGPU_OK;
+	c->devs.resize(n_devices);
+	for (int i = 0; i < n_devices && rc == VAFGPU_OK; ++i) {
+		Device &d = c->devs[i];
+		d.ordinal = i;
+		rc = [&]() -> int {
+			cudaDeviceProp prop;
+			CU(c, cudaSetDevice(i));
+			CU(c, cudaGetDeviceProperties(&prop, i));
+			if (prop.major != 10)
+				return fail(c, VAFGPU_ENOGPU, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", i, prop.name, prop.major, prop.minor);
+			d.n_sm = prop.multiProcessorCount;
+			CU(c, kernels_init_device(d.n_sm));
+			CU(c, cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
+			CU(c, cudaMalloc(&d.d_filter, at.filter.size() * 4));
+			CU(c, cudaMalloc(&d.d_slots, at.slots.size() * sizeof(vg_slot_t)));
+			CU(c, cudaMalloc(&d.d_rkeys, rt.keys.size() * 8));
+			CU(c, cudaMalloc(&d.d_rvals, rt.vals.size() * 4));
+			CU(c, cudaMalloc(&d.d_counts, c->n_counts * 4));
+			CU(c, cudaMalloc(&d.d_stats, ST_N * sizeof(unsigned long long)));
+			CU(c, cudaMemcpy(d.d_filter, at.filter.data(), at.filter.size() * 4, cudaMemcpyHostToDevice));
+			CU(c, cudaMemcpy(d.d_slots, at.slots.data(), at.slots.size() * sizeof(vg_slot_t), cudaMemcpyHostToDevice));
+			CU(c, cudaMemcpy(d.d_rkeys, rt.keys.data(), rt.keys.size() * 8, cudaMemcpyHostToDevice));
+			CU(c, cudaMemcpy(d.d_rvals, rt.vals.data(), rt.vals.size() * 4, cudaMemcpyHostToDevice));
+			CU(c, cudaMemset(d.d_counts, 0, c->n_counts * 4));
+			CU(c, cudaMemset(d.d_stats, 0, ST_N * sizeof(unsigned long long)));
+			d.blocks.resize(n_buffers);
+			for (Block &b : d.blocks) {
+				CU(c, cudaHostAlloc(&b.h, block_bytes + 64, cudaHostAllocPortable));
+				CU(c, cudaMalloc(&b.d, block_bytes + 64));
+				CU(c, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+				CU(c, cudaEventCreate(&b.e0));
+				CU(c, cudaEventCreate(&b.e1));
+				CU(c, cudaEventCreate(&b.e2));
+			}
+			return VAFGPU_OK;
+		}();
+	}
+	if (rc == VAFGPU_OK && n_devices > 1 && !(flags & VAFGPU_F_HOST_MERGE)) {
+		rc = load_nccl(c);
+		if (rc == VAFGPU_OK) {
+			std::vector<ncclComm_t> comms(n_devices);
+			std::vector<int> ids(n_devices);
+			for (int i = 0; i < n_devices; ++i) ids[i] = i;
+			ncclResult_t nr = c->nccl.CommInitAll(comms.data(), n_devices, ids.data());
+			if (nr != ncclSuccess) rc = fail(c, VAFGPU_ENCCL, "ncclCommInitAll: %s", c->nccl.GetErrorString(nr));
+			else for (int i = 0; i < n_devices; ++i) c->devs[i].comm = comms[i];
+		}
+	}
+	if (rc != VAFGPU_OK) {
+		g_create_error = c->err;
+		vafgpu_destroy(c);
+		return rc;
+	}
+	c->st.n_devices = n_devices;
+	c->st.anchor_stride = c->plan.stride;
+	c->st.anchor_len = c->plan.len;
+	c->st.filter_bytes = c->filter_words * 4;
+	c->st.table_slots = 1u << c->slot_bits;
+	*out = c;
+	return VAFGPU_OK;
+}
+
+int vafgpu_add_read(vafgpu_ctx *c, const char *seq, size_t len)
+{
+	if (!c || (!seq && len)) return VAFGPU_EINVAL;
+	if (len < (size_t)c->k) return VAFGPU_OK; /* vaf-counter.c:494 */
+	c->st.n_reads++;
+	c->st.n_bases += len;
+	const bool simd = true; /* the Makefile builds the reference with -mssse3 (Makefile:44) */
+	if (len + 1 <= c->block_bytes) {
+		int rc = ensure_room(c, len + 1);
+		if (rc) return rc;
+		Block *b = c->cur;
+		vafgpu_canonicalise_read(seq, len, b->h + b->used, simd);
+		b->h[b->used + len] = '\n';
+		b->used += len + 1;
+		return VAFGPU_OK;
+	}
+	/* a read longer than a block (a chromosome): canonicalise it whole, since the byte rule
+	 * depends on the offset within the read, then cut it into pieces that overlap by k-1
+	 * bases so that every k-mer lies in exactly one piece */
+	if (c->scratch.size() < len) c->scratch.resize(len);
+	vafgpu_canonicalise_read(seq, len, c->scratch.data(), simd);
+	const size_t piece = c->block_bytes - 1, step = piece - (size_t)(c->k - 1);
+	for (size_t at = 0;; at += step) {
+		size_t n = len - at < piece ? len - at : piece;
+		int rc = ensure_room(c, n + 1);
+		if (rc) return rc;
+		Block *b = c->cur;
+		memcpy(b->h + b->used, c->scratch.data() + at, n);
+		b->h[b->used + n] = '\n';
+		b->used += n + 1;
+		if (at + n >= len) break;
+	}
+	return VAFGPU_OK;
+}
+
+int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint64_t n_reads, uint64_t n_bases)
+{
+	if (!c || (!bytes && n_bytes)) return VAFGPU_EINVAL;
+	c->st.n_reads += n_reads;
+	c->st.n_bases += n_bases;
+	size_t at = 0;
+	while (at < n_bytes) {
+		/* close whatever add_read left open, then fill whole blocks straight from the caller */
+		int rc = submit_current(c);
+		if (rc) return rc;
+		rc = acquire(c);
+		if (rc) return rc;
+		Block *b = c->cur;
+		size_t n = n_bytes - at;
+		if (n > c->block_bytes) {
+			/* cut after the last separator that fits; a single read longer than a block is cut
+			 * with a k-1 overlap like in vafgpu_add_read */
+			n = c->block_bytes;
+			const char *nl = (const char *)memrchr(bytes + at, '\n', n);
+			if (nl) n = (size_t)(nl - (bytes + at)) + 1;
+			else {
+				memcpy(b->h, bytes + at, n - 1);
+				b->h[n - 1] = '\n';
+				b->used = n;
+				at += n - 1 - (size_t)(c->k - 1);
+				continue;
+			}
+		}
+		memcpy(b->h, bytes + at, n);
+		b->used = n;
+		if (b->h[n - 1] != '\n') b->h[b->used++] = '\n';
+		at += n;
+	}
+	return submit_current(c);
+}
+
+int vafgpu_count_device(vafgpu_ctx *c, int device, const void *d_bytes, size_t n_bytes, uint32_t *d_counts, void *stream)
+{
+	if (!c || device < 0 || device >= (int)c->devs.size()) return VAFGPU_EINVAL;
+	if (((uintptr_t)d_bytes & 15) || (n_bytes & 15)) return fail(c, VAFGPU_EINVAL, "device stream must be 16-byte aligned and a multiple of 16 bytes");
+	Device &d = c->devs[device];
+	CU(c, cudaSetDevice(d.ordinal));
+	cudaStream_t s = stream ? (cudaStream_t)stream : d.main_stream;
+	CU(c, launch(c, d, scan_args(c, d, (const uint8_t *)d_bytes, n_bytes, d_counts), s));
+	c->st.n_blocks++;
+	c->st.n_bytes += n_bytes;
+	return VAFGPU_OK;
+}
+
+int vafgpu_finish(vafgpu_ctx *c, uint32_t *counts, vafgpu_stats *stats)
+{
+	if (!c) return VAFGPU_EINVAL;
+	int rc = submit_current(c);
+	if (rc) return rc;
+	for (Device &d : c->devs) {
+		CU(c, cudaSetDevice(d.ordinal));
+		for (Block &b : d.blocks) {
+			rc = wait_block(c, b);
+			if (rc) return rc;
+		}
+		CU(c, cudaStreamSynchronize(d.main_stream));
+	}
+	const size_t nd = c->devs.size();
+	std::vector<uint32_t> total(c->n_counts, 0);
+	if (nd > 1 && !(c->flags & VAFGPU_F_HOST_MERGE)) {
+		/* the one collective of the path: sum the per-device counter vectors over NVLink */
+		ncclResult_t nr = c->nccl.GroupStart();
+		for (size_t i = 0; i < nd && nr == ncclSuccess; ++i) {
+			Device &d = c->devs[i];
+			nr = c->nccl.AllReduce(d.d_counts, d.d_counts, c->n_counts, ncclUint32, ncclSum, d.comm, d.main_stream);
+		}
+		if (nr == ncclSuccess) nr = c->nccl.GroupEnd();
+		if (nr != ncclSuccess) return fail(c, VAFGPU_ENCCL, "ncclAllReduce: %s", c->nccl.GetErrorString(nr));
+		for (size_t i = 0; i < nd; ++i) {
+			Device &d = c->devs[i];
+			CU(c, cudaSetDevice(d.ordinal));
+			CU(c, cudaStreamSynchronize(d.main_stream));
+			/* every device now holds the total; keep it on device 0 only so that counting can
+			 * go on (more input files) and a later finish() still sums to the right answer */
+			if (i) CU(c, cudaMemset(d.d_counts, 0, c->n_counts * 4));
+		}
+		CU(c, cudaSetDevice(c->devs[0].ordinal));
+		CU(c, cudaMemcpy(total.data(), c->devs[0].d_counts, c->n_counts * 4, cudaMemcpyDeviceToHost));
+	} else {
+		std::vector<uint32_t> part(c->n_counts);
+		for (Device &d : c->devs) {
+			CU(c, cudaSetDevice(d.ordinal));
+			CU(c, cudaMemcpy(part.data(), d.d_counts, c->n_counts * 4, cudaMemcpyDeviceToHost));
+			for (size_t j = 0; j < c->n_counts; ++j) total[j] += part[j];
+		}
+	}
+	if (counts) memcpy(counts, total.data(), (size_t)2 * c->n_patterns * 4);
+	if (stats) {
+		c->st.n_candidates = c->st.n_hits = c->st.n_kmers = 0;
+		for (Device &d : c->devs) {
+			unsigned long long s[ST_N];
+			CU(c, cudaSetDevice(d.ordinal));
+			CU(c, cudaMemcpy(s, d.d_stats, sizeof s, cudaMemcpyDeviceToHost));
+			c->st.n_candidates += s[ST_CANDIDATES];
+			c->st.n_hits += s[ST_HITS];
+			c->st.n_kmers += s[ST_KMERS];
+		}
+		*stats = c->st;
+	}
+	return VAFGPU_OK;
+}
+
+int vafgpu_reset(vafgpu_ctx *c)
+{
+	if (!c) return VAFGPU_EINVAL;
+	int rc = vafgpu_finish(c, nullptr, nullptr);
+	if (rc) return rc;
+	for (Device &d : c->devs) {
+		CU(c, cudaSetDevice(d.ordinal));
+		CU(c, cudaMemset(d.d_counts, 0, c->n_counts * 4));
+		CU(c, cudaMemset(d.d_stats, 0, ST_N * sizeof(unsigned long long)));
+	}
+	vafgpu_stats keep = c->st;
+	c->st = vafgpu_stats{};
+	c->st.n_devices = keep.n_devices;
+	c->st.anchor_stride = keep.anchor_stride;
+	c->st.anchor_len = keep.anchor_len;
+	c->st.filter_bytes = keep.filter_bytes;
+	c->st.table_slots = keep.table_slots;
+	return VAFGPU_OK;
+}
+
+void vafgpu_destroy(vafgpu_ctx *c)
+{
+	if (!c) return;
+	for (Device &d : c->devs) {
+		if (d.comm && c->nccl.CommDestroy) c->nccl.CommDestroy(d.comm);
+		destroy_device(d);
+	}
+	delete c;
+}
+
+} // extern "C"

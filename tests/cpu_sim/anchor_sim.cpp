@@ -1,0 +1,111 @@
+/*
+ * anchor_sim.cpp -- TEST-ONLY host emulation of anchor_scan_kernel (vafgpu_kernels.cu).
+ *
+ * Lets the CPU test-suite check the table builder (vafgpu_tables.cpp), the packing
+ * arithmetic and the anchor bookkeeping against the oracle without a GPU.  It is built by
+ * tests/conftest.py into tests/_build/ and is never linked into libvafgpu.so: the product
+ * has no CPU path.
+ */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../kmer-cnt_b200/csrc/vafgpu_tables.hpp"
+
+using namespace vafgpu;
+
+static inline bool is_base(uint32_t b)
+{
+	uint32_t u = b & 0xDFu;
+	return u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'U';
+}
+
+static inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) /* __byte_perm */
+{
+	uint64_t v = (uint64_t)b << 32 | a;
+	uint32_t r = 0;
+	for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> 8 * ((sel >> 4 * i) & 7)) & 0xFF) << 8 * i;
+	return r;
+}
+
+static inline uint32_t pack16(const uint8_t *c)
+{
+	const uint32_t M = 0x00820820u;
+	uint32_t w[4], p[4];
+	memcpy(w, c, 16);
+	for (int i = 0; i < 4; ++i) p[i] = (w[i] & 0x06060606u) * M;
+	uint32_t lo = prmt(p[0], p[1], 0x0073), hi = prmt(p[2], p[3], 0x0073);
+	return prmt(lo, hi, 0x5410);
+}
+
+static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh)
+{
+	sh &= 31;
+	return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+
+extern "C" {
+
+/* counts[val] += occurrences; returns filter survivors.  bytes: stream, n_bytes % 16 == 0 */
+uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uint32_t n,
+                          const uint8_t *bytes, uint64_t n_bytes, uint32_t *counts,
+                          uint32_t *info /* [stride, len, filter_words, slot_bits, entries, filter_keys] */)
+{
+	AnchorTables t;
+	build_anchor_tables(k, keys, vals, n, t);
+	const int S = t.plan.stride, L = t.plan.len;
+	const uint32_t amask = vg_mask32(L), smask = (1u << t.slot_bits) - 1;
+	const uint32_t nw = (uint32_t)t.filter.size();
+	if (info) {
+		info[0] = S, info[1] = L, info[2] = nw, info[3] = t.slot_bits;
+		info[4] = t.n_entries, info[5] = t.n_filter_keys;
+	}
+	uint64_t n_cand = 0;
+	const uint64_t n_chunks = n_bytes / 16;
+	static const uint8_t NL[16] = {10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10};
+	for (uint64_t c = 0; c < n_chunks; ++c) {
+		uint32_t cur = pack16(bytes + 16 * c);
+		uint32_t nxt = pack16(c + 1 < n_chunks ? bytes + 16 * (c + 1) : NL);
+		for (int j = 0; j < 16 / S; ++j) {
+			uint32_t a = (j == 0 ? cur : funnel_r(cur, nxt, 2 * j * S)) & amask;
+			uint32_t h = vg_filter_hash(vg_canon32(a, L));
+			uint32_t m = vg_filter_mask(h);
+			if ((t.filter[vg_filter_word(h, nw)] & m) != m) continue;
+			++n_cand;
+			uint64_t q = 16 * c + (uint64_t)j * S;
+			for (uint32_t s = vg_slot_home(a, t.slot_bits);; s = (s + 1) & smask) {
+				const vg_slot_t &e = t.slots[s];
+				if (e.okey == VG_EMPTY_KEY) break;
+				if (((uint32_t)(e.okey >> 2 * e.off) & amask) != a || q < e.off || q - e.off + k > n_bytes) continue;
+				const uint8_t *b = bytes + (q - e.off);
+				uint64_t km = 0;
+				bool ok = true;
+				for (int i = 0; i < k; ++i) {
+					ok &= is_base(b[i]);
+					km |= (uint64_t)((b[i] >> 1) & 3u) << 2 * i;
+				}
+				if (ok && km == e.okey) ++counts[e.val];
+			}
+		}
+	}
+	return n_cand;
+}
+
+/* recipe-table membership, for checking build_recipe_table against the oracle's map */
+int sim_recipe_get(int k, const uint64_t *keys, const uint32_t *vals, uint32_t n, uint32_t n_patterns,
+                   uint64_t query, uint32_t *bits_out)
+{
+	RecipeTable t;
+	build_recipe_table(k, keys, vals, n, n_patterns, t);
+	if (bits_out) *bits_out = t.bits;
+	const uint32_t mask = (1u << t.bits) - 1;
+	for (uint32_t s = vg_h2b(vg_kmer_hash(query), t.bits);; s = (s + 1) & mask) {
+		if (t.keys[s] == VG_EMPTY_KEY) return -1;
+		if (t.keys[s] == query) return (int)t.vals[s];
+	}
+}
+
+uint32_t sim_pack16(const uint8_t *c) { return pack16(c); }
+uint32_t sim_rc32(uint32_t x, int L) { return vg_rc32(x, L); }
+
+} // extern "C"

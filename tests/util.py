@@ -1,0 +1,256 @@
+"""Shared helpers for the test-suite: ctypes bindings of the oracle (test infrastructure) and of
+the test-only host emulation, seeded synthetic cases, stream packing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "kmer-cnt_b200")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+BUILD_DIR = os.path.join(ROOT, "tests", "_build")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+import vafgpu  # noqa: E402
+
+
+def build_oracle() -> None:
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "liboracle.so", "vaf_oracle", "synth"], check=True)
+
+
+def build_sim() -> str:
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    out = os.path.join(BUILD_DIR, "libanchor_sim.so")
+    srcs = [os.path.join(ROOT, "tests", "cpu_sim", "anchor_sim.cpp"),
+            os.path.join(PKG, "csrc", "vafgpu_tables.cpp")]
+    deps = srcs + [os.path.join(PKG, "csrc", "vafgpu_common.h"), os.path.join(PKG, "csrc", "vafgpu_tables.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out] + srcs, check=True)
+    return out
+
+
+class VoPattern(C.Structure):
+    _fields_ = [("chr", C.c_char * 256), ("start", C.c_int), ("end", C.c_int), ("rsid", C.c_char * 256),
+                ("ref", C.c_char), ("alt", C.c_char), ("ref_kmer", C.c_char * 128), ("alt_kmer", C.c_char * 128),
+                ("ref_count", C.c_uint32), ("alt_count", C.c_uint32)]
+
+
+class VoPatterns(C.Structure):
+    _fields_ = [("n", C.c_int), ("m", C.c_int), ("a", C.POINTER(VoPattern))]
+
+
+class VoMap(C.Structure):
+    _fields_ = [("bits", C.c_uint32), ("count", C.c_uint32), ("used", C.POINTER(C.c_uint32)),
+                ("key", C.POINTER(C.c_uint64)), ("val", C.POINTER(C.c_uint32)), ("n_collisions", C.c_int)]
+
+
+class VoStats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("n_kmers", C.c_uint64)]
+
+
+class Oracle:
+    """liboracle.so: the CPU restatement of the reference path (oracle/vaf_oracle.h)."""
+
+    def __init__(self):
+        build_oracle()
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "liboracle.so"))
+        lib.vo_nt4_strict.argtypes = [C.c_uint8]
+        lib.vo_nt4_nibble.argtypes = [C.c_uint8]
+        lib.vo_encode_kmer.argtypes = [C.c_char_p, C.c_int]
+        lib.vo_encode_kmer.restype = C.c_uint64
+        lib.vo_revcomp.argtypes = [C.c_uint64, C.c_int]
+        lib.vo_revcomp.restype = C.c_uint64
+        lib.vo_canonical.argtypes = [C.c_uint64, C.c_int]
+        lib.vo_canonical.restype = C.c_uint64
+        lib.vo_kmer_hash.argtypes = [C.c_uint64]
+        lib.vo_kmer_hash.restype = C.c_uint32
+        lib.vo_h2b.argtypes = [C.c_uint32, C.c_uint32]
+        lib.vo_h2b.restype = C.c_uint32
+        lib.vo_load_patterns.argtypes = [C.c_char_p]
+        lib.vo_load_patterns.restype = C.POINTER(VoPatterns)
+        lib.vo_patterns_free.argtypes = [C.POINTER(VoPatterns)]
+        lib.vo_map_build.argtypes = [C.POINTER(VoPatterns), C.c_int]
+        lib.vo_map_build.restype = C.POINTER(VoMap)
+        lib.vo_map_free.argtypes = [C.POINTER(VoMap)]
+        lib.vo_map_get.argtypes = [C.POINTER(VoMap), C.c_uint64]
+        lib.vo_map_get.restype = C.c_uint32
+        lib.vo_map_export.argtypes = [C.POINTER(VoMap), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        lib.vo_map_export.restype = C.c_uint32
+        lib.vo_count_read.argtypes = [C.POINTER(VoMap), C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint32)]
+        lib.vo_count_read.restype = C.c_uint64
+        lib.vo_extract_read.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        lib.vo_extract_read.restype = C.c_uint64
+        lib.vo_count_file.argtypes = [C.POINTER(VoMap), C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_uint32), C.POINTER(VoStats)]
+        lib.vo_count_file.restype = C.c_int
+        self.lib = lib
+
+    def extract(self, seq: bytes, k: int, simd: bool = True) -> List[int]:
+        out = (C.c_uint64 * max(len(seq), 1))()
+        n = self.lib.vo_extract_read(k, seq, len(seq), int(simd), out)
+        return [int(out[i]) for i in range(n)]
+
+    def count_reads(self, pattern_file: str, k: int, reads: Sequence[bytes], simd: bool = True) -> Tuple[np.ndarray, int, int]:
+        """(counts[2n], n_kmers, n_collisions) of the reference recipe over `reads` (len >= k only)."""
+        db = self.lib.vo_load_patterns(pattern_file.encode())
+        assert db, pattern_file
+        m = self.lib.vo_map_build(db, k)
+        n = db.contents.n
+        counts = np.zeros(2 * max(n, 1), dtype=np.uint32)
+        cp = counts.ctypes.data_as(C.POINTER(C.c_uint32))
+        nk = 0
+        for r in reads:
+            if len(r) >= k:
+                nk += self.lib.vo_count_read(m, k, r, len(r), int(simd), cp)
+        ncoll = m.contents.n_collisions
+        self.lib.vo_map_free(m)
+        self.lib.vo_patterns_free(db)
+        return counts[: 2 * n], int(nk), int(ncoll)
+
+    def count_file(self, pattern_file: str, k: int, fastx: str, *, simd: bool = True, threads: int = 1,
+                   block_len: int = 10_000_000):
+        db = self.lib.vo_load_patterns(pattern_file.encode())
+        m = self.lib.vo_map_build(db, k)
+        n = db.contents.n
+        counts = np.zeros(2 * max(n, 1), dtype=np.uint32)
+        st = VoStats()
+        rc = self.lib.vo_count_file(m, k, fastx.encode(), int(simd), threads, block_len,
+                                    counts.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st))
+        self.lib.vo_map_free(m)
+        self.lib.vo_patterns_free(db)
+        return rc, counts[: 2 * n], {"n_reads": st.n_reads, "n_bases": st.n_bases, "n_kmers": st.n_kmers}
+
+
+class Sim:
+    """tests/_build/libanchor_sim.so: host emulation of the anchor kernel (test-only)."""
+
+    def __init__(self):
+        lib = C.CDLL(build_sim())
+        lib.sim_anchor_count.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32,
+                                         C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        lib.sim_anchor_count.restype = C.c_uint64
+        lib.sim_recipe_get.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32,
+                                       C.c_uint64, C.POINTER(C.c_uint32)]
+        lib.sim_recipe_get.restype = C.c_int
+        lib.sim_pack16.argtypes = [C.c_char_p]
+        lib.sim_pack16.restype = C.c_uint32
+        lib.sim_rc32.argtypes = [C.c_uint32, C.c_int]
+        lib.sim_rc32.restype = C.c_uint32
+        self.lib = lib
+
+    def count(self, k: int, keys: np.ndarray, vals: np.ndarray, n_patterns: int, stream: np.ndarray):
+        counts = np.zeros(2 * max(n_patterns, 1), dtype=np.uint32)
+        info = (C.c_uint32 * 6)()
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        ncand = self.lib.sim_anchor_count(k, keys.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                          vals.ctypes.data_as(C.POINTER(C.c_uint32)), keys.size,
+                                          stream.ctypes.data, stream.size,
+                                          counts.ctypes.data_as(C.POINTER(C.c_uint32)), info)
+        return counts[: 2 * n_patterns], int(ncand), list(info)
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic cases
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+COMP = np.arange(256, dtype=np.uint8)
+for a, b in zip(b"ACGTacgt", b"TGCAtgca"):
+    COMP[a] = b
+JUNK = np.frombuffer(b"RYKMSWBDHVacgtnUu.-*XQ1357 \x00\x01\x02\x03", dtype=np.uint8)
+
+
+def revcomp(b: bytes) -> bytes:
+    return COMP[np.frombuffer(b, dtype=np.uint8)][::-1].tobytes()
+
+
+def make_patterns(rng: np.random.Generator, n: int, k: int, *, dup_every: int = 0, bad_every: int = 0):
+    """n pattern rows with random k-mers; alt differs from ref at the centre base."""
+    pats = []
+    for i in range(n):
+        ref = ACGT[rng.integers(0, 4, k)].copy()
+        alt = ref.copy()
+        mid = k // 2
+        alt[mid] = ACGT[(int(np.where(ACGT == ref[mid])[0][0]) + int(rng.integers(1, 4))) % 4]
+        if dup_every and i and i % dup_every == 0:  # same position under two ids: identical k-mers
+            ref = np.frombuffer(pats[-1].ref_kmer.encode(), dtype=np.uint8).copy()
+        alt_s = alt.tobytes().decode()
+        if bad_every and i % bad_every == 3:
+            alt_s = alt_s[:2] + "N" + alt_s[3:]  # unusable k-mer: never inserted
+        pats.append(vafgpu.Pattern("chr%d" % (1 + i % 22), 1000 + 7 * i, 1001 + 7 * i, "rs%d" % i,
+                                   chr(ref[mid]), chr(alt[mid]), ref.tobytes().decode(), alt_s))
+    return pats
+
+
+def write_patterns(path: str, pats) -> None:
+    with open(path, "w") as fh:
+        for p in pats:
+            fh.write("%s\t%d\t%d\t%s\t%s\t%s\t%s\t%s\n" % (p.chr, p.start, p.end, p.rsid, p.ref, p.alt, p.ref_kmer, p.alt_kmer))
+
+
+def make_reads(rng: np.random.Generator, pats, k: int, n_reads: int, *, mean_len: int = 150, jitter: int = 0,
+               plant: float = 0.5, n_rate: float = 0.005, junk_rate: float = 0.0, lower_rate: float = 0.0) -> List[bytes]:
+    """Random reads; a fraction carries a pattern k-mer (either allele, either strand) at a
+    random offset, possibly clipped by the read end or broken by an N."""
+    reads = []
+    for _ in range(n_reads):
+        ln = mean_len + (int(rng.integers(-jitter, jitter + 1)) if jitter else 0)
+        ln = max(ln, 0)
+        s = ACGT[rng.integers(0, 4, ln)].copy()
+        if pats and ln and rng.random() < plant:
+            for _ in range(int(rng.integers(1, 3))):
+                p = pats[int(rng.integers(0, len(pats)))]
+                km = (p.alt_kmer if rng.random() < 0.5 else p.ref_kmer).encode()
+                if b"N" in km:
+                    continue
+                if rng.random() < 0.5:
+                    km = revcomp(km)
+                at = int(rng.integers(-k // 2, ln))
+                lo, hi = max(at, 0), min(at + k, ln)
+                if hi > lo:
+                    s[lo:hi] = np.frombuffer(km, dtype=np.uint8)[lo - at:hi - at]
+        if n_rate:
+            s[rng.random(ln) < n_rate] = ord("N")
+        if junk_rate:
+            m = rng.random(ln) < junk_rate
+            s[m] = JUNK[rng.integers(0, len(JUNK), int(m.sum()))]
+        if lower_rate:
+            m = rng.random(ln) < lower_rate
+            s[m] = s[m] | 0x20
+        reads.append(s.tobytes())
+    return reads
+
+
+def pack_stream(reads: Sequence[bytes], k: int, simd_rule: bool = True) -> np.ndarray:
+    """What vafgpu_add_read builds in a staging block: canonicalised reads, '\\n' separated,
+    padded with '\\n' to a multiple of 16."""
+    parts = []
+    for r in reads:
+        if len(r) >= k:
+            parts.append(vafgpu.canonicalise_read(r, simd_rule))
+            parts.append(b"\n")
+    buf = b"".join(parts)
+    buf += b"\n" * (-len(buf) % 16)
+    return np.frombuffer(buf, dtype=np.uint8).copy()
+
+
+def write_fastq(path: str, reads: Sequence[bytes], *, fasta: bool = False, line: int = 0) -> None:
+    with open(path, "wb") as fh:
+        for i, r in enumerate(reads):
+            if fasta:
+                fh.write(b">r%d\n" % i)
+                if line:
+                    for j in range(0, len(r), line):
+                        fh.write(r[j:j + line] + b"\n")
+                else:
+                    fh.write(r + b"\n")
+            else:
+                fh.write(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)))

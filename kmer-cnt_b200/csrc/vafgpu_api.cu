@@ -40,6 +40,7 @@ struct Device {
 	int ordinal = 0;
 	int n_sm = 0;
 	uint32_t *d_filter = nullptr;
+	uint32_t *d_tags = nullptr;
 	vg_slot_t *d_slots = nullptr;
 	uint64_t *d_rkeys = nullptr;
 	uint32_t *d_rvals = nullptr;
@@ -70,7 +71,8 @@ struct vafgpu_ctx {
 	size_t n_counts = 0; /* 2 * n_patterns, at least 2 */
 	size_t block_bytes = 0;
 	Plan plan;
-	uint32_t filter_words = 0, slot_bits = 0, rbits = 0;
+	uint32_t filter_words = 0, bucket_bits = 0, rbits = 0;
+	bool canon = false;
 	std::vector<Device> devs;
 	Nccl nccl;
 	/* producer state */
@@ -161,10 +163,12 @@ ScanArgs scan_args(const vafgpu_ctx *c, const Device &d, const uint8_t *bytes, s
 	a.k = c->k;
 	a.stride = c->plan.stride;
 	a.len = c->plan.len;
+	a.canon = c->canon ? 1 : 0;
 	a.filter = d.d_filter;
 	a.filter_words = c->filter_words;
+	a.tags = d.d_tags;
 	a.slots = d.d_slots;
-	a.slot_bits = c->slot_bits;
+	a.bucket_bits = c->bucket_bits;
 	a.rkeys = d.d_rkeys;
 	a.rvals = d.d_rvals;
 	a.rbits = c->rbits;
@@ -244,6 +248,7 @@ void destroy_device(Device &d)
 	}
 	if (d.main_stream) cudaStreamDestroy(d.main_stream);
 	cudaFree(d.d_filter);
+	cudaFree(d.d_tags);
 	cudaFree(d.d_slots);
 	cudaFree(d.d_rkeys);
 	cudaFree(d.d_rvals);
@@ -316,7 +321,8 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	build_anchor_tables(k, keys, vals, n_entries, at);
 	c->plan = at.plan;
 	c->filter_words = (uint32_t)at.filter.size();
-	c->slot_bits = at.slot_bits;
+	c->bucket_bits = at.bucket_bits;
+	c->canon = at.canon;
 	c->rbits = rt.bits;
 
 	int rc = VAFGPU_OK;
@@ -334,12 +340,14 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			CU(c, kernels_init_device(d.n_sm));
 			CU(c, cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
 			CU(c, cudaMalloc(&d.d_filter, at.filter.size() * 4));
+			CU(c, cudaMalloc(&d.d_tags, at.tags.size() * 4));
 			CU(c, cudaMalloc(&d.d_slots, at.slots.size() * sizeof(vg_slot_t)));
 			CU(c, cudaMalloc(&d.d_rkeys, rt.keys.size() * 8));
 			CU(c, cudaMalloc(&d.d_rvals, rt.vals.size() * 4));
 			CU(c, cudaMalloc(&d.d_counts, c->n_counts * 4));
 			CU(c, cudaMalloc(&d.d_stats, ST_N * sizeof(unsigned long long)));
 			CU(c, cudaMemcpy(d.d_filter, at.filter.data(), at.filter.size() * 4, cudaMemcpyHostToDevice));
+			CU(c, cudaMemcpy(d.d_tags, at.tags.data(), at.tags.size() * 4, cudaMemcpyHostToDevice));
 			CU(c, cudaMemcpy(d.d_slots, at.slots.data(), at.slots.size() * sizeof(vg_slot_t), cudaMemcpyHostToDevice));
 			CU(c, cudaMemcpy(d.d_rkeys, rt.keys.data(), rt.keys.size() * 8, cudaMemcpyHostToDevice));
 			CU(c, cudaMemcpy(d.d_rvals, rt.vals.data(), rt.vals.size() * 4, cudaMemcpyHostToDevice));
@@ -377,7 +385,7 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	c->st.anchor_stride = c->plan.stride;
 	c->st.anchor_len = c->plan.len;
 	c->st.filter_bytes = c->filter_words * 4;
-	c->st.table_slots = 1u << c->slot_bits;
+	c->st.table_slots = 4u << c->bucket_bits;
 	*out = c;
 	return VAFGPU_OK;
 }

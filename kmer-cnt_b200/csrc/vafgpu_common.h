@@ -21,8 +21,15 @@
 #endif
 
 #define VG_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-#define VG_MAX_FILTER_WORDS 57344u /* 224 KiB of shared memory */
+#define VG_SMEM_BUDGET (227 * 1024) /* dynamic shared memory per CTA on sm_100: filter + candidate queues */
 #define VG_MIN_FILTER_WORDS 1024u
+
+/* launch geometry of the anchor kernel for stride S, shared with the table builder because
+ * the candidate queues and the filter split one shared-memory budget */
+#define VG_THREADS(S) ((S) >= 4 ? 1024 : 256)              /* tiny k: fewer warps, deeper queues   */
+#define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)))         /* per warp: a drain's leftovers + one tile */
+#define VG_QUEUE_BYTES(S) ((VG_THREADS(S) / 32) * VG_QUEUE_ENTRIES(S) * 8)
+#define VG_FILTER_BUDGET_WORDS(S) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S) - 4 * 992) / 4) & ~3))
 
 /* exact-table slot: an oriented pattern k-mer (stream encoding) with the offset of the
  * anchor it is filed under.  16 bytes so one LDG.128 fetches it. */
@@ -67,28 +74,44 @@ VG_HD uint32_t vg_rc32(uint32_t x, int L)
 	return r >> (32 - 2 * L); /* the L bases sit at the top after reversal */
 }
 
-VG_HD uint32_t vg_canon32(uint32_t x, int L)
-{
-	uint32_t r = vg_rc32(x, L);
-	return x < r ? x : r;
-}
+/* Filter key of an anchor.  Large panels (canon) use a function that is the same for an
+ * anchor and its reverse complement, so one filter entry serves both strands: the product
+ * a * rc(a) mod 2^32 -- symmetric like min(a, rc(a)) but a multiply (FMA pipe) instead of a
+ * compare-select (the integer ALU pipe is the scarce resource of the kernel). */
+VG_HD uint32_t vg_filter_key(uint32_t a, int L, int canon) { return canon ? a * vg_rc32(a, L) : a; }
 
-/* filter: word index and the two probe bits from one multiplicative hash */
-VG_HD uint32_t vg_filter_hash(uint32_t canon_anchor) { return canon_anchor * 0x9E3779B1u; }
-VG_HD uint32_t vg_filter_word(uint32_t h, uint32_t n_words)
+/* Blocked Bloom filter: one 32-bit word per key, two distinct bits in it.  The word comes
+ * from the top of one multiplicative hash, the bit pair from the top of a second one via a
+ * 992-entry table of all ordered pairs of distinct positions (shared memory on the device:
+ * a table look-up costs no ALU slot, building the mask with shifts costs five). */
+#define VG_MASKTAB 992u
+VG_HD uint32_t vg_hash1(uint32_t key) { return key * 0x9E3779B1u; }
+VG_HD uint32_t vg_hash2(uint32_t key) { return key * 0x85EBCA6Bu; }
+VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)
-	return __umulhi(h, n_words);
+	return __umulhi(a, b);
 #else
-	return (uint32_t)(((uint64_t)h * n_words) >> 32);
+	return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-VG_HD uint32_t vg_filter_mask(uint32_t h) { return (1u << ((h >> 5) & 31)) | (1u << ((h >> 10) & 31)); }
-
-/* exact table: home slot of a forward anchor */
-VG_HD uint32_t vg_slot_home(uint32_t anchor, uint32_t slot_bits)
+VG_HD uint32_t vg_filter_word(uint32_t key, uint32_t n_words) { return vg_mulhi(vg_hash1(key), n_words); }
+VG_HD uint32_t vg_mask_index(uint32_t key) { return vg_mulhi(vg_hash2(key), VG_MASKTAB); }
+VG_HD uint32_t vg_mask_entry(uint32_t i) /* i < VG_MASKTAB */
 {
-	return (anchor * 0xCC9E2D51u) >> (32 - slot_bits);
+	uint32_t b1 = i / 31u, d = i % 31u;
+	return (1u << b1) | (1u << ((b1 + 1u + d) & 31u));
+}
+
+/* exact table: buckets of four 32-bit tags (one LDG.128) with the 16-byte payloads in a
+ * parallel array that is only touched when a tag matches.  Tag 0 marks a free slot; a slot
+ * is filled at the first free position scanning on from the home bucket, so a lookup stops
+ * at the first free slot it meets.  The tag keeps the low 31 bits of the forward anchor
+ * (all of it for L <= 15); the payload decides. */
+VG_HD uint32_t vg_tag(uint32_t anchor) { return anchor | 0x80000000u; }
+VG_HD uint32_t vg_bucket_home(uint32_t anchor, uint32_t bucket_bits)
+{
+	return (anchor * 0xCC9E2D51u) >> (32 - bucket_bits);
 }
 
 #endif

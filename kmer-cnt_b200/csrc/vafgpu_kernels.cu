@@ -59,11 +59,23 @@ __device__ __forceinline__ uint32_t pack16(uint4 w)
 /* ------------------------------------------------------------------------------------ */
 /* anchor-filter kernel                                                                   */
 
+/* Per-warp candidate queue in shared memory: survivors of the filter are compacted into it
+ * and resolved 32 at a time, one per lane, so that the L2 round trips of the exact table
+ * are taken by full warps and off the streaming loop.  It must absorb everything one tile
+ * can produce on top of the < 32 entries left by the last drain. */
+template <int S> struct Launch {
+	static constexpr int kThreads = VG_THREADS(S);
+	static constexpr int kQueue = VG_QUEUE_ENTRIES(S);
+	static constexpr int kQueueBytes = VG_QUEUE_BYTES(S);
+};
+
 struct AnchorParams {
-	const uint4 *chunks;   /* stream as 16-byte chunks */
-	const uint8_t *bytes;
-	uint64_t n_bytes;
-	uint32_t n_chunks;
+	const uint4 *chunks;   /* the launch's range of the stream as 16-byte chunks        */
+	const uint8_t *bytes;  /* the whole stream (candidate verification may look outside
+	                          the range: a k-mer may start up to S-1 bases before it)    */
+	uint64_t n_bytes;      /* length of the whole stream                                */
+	uint64_t range_lo;     /* byte offset of chunks[0] in the stream                    */
+	uint32_t n_chunks;     /* chunks in the range, < 2^28                               */
 	uint32_t n_tiles;      /* 32 chunks each */
 	uint32_t tiles_per_span;
 	uint32_t n_spans;
@@ -71,104 +83,186 @@ struct AnchorParams {
 	unsigned long long *stats;
 	const uint32_t *filter;
 	uint32_t filter_words;
+	const uint4 *tags;     /* buckets of four tags */
 	const vg_slot_t *slots;
-	uint32_t slot_bits;
+	uint32_t bucket_bits;
 	int k, len;
 };
 
-__device__ __forceinline__ uint4 load_chunk(const AnchorParams &p, uint32_t chunk, bool want)
+__device__ __forceinline__ void l2_prefetch(const void *ptr)
 {
-	if (want && chunk < p.n_chunks) return __ldcs(p.chunks + chunk); /* streaming: evict first */
-	return make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+	asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
-/* survivors of the filter: walk the exact table from the anchor's home slot; every slot
- * filed under this anchor names an oriented pattern k-mer and where the anchor sits in it */
-__device__ __noinline__ void resolve_candidate(const AnchorParams &p, uint32_t anchor, uint32_t amask,
-                                               uint64_t q, uint32_t &n_hits)
+/* the k raw bytes at q - off against one oriented pattern k-mer */
+__device__ __noinline__ uint32_t verify_slot(const AnchorParams &p, uint32_t slot, uint32_t anchor, uint32_t amask, uint64_t q)
 {
-	const uint32_t smask = (1u << p.slot_bits) - 1u;
-	uint32_t s = vg_slot_home(anchor, p.slot_bits);
-	for (;;) {
-		uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.slots) + s);
-		uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
-		if (okey == VG_EMPTY_KEY) return;
-		uint32_t val = raw.z, off = raw.w;
-		if (((uint32_t)(okey >> 2 * off) & amask) == anchor && q >= off && q - off + p.k <= p.n_bytes) {
-			/* compare the k raw bytes at q - off with the oriented key */
-			const uint8_t *b = p.bytes + (q - off);
-			uint64_t km = 0;
-			bool ok = true;
-			for (int i = 0; i < p.k; ++i) {
-				uint32_t c = b[i];
-				ok &= is_base(c);
-				km |= (uint64_t)((c >> 1) & 3u) << 2 * i;
+	uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.slots) + slot);
+	uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
+	uint32_t val = raw.z, off = raw.w;
+	if (((uint32_t)(okey >> 2 * off) & amask) != anchor || q < off || q - off + p.k > p.n_bytes) return 0;
+	const uint8_t *b = p.bytes + (q - off);
+	uint64_t km = 0;
+	bool ok = true;
+	for (int i = 0; i < p.k; ++i) {
+		uint32_t c = b[i];
+		ok &= is_base(c);
+		km |= (uint64_t)((c >> 1) & 3u) << 2 * i;
+	}
+	if (!ok || km != okey) return 0;
+	bump(p.counts, val);
+	return 1;
+}
+
+/* Resolve 32 (or the last n < 32) queued survivors of the filter, one per lane: fetch the
+ * anchor's home bucket (four tags, one 16-byte load from L2); a free slot ends the search,
+ * a matching tag sends the lane to the payload and the raw bytes. */
+template <int S>
+__device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uint2 *wq, uint32_t first, uint32_t n,
+                                                uint32_t amask)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t hits = 0;
+	if (lane < n) {
+		const uint2 e = wq[first + lane];
+		const uint32_t anchor = e.x, tag = vg_tag(anchor), bmask = (1u << p.bucket_bits) - 1u;
+		const uint64_t q = p.range_lo + (uint64_t)e.y * (uint32_t)S;
+		for (uint32_t b = vg_bucket_home(anchor, p.bucket_bits);; b = (b + 1) & bmask) {
+			const uint4 t = __ldg(p.tags + b);
+			if (t.x == tag) hits += verify_slot(p, b * 4 + 0, anchor, amask, q);
+			if (t.x == 0) break;
+			if (t.y == tag) hits += verify_slot(p, b * 4 + 1, anchor, amask, q);
+			if (t.y == 0) break;
+			if (t.z == tag) hits += verify_slot(p, b * 4 + 2, anchor, amask, q);
+			if (t.z == 0) break;
+			if (t.w == tag) hits += verify_slot(p, b * 4 + 3, anchor, amask, q);
+			if (t.w == 0) break;
+		}
+	}
+	return hits;
+}
+
+/* state a warp carries through the stream */
+struct Pipe {
+	uint32_t t;        /* next tile to scan                                       */
+	uint32_t c;        /* this lane's chunk in it                                 */
+	const uint4 *ptr;  /* its address                                             */
+	uint32_t cur;      /* that chunk, packed                                      */
+	uint4 w1, w2;      /* raw chunks of tiles t+1 (arrived) and t+2 (in flight)   */
+	uint32_t qn;       /* entries in the candidate queue                          */
+};
+
+/* The hot loop: scan tiles until the span ends or 32 candidates are queued.  No calls, no
+ * table walks; per tile and lane one 16-byte load, one pack, 16/S filter probes.
+ * INTERIOR: every address touched (loads up to tile t1+1, prefetch 8 tiles ahead) is
+ * inside the range, so nothing is clamped or predicated. */
+template <int S, bool CANON, bool INTERIOR>
+__device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, const uint32_t *filter,
+                                           const uint32_t *masktab, uint2 *wq, uint32_t lane, uint32_t amask)
+{
+	const uint32_t nw = p.filter_words, last = p.n_chunks - 1;
+	const int rc_shift = 32 - 2 * p.len;
+	while (s.t < t1) {
+		if (INTERIOR) l2_prefetch(reinterpret_cast<const uint8_t *>(s.ptr) + 4096); /* this lane's chunk, 8 tiles on */
+		const uint32_t nx = pack16(s.w1);
+		uint32_t right = 0;
+		if (S < 16) { /* an anchor may run into the next chunk: lane+1's, or lane 0's of the next tile */
+			right = __shfl_down_sync(FULL, s.cur, 1);
+			const uint32_t head = __shfl_sync(FULL, nx, 0);
+			if (lane == 31) right = head;
+		}
+#pragma unroll
+		for (int j = 0; j < 16 / S; ++j) {
+			const uint32_t a = (j == 0 ? s.cur : __funnelshift_r(s.cur, right, 2 * j * S)) & amask;
+			uint32_t key = a;
+			if (CANON) { /* a * rc(a): vg_rc32 with the shift hoisted */
+				uint32_t r = __brev(a);
+				r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+				key = a * ((r ^ 0xAAAAAAAAu) >> rc_shift);
 			}
-			if (ok && km == okey) {
-				bump(p.counts, val);
-				++n_hits;
+			const uint32_t word = filter[vg_filter_word(key, nw)];
+			const uint32_t m = masktab[vg_mask_index(key)];
+			bool hit = (~word & m) == 0;
+			if (!INTERIOR) hit = hit && s.c <= last;
+			if (__any_sync(FULL, hit)) { /* queue the survivors, compacted */
+				const uint32_t votes = __ballot_sync(FULL, hit);
+				if (hit) wq[s.qn + __popc(votes & ((1u << lane) - 1u))] = make_uint2(a, s.c * (16 / S) + j);
+				s.qn += __popc(votes);
 			}
 		}
-		s = (s + 1) & smask;
+		s.cur = nx;
+		s.w1 = s.w2;
+		s.w2 = INTERIOR ? __ldcs(s.ptr + 96) : __ldcs(p.chunks + min(s.c + 96, last));
+		++s.t;
+		s.c += 32;
+		s.ptr += 32;
+		if (s.qn >= 32) break;
 	}
 }
 
-template <int S>
-__global__ void __launch_bounds__(1024, 1) anchor_scan_kernel(const __grid_constant__ AnchorParams p)
+/* The streaming kernel.  One CTA per SM, persistent over spans of tiles (a tile = 32 chunks
+ * of 16 bytes = one 128-bit load per lane).
+ *   CANON  the filter holds strand-symmetric keys, which halves its load for large panels;
+ *          small panels file both orientations and skip the reverse complement. */
+template <int S, bool CANON>
+__global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(const __grid_constant__ AnchorParams p)
 {
 	extern __shared__ uint32_t s_filter[];
-	{ /* stage the filter */
+	const uint32_t nw = p.filter_words;
+	uint32_t *const s_masktab = s_filter + nw;
+	{ /* stage the filter and build the bit-pair table */
 		const uint4 *src = reinterpret_cast<const uint4 *>(p.filter);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
-		for (uint32_t i = threadIdx.x; i < p.filter_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+		for (uint32_t i = threadIdx.x; i < nw / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+		for (uint32_t i = threadIdx.x; i < VG_MASKTAB; i += blockDim.x) s_masktab[i] = vg_mask_entry(i);
 	}
 	__syncthreads();
 
 	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t amask = vg_mask32(p.len);
+	uint2 *const wq = reinterpret_cast<uint2 *>(s_masktab + VG_MASKTAB) + (threadIdx.x >> 5) * Launch<S>::kQueue;
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
 	const uint32_t n_warps = gridDim.x * warps_per_cta;
-	const uint32_t amask = vg_mask32(p.len);
-	const uint32_t nw = p.filter_words;
+	const uint32_t last = p.n_chunks - 1;
 	uint32_t n_cand = 0, n_hits = 0;
+	Pipe s;
+	s.qn = 0;
 
 	for (uint32_t span = warp; span < p.n_spans; span += n_warps) {
-		const uint32_t t0 = span * p.tiles_per_span;
-		const uint32_t t1 = min(t0 + p.tiles_per_span, p.n_tiles);
-		/* software pipeline: tile t is processed while t+1 is decoded and t+2 is in flight.
-		 * The tile after the span is only needed for its first chunk (lane 0). */
-		uint4 w_next = load_chunk(p, (t0 + 1) * 32 + lane, t0 + 1 < t1 || lane == 0);
-		uint32_t cur = pack16(load_chunk(p, t0 * 32 + lane, true));
-		for (uint32_t t = t0; t < t1; ++t) {
-			uint4 w_after = load_chunk(p, (t + 2) * 32 + lane, t + 2 < t1 || (t + 2 == t1 && lane == 0));
-			uint32_t nxt_tile = pack16(w_next);
-			uint32_t nxt = 0;
-			if (S < 16) { /* the anchor at offset 16 - S may run into the next chunk */
-				nxt = __shfl_down_sync(FULL, cur, 1);
-				uint32_t head = __shfl_sync(FULL, nxt_tile, 0);
-				if (lane == 31) nxt = head;
+		s.t = span * p.tiles_per_span;
+		const uint32_t t1 = min(s.t + p.tiles_per_span, p.n_tiles);
+		/* Interior span: everything the pipeline touches lies inside the range.  Otherwise
+		 * loads are clamped to the last chunk: a chunk past the end is never scanned, and as
+		 * a right neighbour it can only create a false candidate, which the bounds check of
+		 * the verification rejects. */
+		const bool interior = (uint64_t)(t1 + 8) * 32 <= p.n_chunks;
+		s.c = s.t * 32 + lane;
+		s.ptr = p.chunks + s.c;
+		if (interior) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * 128); /* 4 KiB */
+		/* register pipeline: tile t is scanned while t+1 is being packed and t+2 is in flight;
+		 * the L2 prefetch runs 8 tiles ahead of that */
+		s.cur = pack16(__ldcs(p.chunks + min(s.c, last)));
+		s.w1 = __ldcs(p.chunks + min(s.c + 32, last));
+		s.w2 = __ldcs(p.chunks + min(s.c + 64, last));
+		for (;;) {
+			if (interior) scan_tiles<S, CANON, true>(p, s, t1, s_filter, s_masktab, wq, lane, amask);
+			else scan_tiles<S, CANON, false>(p, s, t1, s_filter, s_masktab, wq, lane, amask);
+			__syncwarp();
+			while (s.qn >= 32) {
+				s.qn -= 32;
+				n_cand += 32;
+				n_hits += drain_queue<S>(p, wq, s.qn, 32, amask);
 			}
-			const uint64_t q0 = (uint64_t)(t * 32 + lane) * 16;
-#pragma unroll
-			for (int j = 0; j < 16 / S; ++j) {
-				uint32_t a = (j == 0 ? cur : __funnelshift_r(cur, nxt, 2 * j * S)) & amask;
-				uint32_t h = vg_filter_hash(vg_canon32(a, p.len));
-				uint32_t word = s_filter[vg_filter_word(h, nw)];
-				uint32_t m = vg_filter_mask(h);
-				if ((word & m) == m) {
-					++n_cand;
-					resolve_candidate(p, a, amask, q0 + j * S, n_hits);
-				}
-			}
-			cur = nxt_tile;
-			w_next = w_after;
+			__syncwarp();
+			if (s.t >= t1) break;
 		}
 	}
-	/* statistics: one atomic per warp */
-	for (int o = 16; o; o >>= 1) {
-		n_cand += __shfl_xor_sync(FULL, n_cand, o);
-		n_hits += __shfl_xor_sync(FULL, n_hits, o);
+	if (s.qn) {
+		n_cand += s.qn;
+		n_hits += drain_queue<S>(p, wq, 0, s.qn, amask);
 	}
+	for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(FULL, n_hits, o);
 	if (lane == 0 && (n_cand | n_hits)) {
 		atomicAdd(&p.stats[ST_CANDIDATES], (unsigned long long)n_cand);
 		atomicAdd(&p.stats[ST_HITS], (unsigned long long)n_hits);
@@ -237,55 +331,71 @@ __global__ void __launch_bounds__(256) recipe_scan_kernel(const ScanArgs a)
 /* ------------------------------------------------------------------------------------ */
 /* launchers                                                                              */
 
-static const int kMaxDynSmem = VG_MAX_FILTER_WORDS * 4;
-
-cudaError_t kernels_init_device(int)
+template <int S, bool CANON>
+static cudaError_t launch_one(const AnchorParams &p0, uint32_t filter_words, int n_sm, cudaStream_t stream)
 {
-	cudaError_t e;
-#define OPT_IN(S)                                                                                   \
-	e = cudaFuncSetAttribute(anchor_scan_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-	                         kMaxDynSmem);                                                         \
-	if (e != cudaSuccess) return e;
-	OPT_IN(1) OPT_IN(2) OPT_IN(4) OPT_IN(8) OPT_IN(16)
-#undef OPT_IN
-	return cudaSuccess;
-}
-
-cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream)
-{
-	if (a.n_bytes == 0) return cudaSuccess;
-	if (a.n_bytes / 16 > 0xFFFFFF00ull) return cudaErrorInvalidValue; /* chunk index is 32-bit */
-	AnchorParams p;
-	p.chunks = reinterpret_cast<const uint4 *>(a.bytes);
-	p.bytes = a.bytes;
-	p.n_bytes = a.n_bytes;
-	p.n_chunks = (uint32_t)(a.n_bytes / 16);
-	p.n_tiles = (p.n_chunks + 31) / 32;
-	const int threads = 1024;
+	AnchorParams p = p0;
+	const int threads = Launch<S>::kThreads;
+	const size_t smem = (size_t)filter_words * 4 + VG_MASKTAB * 4 + Launch<S>::kQueueBytes;
+	static bool opted_in[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 64 && !opted_in[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(anchor_scan_kernel<S, CANON>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                     VG_SMEM_BUDGET);
+		if (e != cudaSuccess) return e;
+		opted_in[dev] = true;
+	}
 	const uint32_t resident_warps = (uint32_t)n_sm * (threads / 32);
 	uint32_t tps = p.n_tiles / (resident_warps * 4u);
 	p.tiles_per_span = tps < 1 ? 1 : (tps > 64 ? 64 : tps);
 	p.n_spans = (p.n_tiles + p.tiles_per_span - 1) / p.tiles_per_span;
-	p.counts = a.counts;
-	p.stats = a.stats;
-	p.filter = a.filter;
-	p.filter_words = a.filter_words;
-	p.slots = a.slots;
-	p.slot_bits = a.slot_bits;
-	p.k = a.k;
-	p.len = a.len;
 	uint32_t ctas = (p.n_spans + (threads / 32) - 1) / (threads / 32);
 	if (ctas > (uint32_t)n_sm) ctas = (uint32_t)n_sm;
-	const size_t smem = (size_t)a.filter_words * 4;
-	switch (a.stride) {
-	case 1: anchor_scan_kernel<1><<<ctas, threads, smem, stream>>>(p); break;
-	case 2: anchor_scan_kernel<2><<<ctas, threads, smem, stream>>>(p); break;
-	case 4: anchor_scan_kernel<4><<<ctas, threads, smem, stream>>>(p); break;
-	case 8: anchor_scan_kernel<8><<<ctas, threads, smem, stream>>>(p); break;
-	case 16: anchor_scan_kernel<16><<<ctas, threads, smem, stream>>>(p); break;
-	default: return cudaErrorInvalidValue;
-	}
+	anchor_scan_kernel<S, CANON><<<ctas, threads, smem, stream>>>(p);
 	return cudaGetLastError();
+}
+
+cudaError_t kernels_init_device(int) { return cudaSuccess; }
+
+cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream)
+{
+	/* queue entries carry a 32-bit anchor index within the launch: cut the stream into
+	 * ranges of at most 2 GiB; verification still sees the whole stream */
+	const uint64_t kRange = 1ull << 31;
+	for (uint64_t lo = 0; lo < a.n_bytes; lo += kRange) {
+		const uint64_t n = a.n_bytes - lo < kRange ? a.n_bytes - lo : kRange;
+		AnchorParams p;
+		p.chunks = reinterpret_cast<const uint4 *>(a.bytes + lo);
+		p.bytes = a.bytes;
+		p.n_bytes = a.n_bytes;
+		p.range_lo = lo;
+		p.n_chunks = (uint32_t)(n / 16);
+		p.n_tiles = (p.n_chunks + 31) / 32;
+		p.tiles_per_span = p.n_spans = 0;
+		p.counts = a.counts;
+		p.stats = a.stats;
+		p.filter = a.filter;
+		p.filter_words = a.filter_words;
+		p.tags = reinterpret_cast<const uint4 *>(a.tags);
+		p.slots = a.slots;
+		p.bucket_bits = a.bucket_bits;
+		p.k = a.k;
+		p.len = a.len;
+		cudaError_t e;
+#define GO(S) e = a.canon ? launch_one<S, true>(p, a.filter_words, n_sm, stream) : launch_one<S, false>(p, a.filter_words, n_sm, stream)
+		switch (a.stride) {
+		case 1: GO(1); break;
+		case 2: GO(2); break;
+		case 4: GO(4); break;
+		case 8: GO(8); break;
+		case 16: GO(16); break;
+		default: return cudaErrorInvalidValue;
+		}
+#undef GO
+		if (e != cudaSuccess) return e;
+	}
+	return cudaSuccess;
 }
 
 cudaError_t launch_recipe_scan(const ScanArgs &a, int, cudaStream_t stream)

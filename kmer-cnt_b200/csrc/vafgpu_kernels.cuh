@@ -22,10 +22,12 @@ struct ScanArgs {
 	int k;
 	/* anchor-filter kernel */
 	int stride, len;
+	int canon;             /* the filter holds canonical anchors */
 	const uint32_t *filter;
 	uint32_t filter_words;
+	const uint32_t *tags;
 	const vg_slot_t *slots;
-	uint32_t slot_bits;
+	uint32_t bucket_bits;
 	/* recipe kernel */
 	const uint64_t *rkeys;
 	const uint32_t *rvals;

@@ -86,7 +86,7 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	struct Item { uint64_t okey; uint32_t val, off, anchor; };
 	std::vector<Item> items;
 	std::unordered_set<uint64_t> seen;
-	std::unordered_set<uint32_t> canon;
+	std::unordered_set<uint32_t> canon, plain; /* filter keys with / without strand folding */
 	items.reserve((size_t)n * 2 * S);
 	for (uint32_t i = 0; i < n; ++i) {
 		if (!seen.insert(keys[i]).second) continue; /* first insert wins */
@@ -97,33 +97,38 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 			for (int o = 0; o < S; ++o) {
 				uint32_t a = (uint32_t)(ok >> 2 * o) & amask;
 				items.push_back({ok, vals[i], (uint32_t)o, a});
-				canon.insert(vg_canon32(a, L));
+				canon.insert(vg_filter_key(a, L, 1));
+				plain.insert(a);
 			}
 		}
 	}
 	out.n_entries = (uint32_t)items.size();
-	out.n_filter_keys = (uint32_t)canon.size();
 
-	/* filter: 64 bits per distinct anchor if shared memory allows, two bits set per anchor */
+	/* Filter: two bits per key in one 32-bit word.  A panel small enough to get >= 64 bits
+	 * per key with both orientations filed keeps them (the kernel then hashes the forward
+	 * anchor as it is); a large panel files strand-symmetric keys, halving the load of the
+	 * filter at the price of a reverse complement per anchor in the kernel. */
+	const uint32_t budget = VG_FILTER_BUDGET_WORDS(S);
+	out.canon = (uint64_t)plain.size() * 24 > (uint64_t)budget * 32; /* < 24 bits per key */
+	const std::unordered_set<uint32_t> &fkeys = out.canon ? canon : plain;
+	out.n_filter_keys = (uint32_t)fkeys.size();
 	uint64_t want = (uint64_t)out.n_filter_keys * 2;
-	uint32_t nw = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, VG_MIN_FILTER_WORDS),
-	                                           VG_MAX_FILTER_WORDS);
+	uint32_t nw = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, VG_MIN_FILTER_WORDS), budget);
 	nw = (nw + 3u) & ~3u;
 	out.filter.assign(nw, 0);
-	for (uint32_t c : canon) {
-		uint32_t h = vg_filter_hash(c);
-		out.filter[vg_filter_word(h, nw)] |= vg_filter_mask(h);
-	}
+	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_mask_entry(vg_mask_index(key));
 
-	/* exact table at <= 50 % load */
-	uint32_t bits = 4;
-	while ((1ull << bits) < (uint64_t)items.size() * 2) ++bits;
-	out.slot_bits = bits;
-	out.slots.assign((size_t)1 << bits, vg_slot_t{VG_EMPTY_KEY, 0, 0});
-	const uint32_t smask = (1u << bits) - 1;
+	/* exact table at <= 1/3 load, buckets of four slots */
+	uint32_t bits = 2;
+	while ((4ull << bits) < (uint64_t)items.size() * 3) ++bits;
+	out.bucket_bits = bits;
+	const size_t n_slots = (size_t)4 << bits;
+	out.tags.assign(n_slots, 0);
+	out.slots.assign(n_slots, vg_slot_t{VG_EMPTY_KEY, 0, 0});
 	for (const Item &it : items) {
-		uint32_t s = vg_slot_home(it.anchor, bits);
-		while (out.slots[s].okey != VG_EMPTY_KEY) s = (s + 1) & smask;
+		size_t s = (size_t)vg_bucket_home(it.anchor, bits) * 4;
+		while (out.tags[s]) s = (s + 1) & (n_slots - 1);
+		out.tags[s] = vg_tag(it.anchor);
 		out.slots[s] = vg_slot_t{it.okey, it.val, it.off};
 	}
 }

@@ -31,11 +31,14 @@ struct RecipeTable {
 /* Structures of the anchor-filter kernel. */
 struct AnchorTables {
 	Plan plan;
-	std::vector<uint32_t> filter; /* blocked Bloom filter over canonical anchors       */
-	uint32_t slot_bits = 4;
-	std::vector<vg_slot_t> slots; /* open addressing on the forward anchor, linear probe */
+	std::vector<uint32_t> filter; /* blocked Bloom filter over the anchors                 */
+	bool canon = false;           /* filter keys are canonical anchors (large panels) rather
+	                                 than both orientations of every anchor (small panels)  */
+	uint32_t bucket_bits = 2;     /* the exact table has 4 << bucket_bits slots             */
+	std::vector<uint32_t> tags;   /* vg_tag(forward anchor), 0 = free                      */
+	std::vector<vg_slot_t> slots; /* payload of the slot with the same index              */
 	uint32_t n_entries = 0;       /* (oriented key, offset) pairs filed                  */
-	uint32_t n_filter_keys = 0;   /* distinct canonical anchors                          */
+	uint32_t n_filter_keys = 0;   /* distinct keys in the filter                         */
 };
 
 /* keys are canonical k-mers in the reference encoding; duplicates keep the first value */

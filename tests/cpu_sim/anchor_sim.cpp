@@ -54,11 +54,11 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 	AnchorTables t;
 	build_anchor_tables(k, keys, vals, n, t);
 	const int S = t.plan.stride, L = t.plan.len;
-	const uint32_t amask = vg_mask32(L), smask = (1u << t.slot_bits) - 1;
+	const uint32_t amask = vg_mask32(L), bmask = (1u << t.bucket_bits) - 1;
 	const uint32_t nw = (uint32_t)t.filter.size();
 	if (info) {
-		info[0] = S, info[1] = L, info[2] = nw, info[3] = t.slot_bits;
-		info[4] = t.n_entries, info[5] = t.n_filter_keys;
+		info[0] = S, info[1] = L, info[2] = nw, info[3] = t.bucket_bits;
+		info[4] = t.n_entries, info[5] = t.n_filter_keys | (t.canon ? 0x80000000u : 0);
 	}
 	uint64_t n_cand = 0;
 	const uint64_t n_chunks = n_bytes / 16;
@@ -68,23 +68,28 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 		uint32_t nxt = pack16(c + 1 < n_chunks ? bytes + 16 * (c + 1) : NL);
 		for (int j = 0; j < 16 / S; ++j) {
 			uint32_t a = (j == 0 ? cur : funnel_r(cur, nxt, 2 * j * S)) & amask;
-			uint32_t h = vg_filter_hash(vg_canon32(a, L));
-			uint32_t m = vg_filter_mask(h);
-			if ((t.filter[vg_filter_word(h, nw)] & m) != m) continue;
+			uint32_t key = vg_filter_key(a, L, t.canon);
+			uint32_t m = vg_mask_entry(vg_mask_index(key));
+			if ((t.filter[vg_filter_word(key, nw)] & m) != m) continue;
 			++n_cand;
 			uint64_t q = 16 * c + (uint64_t)j * S;
-			for (uint32_t s = vg_slot_home(a, t.slot_bits);; s = (s + 1) & smask) {
-				const vg_slot_t &e = t.slots[s];
-				if (e.okey == VG_EMPTY_KEY) break;
-				if (((uint32_t)(e.okey >> 2 * e.off) & amask) != a || q < e.off || q - e.off + k > n_bytes) continue;
-				const uint8_t *b = bytes + (q - e.off);
-				uint64_t km = 0;
-				bool ok = true;
-				for (int i = 0; i < k; ++i) {
-					ok &= is_base(b[i]);
-					km |= (uint64_t)((b[i] >> 1) & 3u) << 2 * i;
+			bool open_slot = false;
+			for (uint32_t bk = vg_bucket_home(a, t.bucket_bits); !open_slot; bk = (bk + 1) & bmask) {
+				for (int i = 0; i < 4 && !open_slot; ++i) {
+					uint32_t tag = t.tags[(size_t)bk * 4 + i];
+					if (tag == 0) { open_slot = true; break; }
+					if (tag != vg_tag(a)) continue;
+					const vg_slot_t &e = t.slots[(size_t)bk * 4 + i];
+					if (((uint32_t)(e.okey >> 2 * e.off) & amask) != a || q < e.off || q - e.off + k > n_bytes) continue;
+					const uint8_t *b = bytes + (q - e.off);
+					uint64_t km = 0;
+					bool ok = true;
+					for (int x = 0; x < k; ++x) {
+						ok &= is_base(b[x]);
+						km |= (uint64_t)((b[x] >> 1) & 3u) << 2 * x;
+					}
+					if (ok && km == e.okey) ++counts[e.val];
 				}
-				if (ok && km == e.okey) ++counts[e.val];
 			}
 		}
 	}

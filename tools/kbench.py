@@ -24,7 +24,10 @@ s = lut[torch.randint(0, 4, (n,), device="cuda", generator=g)]
 s[150::151] = 10
 s[torch.rand(n, device="cuda", generator=g) < 0.005] = ord("N")
 eng = vafgpu.Engine(a.k, keys, vals, a.snps, n_devices=1, flags=vafgpu.F_REFERENCE_RECIPE if a.recipe else 0)
-st = torch.cuda.current_stream().cuda_stream
+ts_ = torch.cuda.Stream()
+torch.cuda.set_stream(ts_)
+st = ts_.cuda_stream
+assert st != 0
 for _ in range(2):
     eng.count_device(s.data_ptr(), n, stream=st)
 torch.cuda.synchronize()

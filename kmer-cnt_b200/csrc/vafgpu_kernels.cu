@@ -94,49 +94,81 @@ __device__ __forceinline__ void l2_prefetch(const void *ptr)
 	asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
-/* the k raw bytes at q - off against one oriented pattern k-mer */
-__device__ __noinline__ uint32_t verify_slot(const AnchorParams &p, uint32_t slot, uint32_t anchor, uint32_t amask, uint64_t q)
+/* One (candidate, slot) pair whose tag matched, checked by the whole warp: the payload names
+ * an oriented pattern k-mer and where the anchor sits in it; lane i compares raw byte i of
+ * the stream at q - off with base i of the key.  Returns 1 (on every lane) if the k-mer is
+ * there, and *val_out is its counter. */
+__device__ __forceinline__ uint32_t verify_coop(const AnchorParams &p, uint32_t slot, uint32_t anchor, uint32_t amask,
+                                                uint64_t q, uint32_t lane, uint32_t *val_out)
 {
-	uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.slots) + slot);
-	uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
-	uint32_t val = raw.z, off = raw.w;
+	const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.slots) + slot); /* same address on all lanes */
+	const uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
+	const uint32_t off = raw.w;
+	*val_out = raw.z;
 	if (((uint32_t)(okey >> 2 * off) & amask) != anchor || q < off || q - off + p.k > p.n_bytes) return 0;
-	const uint8_t *b = p.bytes + (q - off);
-	uint64_t km = 0;
 	bool ok = true;
-	for (int i = 0; i < p.k; ++i) {
-		uint32_t c = b[i];
-		ok &= is_base(c);
-		km |= (uint64_t)((c >> 1) & 3u) << 2 * i;
+	if (lane < (uint32_t)p.k) {
+		const uint32_t c = p.bytes[q - off + lane];
+		ok = is_base(c) && ((c >> 1) & 3u) == ((uint32_t)(okey >> 2 * lane) & 3u);
 	}
-	if (!ok || km != okey) return 0;
-	bump(p.counts, val);
-	return 1;
+	return __all_sync(FULL, ok) ? 1u : 0u;
 }
 
-/* Resolve 32 (or the last n < 32) queued survivors of the filter, one per lane: fetch the
- * anchor's home bucket (four tags, one 16-byte load from L2); a free slot ends the search,
- * a matching tag sends the lane to the payload and the raw bytes. */
+/* Resolve n <= 32 queued survivors of the filter, one per lane: fetch the anchor's home
+ * bucket (four tags, one 16-byte load from L2); a free slot ends the search, a matching tag
+ * (rare: the anchor really is one a pattern carries) is verified by the whole warp.
+ * Returns the number of k-mer hits (same on every lane). */
 template <int S>
 __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uint2 *wq, uint32_t first, uint32_t n,
-                                                uint32_t amask)
+                                                uint32_t amask, uint32_t lane)
 {
-	const uint32_t lane = threadIdx.x & 31;
-	uint32_t hits = 0;
-	if (lane < n) {
-		const uint2 e = wq[first + lane];
-		const uint32_t anchor = e.x, tag = vg_tag(anchor), bmask = (1u << p.bucket_bits) - 1u;
-		const uint64_t q = p.range_lo + (uint64_t)e.y * (uint32_t)S;
-		for (uint32_t b = vg_bucket_home(anchor, p.bucket_bits);; b = (b + 1) & bmask) {
-			const uint4 t = __ldg(p.tags + b);
-			if (t.x == tag) hits += verify_slot(p, b * 4 + 0, anchor, amask, q);
-			if (t.x == 0) break;
-			if (t.y == tag) hits += verify_slot(p, b * 4 + 1, anchor, amask, q);
-			if (t.y == 0) break;
-			if (t.z == tag) hits += verify_slot(p, b * 4 + 2, anchor, amask, q);
-			if (t.z == 0) break;
-			if (t.w == tag) hits += verify_slot(p, b * 4 + 3, anchor, amask, q);
-			if (t.w == 0) break;
+	const uint32_t bmask = (1u << p.bucket_bits) - 1u;
+	bool active = lane < n;
+	uint2 e = make_uint2(0u, 0u);
+	if (active) e = wq[first + lane];
+	const uint32_t anchor = e.x, tag = vg_tag(anchor);
+	uint32_t b = vg_bucket_home(anchor, p.bucket_bits);
+	uint32_t hits = 0, my_val = 0;
+	bool my_hit = false;
+	while (__any_sync(FULL, active)) {
+		uint4 t = make_uint4(0u, 0u, 0u, 0u);
+		if (active) t = __ldg(p.tags + b);
+		/* slots of this bucket that carry my tag, up to the first free slot (tag != 0) */
+		const bool z0 = t.x == 0, z1 = z0 || t.y == 0, z2 = z1 || t.z == 0, z3 = z2 || t.w == 0;
+		uint32_t mm = (t.x == tag ? 1u : 0u) | (!z0 && t.y == tag ? 2u : 0u) | (!z1 && t.z == tag ? 4u : 0u) |
+		              (!z2 && t.w == tag ? 8u : 0u);
+		if (!active) mm = 0;
+		uint32_t pend = __ballot_sync(FULL, mm != 0);
+		while (pend) { /* uniform loop over the lanes that have something to verify */
+			const int src = __ffs(pend) - 1;
+			pend &= pend - 1;
+			uint32_t smm = __shfl_sync(FULL, mm, src);
+			const uint32_t sb = __shfl_sync(FULL, b, src);
+			const uint32_t sa = __shfl_sync(FULL, anchor, src);
+			const uint64_t sq = p.range_lo + (uint64_t)__shfl_sync(FULL, e.y, src) * (uint32_t)S;
+			while (smm) {
+				const int i = __ffs(smm) - 1;
+				smm &= smm - 1;
+				uint32_t val;
+				if (verify_coop(p, sb * 4 + i, sa, amask, sq, lane, &val)) {
+					++hits;
+					if (lane == (uint32_t)src) { /* remember it on the lane that found it */
+						if (my_hit) atomicAdd(&p.counts[my_val], 1u);
+						my_hit = true;
+						my_val = val;
+					}
+				}
+			}
+		}
+		if (z3) active = false; /* met a free slot: the chain ends here */
+		else b = (b + 1) & bmask;
+	}
+	/* warp-aggregated counter update: lanes that found the same counter elect one leader */
+	const uint32_t have = __ballot_sync(FULL, my_hit);
+	if (have) {
+		if (my_hit) {
+			const uint32_t peers = __match_any_sync(have, my_val);
+			if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&p.counts[my_val], (uint32_t)__popc(peers));
 		}
 	}
 	return hits;
@@ -148,55 +180,71 @@ struct Pipe {
 	uint32_t c;        /* this lane's chunk in it                                 */
 	const uint4 *ptr;  /* its address                                             */
 	uint32_t cur;      /* that chunk, packed                                      */
-	uint4 w1, w2;      /* raw chunks of tiles t+1 (arrived) and t+2 (in flight)   */
+	uint4 wa, wb;      /* raw chunks of tiles t+1 and t+2: (wa, wb) when !odd, (wb, wa) when odd */
+	bool odd;
 	uint32_t qn;       /* entries in the candidate queue                          */
 };
 
+/* one tile: pack the next tile's chunk out of `w`, scan the current one, then refill `w`
+ * with the chunk three tiles on.  The refill is issued at the END, behind the vote/branch of
+ * the last probe, into the registers just consumed: the assembler then neither hoists it
+ * above the consumer nor needs a copy, and it has two whole tiles to arrive. */
+template <int S, bool CANON, bool INTERIOR>
+__device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 &w, const uint32_t *filter,
+                                          const uint32_t *masktab, uint2 *wq, uint32_t lane, uint32_t amask)
+{
+	const uint32_t nw = p.filter_words, last = p.n_chunks - 1;
+	const int rc_shift = 32 - 2 * p.len;
+	if (INTERIOR) l2_prefetch(reinterpret_cast<const uint8_t *>(s.ptr) + 4096); /* this lane's chunk, 8 tiles on */
+	const uint32_t nx = pack16(w);
+	uint32_t right = 0;
+	if (S < 16) { /* an anchor may run into the next chunk: lane+1's, or lane 0's of the next tile */
+		right = __shfl_down_sync(FULL, s.cur, 1);
+		const uint32_t head = __shfl_sync(FULL, nx, 0);
+		if (lane == 31) right = head;
+	}
+#pragma unroll
+	for (int j = 0; j < 16 / S; ++j) {
+		const uint32_t a = (j == 0 ? s.cur : __funnelshift_r(s.cur, right, 2 * j * S)) & amask;
+		uint32_t key = a;
+		if (CANON) { /* a * rc(a): vg_rc32 with the shift hoisted */
+			uint32_t r = __brev(a);
+			r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+			key = a * ((r ^ 0xAAAAAAAAu) >> rc_shift);
+		}
+		const uint32_t word = filter[vg_filter_word(key, nw)];
+		const uint32_t m = masktab[vg_mask_index(key)];
+		bool hit = (~word & m) == 0;
+		if (!INTERIOR) hit = hit && s.c <= last;
+		if (__any_sync(FULL, hit)) { /* queue the survivors, compacted */
+			const uint32_t votes = __ballot_sync(FULL, hit);
+			if (hit) wq[s.qn + __popc(votes & ((1u << lane) - 1u))] = make_uint2(a, s.c * (16 / S) + j);
+			s.qn += __popc(votes);
+		}
+	}
+	s.cur = nx;
+	w = INTERIOR ? __ldcs(s.ptr + 96) : __ldcs(p.chunks + min(s.c + 96, last));
+	++s.t;
+	s.c += 32;
+	s.ptr += 32;
+}
+
 /* The hot loop: scan tiles until the span ends or 32 candidates are queued.  No calls, no
- * table walks; per tile and lane one 16-byte load, one pack, 16/S filter probes.
- * INTERIOR: every address touched (loads up to tile t1+1, prefetch 8 tiles ahead) is
- * inside the range, so nothing is clamped or predicated. */
+ * table walks.  INTERIOR: every address touched (loads up to tile t1+2, prefetch 8 tiles
+ * ahead) is inside the range, so nothing is clamped or predicated. */
 template <int S, bool CANON, bool INTERIOR>
 __device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, const uint32_t *filter,
                                            const uint32_t *masktab, uint2 *wq, uint32_t lane, uint32_t amask)
 {
-	const uint32_t nw = p.filter_words, last = p.n_chunks - 1;
-	const int rc_shift = 32 - 2 * p.len;
-	while (s.t < t1) {
-		if (INTERIOR) l2_prefetch(reinterpret_cast<const uint8_t *>(s.ptr) + 4096); /* this lane's chunk, 8 tiles on */
-		const uint32_t nx = pack16(s.w1);
-		uint32_t right = 0;
-		if (S < 16) { /* an anchor may run into the next chunk: lane+1's, or lane 0's of the next tile */
-			right = __shfl_down_sync(FULL, s.cur, 1);
-			const uint32_t head = __shfl_sync(FULL, nx, 0);
-			if (lane == 31) right = head;
+	for (;;) {
+		if (!s.odd) {
+			scan_tile<S, CANON, INTERIOR>(p, s, s.wa, filter, masktab, wq, lane, amask);
+			s.odd = true;
+			if (s.t >= t1 || s.qn >= 32) break;
 		}
-#pragma unroll
-		for (int j = 0; j < 16 / S; ++j) {
-			const uint32_t a = (j == 0 ? s.cur : __funnelshift_r(s.cur, right, 2 * j * S)) & amask;
-			uint32_t key = a;
-			if (CANON) { /* a * rc(a): vg_rc32 with the shift hoisted */
-				uint32_t r = __brev(a);
-				r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
-				key = a * ((r ^ 0xAAAAAAAAu) >> rc_shift);
-			}
-			const uint32_t word = filter[vg_filter_word(key, nw)];
-			const uint32_t m = masktab[vg_mask_index(key)];
-			bool hit = (~word & m) == 0;
-			if (!INTERIOR) hit = hit && s.c <= last;
-			if (__any_sync(FULL, hit)) { /* queue the survivors, compacted */
-				const uint32_t votes = __ballot_sync(FULL, hit);
-				if (hit) wq[s.qn + __popc(votes & ((1u << lane) - 1u))] = make_uint2(a, s.c * (16 / S) + j);
-				s.qn += __popc(votes);
-			}
-		}
-		s.cur = nx;
-		s.w1 = s.w2;
-		s.w2 = INTERIOR ? __ldcs(s.ptr + 96) : __ldcs(p.chunks + min(s.c + 96, last));
-		++s.t;
-		s.c += 32;
-		s.ptr += 32;
-		if (s.qn >= 32) break;
+		scan_tile<S, CANON, INTERIOR>(p, s, s.wb, filter, masktab, wq, lane, amask);
+		s.odd = false;
+		if (s.t >= t1 || s.qn >= 32) break;
 	}
 }
 
@@ -228,41 +276,45 @@ __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(con
 	uint32_t n_cand = 0, n_hits = 0;
 	Pipe s;
 	s.qn = 0;
+	s.t = 0;
+	s.odd = false;
+	uint32_t t1 = 0, span = warp;
+	bool interior = false;
 
-	for (uint32_t span = warp; span < p.n_spans; span += n_warps) {
-		s.t = span * p.tiles_per_span;
-		const uint32_t t1 = min(s.t + p.tiles_per_span, p.n_tiles);
-		/* Interior span: everything the pipeline touches lies inside the range.  Otherwise
-		 * loads are clamped to the last chunk: a chunk past the end is never scanned, and as
-		 * a right neighbour it can only create a false candidate, which the bounds check of
-		 * the verification rejects. */
-		const bool interior = (uint64_t)(t1 + 8) * 32 <= p.n_chunks;
-		s.c = s.t * 32 + lane;
-		s.ptr = p.chunks + s.c;
-		if (interior) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * 128); /* 4 KiB */
-		/* register pipeline: tile t is scanned while t+1 is being packed and t+2 is in flight;
-		 * the L2 prefetch runs 8 tiles ahead of that */
-		s.cur = pack16(__ldcs(p.chunks + min(s.c, last)));
-		s.w1 = __ldcs(p.chunks + min(s.c + 32, last));
-		s.w2 = __ldcs(p.chunks + min(s.c + 64, last));
-		for (;;) {
+	for (;;) {
+		if (s.t >= t1 && span < p.n_spans) { /* open the next span */
+			s.t = span * p.tiles_per_span;
+			t1 = min(s.t + p.tiles_per_span, p.n_tiles);
+			span += n_warps;
+			/* Interior span: everything the pipeline touches (loads up to tile t1+1, prefetch up
+			 * to tile t1+7) lies inside the range.  Otherwise loads are clamped to the last
+			 * chunk: a chunk past the end is never scanned, and as a right neighbour it can only
+			 * create a false candidate, which the bounds check of the verification rejects. */
+			interior = (uint64_t)(t1 + 9) * 32 <= p.n_chunks;
+			s.c = s.t * 32 + lane;
+			s.ptr = p.chunks + s.c;
+			if (interior) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * 128); /* 4 KiB */
+			/* register pipeline: tile t is scanned while t+1 is being packed and t+2 is in
+			 * flight; the L2 prefetch runs 8 tiles ahead of that */
+			s.cur = pack16(__ldcs(p.chunks + min(s.c, last)));
+			s.wa = __ldcs(p.chunks + min(s.c + 32, last));
+			s.wb = __ldcs(p.chunks + min(s.c + 64, last));
+			s.odd = false;
+		}
+		const bool finished = s.t >= t1; /* no span left */
+		if (!finished) {
 			if (interior) scan_tiles<S, CANON, true>(p, s, t1, s_filter, s_masktab, wq, lane, amask);
 			else scan_tiles<S, CANON, false>(p, s, t1, s_filter, s_masktab, wq, lane, amask);
-			__syncwarp();
-			while (s.qn >= 32) {
-				s.qn -= 32;
-				n_cand += 32;
-				n_hits += drain_queue<S>(p, wq, s.qn, 32, amask);
-			}
-			__syncwarp();
-			if (s.t >= t1) break;
 		}
+		if (s.qn >= 32 || (finished && s.qn)) { /* the one place candidates are resolved */
+			const uint32_t n = min(s.qn, 32u);
+			s.qn -= n;
+			n_cand += n;
+			__syncwarp();
+			n_hits += drain_queue<S>(p, wq, s.qn, n, amask, lane);
+			__syncwarp();
+		} else if (finished) break;
 	}
-	if (s.qn) {
-		n_cand += s.qn;
-		n_hits += drain_queue<S>(p, wq, 0, s.qn, amask);
-	}
-	for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(FULL, n_hits, o);
 	if (lane == 0 && (n_cand | n_hits)) {
 		atomicAdd(&p.stats[ST_CANDIDATES], (unsigned long long)n_cand);
 		atomicAdd(&p.stats[ST_HITS], (unsigned long long)n_hits);

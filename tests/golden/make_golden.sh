@@ -1,0 +1,32 @@
+#!/bin/bash
+# Regenerates the committed fixtures from the UNMODIFIED reference (needs /root/reference,
+# i.e. this only runs in the build container).  Everything written here is an OUTPUT of the
+# reference tools or an input we generated ourselves; no reference source is copied.
+#   kat_vaf.tsv            known answers of the reference's own functions (oracle/ref_kat.c)
+#   e2e_*/                 small inputs + the .vaf the reference vaf-counter wrote for them
+#   cfg2_patterns.txt.gz   snp-pattern-gen -k 21 over a synthetic hg38-length genome and the
+#                          NGSCheckMate GRCh38 panel (made separately, see tools/make_cfg2_patterns.sh)
+set -euo pipefail
+here=$(cd "$(dirname "$0")" && pwd)
+root=$(cd "$here/../.." && pwd)
+make -s -C "$root/oracle" all
+ref="$root/oracle/_ref"
+synth="$root/oracle/synth"
+"$ref/ref_kat" > "$here/kat_vaf.tsv" 2>/dev/null
+
+mk() { # name k synth-args...
+	local name=$1 k=$2; shift 2
+	local d="$here/e2e_$name"; rm -rf "$d"; mkdir -p "$d"
+	"$synth" cfg -o "$d/x" "$@"
+	"$ref/snp-pattern-gen" -k "$k" -b "$d/x.bed" -f "$d/x.fa" -o "$d/patterns.txt" 2>/dev/null
+	"$ref/vaf-counter" -k "$k" -t 2 -b 200000 -p "$d/patterns.txt" -o "$d/expected.vaf" "$d/x.fq" 2>/dev/null
+	"$ref/vaf-counter-scalar" -k "$k" -t 1 -p "$d/patterns.txt" -o "$d/expected_scalar.vaf" "$d/x.fq" 2>/dev/null
+	mv "$d/x.fq" "$d/reads.fq"; gzip -9n "$d/reads.fq"
+	rm -f "$d/x.fa" "$d/x.bed"
+	echo "$k" > "$d/k"
+}
+mk k21 21 -L 60000 -n 300 -r 4000 -l 150 -s 11
+mk k15 15 -L 60000 -n 300 -r 4000 -l 150 -s 12 -N 0.02 -M 4
+mk k31 31 -L 60000 -n 300 -r 4000 -l 150 -s 13 -N 0.05 -M 5
+mk exotic 21 -L 60000 -n 300 -r 4000 -l 150 -j 40 -s 14 -x 0.01
+ls -la "$here" "$here"/e2e_*

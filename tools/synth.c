@@ -6,6 +6,8 @@
  * genome can be regenerated elsewhere (bench.py rebuilds it on the GPU with integer
  * tensor ops) without shipping files.
  *
+ *   synth genome -o out.fa -b panel.bed [-s 38]
+ *     an hg38-length random FASTA (3.1 Gb) with the BED's ref alleles planted
  *   synth cfg -o PREFIX [-L 1000000] [-n 1000] [-r 1000000] [-l 150] [-e 0.01]
  *             [-N 0.005] [-M 1] [-s 1] [-c chr1] [-j 0] [-x 0]
  *     writes PREFIX.fa, PREFIX.bed, PREFIX.fq
@@ -58,6 +60,78 @@ static inline char comp(char c)
 	return c;
 }
 
+/* hg38 primary contigs that carry SNPs of the NGSCheckMate panel, plus its two alt contigs */
+static const struct { const char *name; long len; } HG38[] = {
+	{"chr1", 248956422}, {"chr2", 242193529}, {"chr3", 198295559}, {"chr4", 190214555},
+	{"chr5", 181538259}, {"chr6", 170805979}, {"chr7", 159345973}, {"chr8", 145138636},
+	{"chr9", 138394717}, {"chr10", 133797422}, {"chr11", 135086622}, {"chr12", 133275309},
+	{"chr13", 114364328}, {"chr14", 107043718}, {"chr15", 101991189}, {"chr16", 90338345},
+	{"chr17", 83257441}, {"chr18", 80373285}, {"chr19", 58617616}, {"chr20", 64444167},
+	{"chr21", 46709983}, {"chr22", 50818468}, {"chrX", 156040895},
+	{"chr19_KI270938v1_alt", 1066800}, {"chr1_KI270766v1_alt", 256271},
+};
+
+/* synth genome -o out.fa -b panel.bed [-s seed]: an hg38-length random reference in which the
+ * `ref` allele of every BED row is planted at its position (otherwise a quarter of the panel
+ * would name an alt allele equal to the random base and be dropped by snp-pattern-gen). */
+static int genome_main(int argc, char **argv)
+{
+	const char *out = NULL, *bed = NULL;
+	uint64_t seed = 38;
+	int c;
+	optind = 2;
+	while ((c = getopt(argc, argv, "o:b:s:")) >= 0) {
+		if (c == 'o') out = optarg;
+		else if (c == 'b') bed = optarg;
+		else if (c == 's') seed = strtoull(optarg, 0, 10);
+	}
+	if (!out) { fprintf(stderr, "Usage: synth genome -o out.fa [-b panel.bed] [-s seed]\n"); return 1; }
+	typedef struct { char chr[64]; long pos; char ref; } row_t;
+	row_t *rows = NULL;
+	long n_rows = 0, m_rows = 0;
+	if (bed) {
+		FILE *fb = fopen(bed, "r");
+		char chr[256], id[256], r, a;
+		long st, en;
+		if (!fb) { perror(bed); return 1; }
+		while (fscanf(fb, "%255s%ld%ld%255s %c %c", chr, &st, &en, id, &r, &a) == 6) {
+			if (n_rows == m_rows) rows = (row_t *)realloc(rows, (m_rows = m_rows ? m_rows * 2 : 1024) * sizeof(row_t));
+			snprintf(rows[n_rows].chr, sizeof rows[n_rows].chr, "%.63s", chr);
+			rows[n_rows].pos = st;
+			rows[n_rows++].ref = r;
+		}
+		fclose(fb);
+	}
+	FILE *fp = fopen(out, "w");
+	if (!fp) { perror(out); return 1; }
+	static char obuf[1 << 22];
+	setvbuf(fp, obuf, _IOFBF, sizeof obuf);
+	uint64_t base = 0;
+	long planted = 0;
+	for (unsigned k = 0; k < sizeof HG38 / sizeof *HG38; ++k) {
+		long L = HG38[k].len;
+		char *s = (char *)malloc((size_t)L);
+		for (long i = 0; i < L; ++i) s[i] = BASES[at(seed, base + (uint64_t)i) >> 62];
+		for (long j = 0; j < n_rows; ++j)
+			if (strcmp(rows[j].chr, HG38[k].name) == 0 && rows[j].pos >= 0 && rows[j].pos < L &&
+			    strchr("ACGT", rows[j].ref)) {
+				s[rows[j].pos] = rows[j].ref;
+				++planted;
+			}
+		fprintf(fp, ">%s\n", HG38[k].name);
+		for (long i = 0; i < L; i += 60) {
+			fwrite(s + i, 1, (size_t)(L - i < 60 ? L - i : 60), fp);
+			fputc('\n', fp);
+		}
+		free(s);
+		base += (uint64_t)L;
+	}
+	fclose(fp);
+	fprintf(stderr, "synth genome: %llu bases, %ld alleles planted\n", (unsigned long long)base, planted);
+	free(rows);
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	long L = 1000000, n_snp = 1000, n_reads = 1000000;
@@ -68,6 +142,7 @@ int main(int argc, char **argv)
 	char path[4096];
 	static const char EXOTIC[] = "RYKMSWBDHVacgtnUu.-*XQ17";
 
+	if (argc >= 2 && strcmp(argv[1], "genome") == 0) return genome_main(argc, argv);
 	if (argc < 2 || strcmp(argv[1], "cfg") != 0) {
 		fprintf(stderr, "Usage: synth cfg -o PREFIX [-L len] [-n snps] [-r reads] [-l readlen] [-e sub] [-N nrate] [-M nrun] [-s seed] [-c chr] [-j jitter] [-x exotic]\n");
 		return 1;

@@ -1,0 +1,542 @@
+#!/usr/bin/env python
+"""bench.py -- Gbases/s of the vaf-counter k-mer extract-and-lookup path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at N = 1: BASELINE config 2 -- k = 21, the full NGSCheckMate GRCh38 panel
+(tests/golden/cfg2_patterns.txt.gz: the reference's snp-pattern-gen over a synthetic
+hg38-length genome), 100 M x 150 bp synthetic reads (15 Gbases) drawn at ~5x from a diploid
+donor that carries the panel's SNPs, 1 % substitutions, 0.5 % N, both strands.  The reads are
+generated on the GPU (torch is plumbing: device memory, RNG, streams, torch.distributed) as the
+stream the engine consumes: reads separated by '\\n'.  One step = one pass of the hot path over
+the whole resident stream.  N > 1: weak scaling, every rank holds its own 100 M reads, the
+pattern tables are replicated, and the per-SNP counters are summed with one NCCL all-reduce
+per step (the path's only collective).
+
+  value     kernel-only Gbases/s: stream already in HBM, CUDA events on the launch stream
+  e2e       the same through the C ABI from page-locked HOST memory: vafgpu_submit_stream
+            (H2D copies overlapped with the kernel on the engine's streams) + vafgpu_finish
+            (counter read-back), wall clock around a device synchronize
+  roofline  algorithmic bytes (1 byte per base) per second of the anchor kernel against the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference
+            the UNMODIFIED reference vaf-counter (oracle/_ref, built from /root/reference by
+            oracle/Makefile) on this box's host cores, on a bounded sample of the same reads
+
+Nothing here runs the oracle or the reference as the product: they appear only as the
+checker (parity of a sample) and as the timed CPU baseline.
+"""
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "kmer-cnt_b200")
+sys.path.insert(0, PKG)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K = 21
+READ_LEN = 150
+PATTERNS_GZ = os.path.join(ROOT, "tests", "golden", "cfg2_patterns.txt.gz")
+HG38 = [("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 190214555), ("chr5", 181538259),
+        ("chr6", 170805979), ("chr7", 159345973), ("chr8", 145138636), ("chr9", 138394717), ("chr10", 133797422),
+        ("chr11", 135086622), ("chr12", 133275309), ("chr13", 114364328), ("chr14", 107043718), ("chr15", 101991189),
+        ("chr16", 90338345), ("chr17", 83257441), ("chr18", 80373285), ("chr19", 58617616), ("chr20", 64444167),
+        ("chr21", 46709983), ("chr22", 50818468), ("chrX", 156040895), ("chr19_KI270938v1_alt", 1066800),
+        ("chr1_KI270766v1_alt", 256271)]
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+
+
+def load_cfg2_patterns(tmpdir):
+    import vafgpu
+    path = os.path.join(tmpdir, "cfg2_patterns.txt")
+    with gzip.open(PATTERNS_GZ, "rb") as src, open(path, "wb") as dst:
+        dst.write(src.read())
+    pats = vafgpu.load_patterns(path)
+    keys, vals, n_coll = vafgpu.build_key_list(pats, K)
+    return path, pats, keys, vals, n_coll
+
+
+def build_donor(torch, pats, genome_len, seed, device):
+    """Two haplotypes of a random genome of `genome_len` bases that carries every pattern's
+    21-mer at its (scaled) position: 1/4 of the SNPs hom-ref, 1/2 het, 1/4 hom-alt."""
+    import numpy as np
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    hap0 = torch.empty(genome_len, dtype=torch.uint8, device=device)
+    step = 1 << 28
+    for lo in range(0, genome_len, step):
+        n = min(step, genome_len - lo)
+        hap0[lo:lo + n] = acgt[torch.randint(0, 4, (n,), device=device, generator=g)]
+    offs, off = {}, 0
+    for name, ln in HG38:
+        offs[name] = off
+        off += ln
+    scale = genome_len / off
+    flank = K // 2
+    pos = np.array([int((offs.get(p.chr, 0) + p.start) * scale) for p in pats], dtype=np.int64)
+    pos = np.clip(pos, flank, genome_len - flank - 2)
+    ref = np.frombuffer("".join(p.ref_kmer for p in pats).encode(), dtype=np.uint8).reshape(len(pats), K)
+    alt = np.array([ord(p.alt) for p in pats], dtype=np.uint8)
+    idx = torch.from_numpy(pos[:, None] - flank + np.arange(K)[None, :]).to(device)
+    # later rows overwrite earlier ones where windows overlap (the 27 duplicated positions agree)
+    hap0[idx.reshape(-1)] = torch.from_numpy(ref.reshape(-1).copy()).to(device)
+    hap1 = hap0.clone()
+    rng = np.random.default_rng(seed)
+    geno = rng.integers(0, 4, len(pats))
+    mid = torch.from_numpy(pos).to(device)
+    alt_t = torch.from_numpy(alt).to(device)
+    m1 = torch.from_numpy(geno >= 1).to(device)
+    m3 = torch.from_numpy(geno == 3).to(device)
+    hap1[mid[m1]] = alt_t[m1]
+    hap0[mid[m3]] = alt_t[m3]
+    return torch.cat([hap0, hap1]), genome_len
+
+
+def make_stream(torch, donor, genome_len, n_reads, seed, device, sub_rate=0.01, n_rate=0.005):
+    """n_reads x 150 bp as the engine's stream: bytes + '\\n' per read, padded to 16."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rec = READ_LEN + 1
+    n_bytes = n_reads * rec
+    stream = torch.full(((n_bytes + 15) // 16 * 16,), 10, dtype=torch.uint8, device=device)
+    comp = torch.arange(256, dtype=torch.uint8, device=device)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    ar = torch.arange(READ_LEN, device=device)
+    chunk = 1 << 20
+    for lo in range(0, n_reads, chunk):
+        r = min(chunk, n_reads - lo)
+        start = torch.randint(0, genome_len - READ_LEN, (r,), device=device, generator=g)
+        hap = torch.randint(0, 2, (r,), device=device, generator=g)
+        seq = donor[(start + hap * genome_len)[:, None] + ar[None, :]]
+        rev = torch.randint(0, 2, (r, 1), device=device, generator=g).bool()
+        seq = torch.where(rev, comp[seq.long()].flip(1), seq)
+        sub = torch.rand((r, READ_LEN), device=device, generator=g) < sub_rate * 4 / 3
+        seq = torch.where(sub, acgt[torch.randint(0, 4, (r, READ_LEN), device=device, generator=g)], seq)
+        isn = torch.rand((r, READ_LEN), device=device, generator=g) < n_rate
+        seq = torch.where(isn, torch.full_like(seq, ord("N")), seq)
+        stream[lo * rec:(lo + r) * rec].view(r, rec)[:, :READ_LEN] = seq
+    return stream, n_bytes
+
+
+def stream_to_reads(buf):
+    """host bytes of a stream -> list of reads"""
+    return [r for r in bytes(buf).split(b"\n") if r]
+
+
+def write_fastq(path, reads):
+    with open(path, "wb") as fh:
+        q = b"I" * READ_LEN
+        fh.write(b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, q[:len(r)]) for i, r in enumerate(reads)))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML (every ~2 ms: the timed region lasts
+    tens of milliseconds, too short for `nvidia-smi -lms`) while the timed region runs."""
+
+    def __init__(self, index=0):
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self.stop = threading.Event()
+        self.th = None
+        self.nv = self.h = None
+        try:  # NVML start-up takes ~0.1 s: do it before the timed region, not in it
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as exc:  # no NVML: report that instead of inventing numbers
+            self.reasons.add("nvml unavailable: %r" % (exc,))
+
+    def _sample(self):
+        nv, h = self.nv, self.h
+        self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for k, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                       ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                       ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                       ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(k)
+
+    def _run(self):
+        try:
+            while not self.stop.is_set():
+                self._sample()
+                time.sleep(0.001)
+        except Exception as exc:
+            self.reasons.add("nvml sampling failed: %r" % (exc,))
+
+    def __enter__(self):
+        if self.nv:
+            self.sm.clear()
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        if self.th:
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline
+
+
+def reference_binary():
+    ref = os.path.join(ROOT, "oracle", "_ref", "vaf-counter")
+    if os.path.exists(ref):
+        return ref, "reference"
+    port = os.path.join(ROOT, "oracle", "vaf_oracle")       # the C restatement, if the reference did not travel
+    if not os.path.exists(port):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "vaf_oracle"], check=True)
+    return port, "port"
+
+
+def time_reference(exe, pattern_file, fastq, out, threads):
+    t0 = time.perf_counter()
+    subprocess.run([exe, "-k", str(K), "-t", str(threads), "-p", pattern_file, "-o", out, fastq],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.perf_counter() - t0
+
+
+def shm_dir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+
+
+# ------------------------------------------------------------------------------------------------
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (config 2: 100 M)")
+    ap.add_argument("--genome", type=int, default=sum(l for _, l in HG38), help="synthetic donor genome length")
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--e2e-max-gb", type=float, default=16.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0                                    # the CPU arm runs on rank 0 alone
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys_index = local
+    if world > 1 and args.impl == "ours":
+        # one process per GPU: each sees exactly its own device as ordinal 0
+        ids = vis.split(",") if vis else [str(i) for i in range(world)]
+        os.environ["CUDA_VISIBLE_DEVICES"] = ids[local % len(ids)]
+        phys_index = int(ids[local % len(ids)]) if ids[local % len(ids)].isdigit() else local
+    elif vis and vis.split(",")[0].isdigit():
+        phys_index = int(vis.split(",")[0])
+
+    import numpy as np
+    import torch
+    import vafgpu
+
+    tmp = tempfile.mkdtemp(prefix="vafbench_", dir=shm_dir())
+    pattern_file, pats, keys, vals, n_coll = load_cfg2_patterns(tmp)
+    n_pat = len(pats)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peaks else "fallback 6.65 TB/s"
+    config = {"workload": "config 2: vaf-counter k=21, NGSCheckMate GRCh38 panel (%d patterns from a synthetic "
+                          "hg38-length reference), %d x %d bp synthetic reads per GPU" % (n_pat, args.reads, READ_LEN),
+              "k": K, "patterns": n_pat, "reads_per_gpu": args.reads, "read_len": READ_LEN,
+              "l2": "inputs (%.1f GB per GPU) are far larger than L2" % (args.reads * (READ_LEN + 1) / 1e9),
+              "parallelism": "reads sharded per rank, tables replicated, one all-reduce of the counters per step"}
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); --impl reference also builds its "
+                         "sample of the workload on the GPU")
+    dev = torch.device("cuda", 0 if world > 1 else local)
+    torch.cuda.set_device(dev)
+
+    # ---------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        exe, kind = reference_binary()
+        donor, glen = build_donor(torch, pats, min(args.genome, 1 << 28), 1234, dev)
+        s, nb = make_stream(torch, donor, glen, args.cpu_sample_reads, 99, dev)
+        reads = stream_to_reads(s[:nb].cpu().numpy().tobytes())
+        fq = os.path.join(tmp, "sample.fq")
+        write_fastq(fq, reads)
+        bases = sum(map(len, reads))
+        ncpu = os.cpu_count() or 1
+        best_t = 1
+        t1 = time_reference(exe, pattern_file, fq, os.path.join(tmp, "r.vaf"), 1)
+        tn = time_reference(exe, pattern_file, fq, os.path.join(tmp, "r.vaf"), ncpu)
+        threads = 1 if t1 <= tn else ncpu          # more threads make the reference slower
+        log(f"reference: -t 1 {bases / t1 / 1e6:.1f} Mbases/s, -t {ncpu} {bases / tn / 1e6:.1f} Mbases/s")
+        times = []
+        for i in range(args.warmup + args.steps):
+            dt = time_reference(exe, pattern_file, fq, os.path.join(tmp, "r.vaf"), threads)
+            if i >= args.warmup:
+                times.append(dt)
+        total = sum(times)
+        v = bases * len(times) / total / 1e9
+        line = {"impl": "reference", "metric": "Gbases/s", "value": v, "unit": "Gbases/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": threads, "kind": kind,
+                                 "sample": "%d reads x %d bp of the config-2 workload per step; whole process wall "
+                                           "clock (pattern load + FASTQ parse + count); best of -t 1 (%.4f) and -t %d "
+                                           "(%.4f Gbases/s)" % (len(reads), READ_LEN, bases / t1 / 1e9, ncpu, bases / tn / 1e9)},
+                "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    t_gen = time.perf_counter()
+    donor, glen = build_donor(torch, pats, args.genome, 1234, dev)
+    stream, n_bytes = make_stream(torch, donor, glen, args.reads, 1000 + rank, dev)
+    del donor
+    torch.cuda.synchronize()
+    log(f"generated {args.reads} reads ({n_bytes / 1e9:.2f} GB) in {time.perf_counter() - t_gen:.1f} s")
+    bases_per_step = args.reads * READ_LEN
+
+    eng = vafgpu.Engine(K, keys, vals, n_pat, n_devices=1, block_bytes=256 << 20, n_buffers=3)
+    counts = torch.zeros(2 * n_pat, dtype=torch.int32, device=dev)
+    ts = torch.cuda.Stream()
+    n16 = stream.numel()
+    launches_per_step = (n16 + (1 << 31) - 1) >> 31
+
+    def step():
+        counts.zero_()
+        eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
+        if world > 1:
+            dist.all_reduce(counts)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(ts):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk = ClockSampler(phys_index)
+        with clk:
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        # the dominant kernel alone (no counter reset, no collective), for the roofline
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
+        k1.record()
+        barrier()
+        kernel_ms = k0.elapsed_time(k1) / (args.steps * launches_per_step)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = bases_per_step * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- parity at full size: linearity over a split, the literal recipe kernel on a slice,
+    #      the oracle and the reference on a sample
+    with torch.cuda.stream(ts):
+        counts.zero_()
+        eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
+        torch.cuda.synchronize()
+        full = counts.clone()
+        rec = READ_LEN + 1
+        cut = (args.reads // 2) * rec
+        cut16 = (cut + 15) // 16 * 16
+        head = torch.full((cut16,), 10, dtype=torch.uint8, device=dev)
+        head[:cut] = stream[:cut]
+        tail = torch.full(((n_bytes - cut + 15) // 16 * 16,), 10, dtype=torch.uint8, device=dev)
+        tail[:n_bytes - cut] = stream[cut:n_bytes]
+        counts.zero_()
+        eng.count_device(head.data_ptr(), head.numel(), d_counts=counts.data_ptr(), stream=ts.cuda_stream)
+        eng.count_device(tail.data_ptr(), tail.numel(), d_counts=counts.data_ptr(), stream=ts.cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(full, counts), "linearity over a split of the stream failed"
+        del head, tail
+    _, st_kernel = eng.finish()
+    hits_per_step = int(full.to(torch.int64).sum().item())
+    slice_reads = min(args.reads, 2_000_000)
+    sl = stream[:(slice_reads * rec + 15) // 16 * 16].clone()
+    sl[slice_reads * rec:] = 10
+    with vafgpu.Engine(K, keys, vals, n_pat, n_devices=1, flags=vafgpu.F_REFERENCE_RECIPE) as rec_eng:
+        c2 = torch.zeros_like(counts)
+        rec_eng.count_device(sl.data_ptr(), sl.numel(), d_counts=c2.data_ptr())
+        torch.cuda.synchronize()
+    c1 = torch.zeros_like(counts)
+    eng.count_device(sl.data_ptr(), sl.numel(), d_counts=c1.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(c1, c2), "anchor kernel and literal recipe kernel disagree"
+    parity = {"split_linearity": "ok", "recipe_kernel_on_%d_reads" % slice_reads: "ok"}
+
+    # ---- end to end through the C ABI from page-locked host memory
+    avail_gb = 0.0
+    try:
+        for l in open("/proc/meminfo"):
+            if l.startswith("MemAvailable"):
+                avail_gb = int(l.split()[1]) / 1e6
+    except OSError:
+        pass
+    e2e_bytes = int(min(n_bytes, args.e2e_max_gb * 1e9, max(avail_gb, 1.0) * 1e9 / 3))
+    e2e_reads = e2e_bytes // rec
+    e2e_bytes = e2e_reads * rec
+    host = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True)
+    host.copy_(stream[:e2e_bytes])
+    torch.cuda.synchronize()
+    eng.reset()
+    e2e_times, got = [], None
+    for i in range(args.warmup + args.steps):
+        if world > 1:
+            dist.barrier()
+        eng.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.submit_stream((host.data_ptr(), e2e_bytes), n_reads=e2e_reads, n_bases=e2e_reads * READ_LEN)
+        got, st_e2e = eng.finish()
+        if world > 1:
+            g = torch.from_numpy(got.astype(np.int32)).to(dev)
+            dist.all_reduce(g)
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            e2e_times.append(dt)
+    e2e_dt = sum(e2e_times) / len(e2e_times)
+    if world > 1:
+        t = torch.tensor([e2e_dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = e2e_reads * READ_LEN * world / e2e_dt / 1e9
+    # what came back must be what the resident pass counted for the same reads
+    chk = torch.zeros_like(counts)
+    n_e16 = (e2e_bytes + 15) // 16 * 16
+    if n_e16 <= n16:
+        part = stream[:n_e16].clone()
+        part[e2e_bytes:] = 10
+        eng2 = vafgpu.Engine(K, keys, vals, n_pat, n_devices=1)
+        eng2.count_device(part.data_ptr(), part.numel(), d_counts=chk.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(chk.cpu().numpy().view(np.uint32), got), "e2e counters differ from the resident pass"
+        eng2.close()
+        parity["e2e_equals_resident"] = "ok"
+
+    # ---- CPU baseline + byte parity of the .vaf on a sample (rank 0 only)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        exe, kind = reference_binary()
+        n_s = min(args.cpu_sample_reads, args.reads)
+        reads = stream_to_reads(stream[:n_s * rec].cpu().numpy().tobytes())
+        fq = os.path.join(tmp, "sample.fq")
+        write_fastq(fq, reads)
+        bases = sum(map(len, reads))
+        ncpu = os.cpu_count() or 1
+        t1 = time_reference(exe, pattern_file, fq, os.path.join(tmp, "ref1.vaf"), 1)
+        tn = time_reference(exe, pattern_file, fq, os.path.join(tmp, "refn.vaf"), ncpu)
+        best, threads = (t1, 1) if t1 <= tn else (tn, ncpu)
+        cpu = {"value": bases / best / 1e9, "unit": "Gbases/s", "cores": threads, "kind": kind,
+               "sample": "%d reads x %d bp of this workload, whole process wall clock; -t 1: %.4f, -t %d: %.4f Gbases/s; "
+                         "host has %d cores" % (len(reads), READ_LEN, bases / t1 / 1e9, ncpu, bases / tn / 1e9, ncpu)}
+        # our CLI-equivalent path on the same FASTQ sample: byte-identical .vaf
+        with vafgpu.Engine(K, keys, vals, n_pat, n_devices=1) as e3:
+            for r in reads:
+                e3.add_read(r)
+            mine, _ = e3.finish()
+        ours_txt = vafgpu.format_vaf(pats, mine)
+        ref_txt = open(os.path.join(tmp, "ref1.vaf")).read()
+        assert ours_txt == ref_txt, "VAF text differs from the reference's on the sample"
+        assert open(os.path.join(tmp, "refn.vaf")).read() == ref_txt
+        parity["vaf_bytes_vs_%s_on_%d_reads" % (kind, len(reads))] = "identical"
+        try:
+            import util
+            want, _, _ = util.Oracle().count_reads(pattern_file, K, reads)
+            assert np.array_equal(want, mine)
+            parity["oracle_counts_on_sample"] = "identical"
+        except Exception as exc:  # the oracle is a checker; its absence is reported, not hidden
+            parity["oracle_counts_on_sample"] = "not run: %r" % (exc,)
+
+    if rank == 0:
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = prof["dram_bytes_per_stream_byte"] * (n16 / launches_per_step)
+        except (OSError, KeyError, ValueError):
+            pass
+        algo_bytes_per_launch = bases_per_step / launches_per_step            # 1 byte per base
+        achieved = algo_bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 in, u32/u64 integer arithmetic", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": 8 * n_pat,
+                    "sample": "%d of %d reads per GPU from page-locked host memory through vafgpu_submit_stream + "
+                              "vafgpu_finish" % (e2e_reads, args.reads)},
+            "gpu_launches": int(args.steps * launches_per_step),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "anchor_scan_kernel<8,true>",
+                         "algorithmic_bytes_per_launch": algo_bytes_per_launch, "ms_per_launch": kernel_ms},
+            "cpu_baseline": cpu,
+            "clocks": clk.summary(),
+            "parity": parity,
+            "stats": {"hits_per_step": hits_per_step, "filter_survivors_per_base":
+                      st_kernel["n_candidates"] / max(st_kernel["n_bytes"], 1), "anchor_stride": st_kernel["anchor_stride"],
+                      "anchor_len": st_kernel["anchor_len"], "filter_bytes": st_kernel["filter_bytes"],
+                      "pattern_collisions": n_coll},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -430,6 +430,11 @@ int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint6
 	if (!c || (!bytes && n_bytes)) return VAFGPU_EINVAL;
 	c->st.n_reads += n_reads;
 	c->st.n_bases += n_bases;
+	/* page-locked caller memory is copied to the device as it is; pageable memory goes through
+	 * the pinned staging blocks */
+	cudaPointerAttributes attr;
+	bool pinned = cudaPointerGetAttributes(&attr, bytes) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError(); /* a plain malloc pointer is reported as an error by older drivers */
 	size_t at = 0;
 	while (at < n_bytes) {
 		/* close whatever add_read left open, then fill whole blocks straight from the caller */
@@ -438,25 +443,47 @@ int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint6
 		rc = acquire(c);
 		if (rc) return rc;
 		Block *b = c->cur;
-		size_t n = n_bytes - at;
+		size_t n = n_bytes - at, advance;
+		bool add_nl = false;
 		if (n > c->block_bytes) {
 			/* cut after the last separator that fits; a single read longer than a block is cut
 			 * with a k-1 overlap like in vafgpu_add_read */
 			n = c->block_bytes;
 			const char *nl = (const char *)memrchr(bytes + at, '\n', n);
-			if (nl) n = (size_t)(nl - (bytes + at)) + 1;
-			else {
-				memcpy(b->h, bytes + at, n - 1);
-				b->h[n - 1] = '\n';
-				b->used = n;
-				at += n - 1 - (size_t)(c->k - 1);
-				continue;
+			if (nl) {
+				n = (size_t)(nl - (bytes + at)) + 1;
+				advance = n;
+			} else {
+				n -= 1;
+				add_nl = true;
+				advance = n - (size_t)(c->k - 1);
 			}
+		} else {
+			advance = n;
+			add_nl = bytes[at + n - 1] != '\n';
 		}
-		memcpy(b->h, bytes + at, n);
-		b->used = n;
-		if (b->h[n - 1] != '\n') b->h[b->used++] = '\n';
-		at += n;
+		if (!pinned) {
+			memcpy(b->h, bytes + at, n);
+			if (add_nl) b->h[n++] = '\n';
+			b->used = n;
+			at += advance;
+			continue; /* submitted at the top of the loop or after it */
+		}
+		/* zero-copy path: H2D from the caller's buffer, separator and padding written on the device */
+		Device &d = c->devs[c->cur_dev];
+		c->cur = nullptr;
+		const size_t n16 = (n + (add_nl ? 1 : 0) + 15) & ~(size_t)15;
+		CU(c, cudaSetDevice(d.ordinal));
+		CU(c, cudaEventRecord(b->e0, b->stream));
+		CU(c, cudaMemcpyAsync(b->d, bytes + at, n, cudaMemcpyHostToDevice, b->stream));
+		if (n16 > n) CU(c, cudaMemsetAsync(b->d + n, '\n', n16 - n, b->stream));
+		CU(c, cudaEventRecord(b->e1, b->stream));
+		CU(c, launch(c, d, scan_args(c, d, b->d, n16, nullptr), b->stream));
+		CU(c, cudaEventRecord(b->e2, b->stream));
+		b->in_flight = true;
+		c->st.n_blocks++;
+		c->st.n_bytes += n16;
+		at += advance;
 	}
 	return submit_current(c);
 }

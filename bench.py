@@ -266,6 +266,7 @@ def main():
 
     import numpy as np
     import torch
+    import sharding
     import vafgpu
 
     tmp = tempfile.mkdtemp(prefix="vafbench_", dir=shm_dir())
@@ -347,7 +348,7 @@ def main():
         counts.zero_()
         eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
         if world > 1:
-            dist.all_reduce(counts)
+            sharding.all_reduce_counts(counts, dist)
 
     def barrier():
         torch.cuda.synchronize()

@@ -29,14 +29,15 @@
 #define VG_THREADS(S) ((S) >= 4 ? 1024 : 256)              /* tiny k: fewer warps, deeper queues   */
 #define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)))         /* per warp: a drain's leftovers + one tile */
 #define VG_QUEUE_BYTES(S) ((VG_THREADS(S) / 32) * VG_QUEUE_ENTRIES(S) * 8)
-#define VG_FILTER_BUDGET_WORDS(S) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S) - 4 * 992) / 4) & ~3))
+#define VG_FILTER_BUDGET_WORDS(S) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S)) / 4) & ~3))
 
 /* exact-table slot: an oriented pattern k-mer (stream encoding) with the offset of the
  * anchor it is filed under.  16 bytes so one LDG.128 fetches it. */
 typedef struct {
 	uint64_t okey; /* oriented k-mer, VG_EMPTY_KEY if the slot is free */
 	uint32_t val;  /* (pattern index << 1) | is_alt                     */
-	uint32_t off;  /* anchor = (okey >> 2*off) & mask(L)                */
+	uint32_t off;  /* t: the anchor ends t bases before the k-mer does:
+	                  anchor = (okey >> 2*(k-t-L)) & mask(L)            */
 } vg_slot_t;
 
 /* ---- the reference's hash (recipe kernel and its table) ---- */
@@ -80,11 +81,11 @@ VG_HD uint32_t vg_rc32(uint32_t x, int L)
  * compare-select (the integer ALU pipe is the scarce resource of the kernel). */
 VG_HD uint32_t vg_filter_key(uint32_t a, int L, int canon) { return canon ? a * vg_rc32(a, L) : a; }
 
-/* Blocked Bloom filter: one 32-bit word per key, two distinct bits in it.  The word comes
- * from the top of one multiplicative hash, the bit pair from the top of a second one via a
- * 992-entry table of all ordered pairs of distinct positions (shared memory on the device:
- * a table look-up costs no ALU slot, building the mask with shifts costs five). */
-#define VG_MASKTAB 992u
+/* Blocked Bloom filter: one 32-bit word per key, two bits in it.  The word comes from the
+ * top of one multiplicative hash, the two bit positions from the top ten bits of a second
+ * one.  (A shared-memory table of bit pairs was tried: it saves three ALU slots per probe but
+ * its bank conflicts made the L1 data path, already busy with the filter words and the
+ * stream, the bottleneck -- profiles/r1_notes.md.) */
 VG_HD uint32_t vg_hash1(uint32_t key) { return key * 0x9E3779B1u; }
 VG_HD uint32_t vg_hash2(uint32_t key) { return key * 0x85EBCA6Bu; }
 VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
@@ -96,11 +97,10 @@ VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
 #endif
 }
 VG_HD uint32_t vg_filter_word(uint32_t key, uint32_t n_words) { return vg_mulhi(vg_hash1(key), n_words); }
-VG_HD uint32_t vg_mask_index(uint32_t key) { return vg_mulhi(vg_hash2(key), VG_MASKTAB); }
-VG_HD uint32_t vg_mask_entry(uint32_t i) /* i < VG_MASKTAB */
+VG_HD uint32_t vg_filter_mask(uint32_t key)
 {
-	uint32_t b1 = i / 31u, d = i % 31u;
-	return (1u << b1) | (1u << ((b1 + 1u + d) & 31u));
+	const uint32_t h = vg_hash2(key);
+	return (1u << (h >> 27)) | (1u << ((h >> 22) & 31u));
 }
 
 /* exact table: buckets of four 32-bit tags (one LDG.128) with the 16-byte payloads in a

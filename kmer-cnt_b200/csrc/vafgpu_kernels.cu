@@ -19,6 +19,8 @@
  */
 #include "vafgpu_kernels.cuh"
 
+#include <cstdlib>
+
 namespace vafgpu {
 
 #define FULL 0xFFFFFFFFu
@@ -87,6 +89,7 @@ struct AnchorParams {
 	const vg_slot_t *slots;
 	uint32_t bucket_bits;
 	int k, len;
+	uint32_t pf_bytes;     /* L2 prefetch distance ahead of the register pipeline, 0 = off */
 };
 
 __device__ __forceinline__ void l2_prefetch(const void *ptr)
@@ -94,21 +97,61 @@ __device__ __forceinline__ void l2_prefetch(const void *ptr)
 	asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
+/* the stream load: read once, 16 bytes per lane.  VG_STREAM_LOAD picks the cache operator
+ * (tuning knob kept while the kernel is being profiled). */
+#ifndef VG_STREAM_LOAD
+#define VG_STREAM_LOAD 0
+#endif
+__device__ __forceinline__ uint4 ld_stream(const uint4 *ptr)
+{
+#if VG_STREAM_LOAD == 0
+	return __ldcs(ptr); /* ld.global.cs: evict-first in L1 and L2 */
+#elif VG_STREAM_LOAD == 1
+	return __ldg(ptr); /* ld.global.nc */
+#elif VG_STREAM_LOAD == 2
+	return __ldcg(ptr); /* ld.global.cg: L2 only */
+#elif VG_STREAM_LOAD == 3
+	uint4 v;
+	asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+	return v;
+#else
+	return *ptr;
+#endif
+}
+
+/* The exact table is hit at random while gigabytes stream past it: its lines are loaded
+ * with an evict-last L2 policy so the stream (loaded evict-first) does not push them out. */
+__device__ __forceinline__ uint64_t l2_keep_policy()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint4 ldg_keep(const uint4 *ptr, uint64_t pol)
+{
+	uint4 v;
+	asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+	             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+	             : "l"(ptr), "l"(pol));
+	return v;
+}
+
 /* One (candidate, slot) pair whose tag matched, checked by the whole warp: the payload names
- * an oriented pattern k-mer and where the anchor sits in it; lane i compares raw byte i of
- * the stream at q - off with base i of the key.  Returns 1 (on every lane) if the k-mer is
- * there, and *val_out is its counter. */
+ * an oriented pattern k-mer and how far before its end the anchor ends; lane i compares raw
+ * byte i of the k-mer's place in the stream with base i of the key.  Returns 1 (on every
+ * lane) if the k-mer is there, and *val_out is its counter. */
 __device__ __forceinline__ uint32_t verify_coop(const AnchorParams &p, uint32_t slot, uint32_t anchor, uint32_t amask,
                                                 uint64_t q, uint32_t lane, uint32_t *val_out)
 {
-	const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.slots) + slot); /* same address on all lanes */
+	const uint4 raw = ldg_keep(reinterpret_cast<const uint4 *>(p.slots) + slot, l2_keep_policy()); /* same address on all lanes */
 	const uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
-	const uint32_t off = raw.w;
+	const uint32_t t = raw.w;
+	const uint64_t end = q + t; /* the k-mer would occupy [end - k, end) */
 	*val_out = raw.z;
-	if (((uint32_t)(okey >> 2 * off) & amask) != anchor || q < off || q - off + p.k > p.n_bytes) return 0;
+	if (((uint32_t)(okey >> 2 * (p.k - (int)t - p.len)) & amask) != anchor || end < (uint64_t)p.k || end > p.n_bytes) return 0;
 	bool ok = true;
 	if (lane < (uint32_t)p.k) {
-		const uint32_t c = p.bytes[q - off + lane];
+		const uint32_t c = p.bytes[end - p.k + lane];
 		ok = is_base(c) && ((c >> 1) & 3u) == ((uint32_t)(okey >> 2 * lane) & 3u);
 	}
 	return __all_sync(FULL, ok) ? 1u : 0u;
@@ -123,6 +166,7 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
                                                 uint32_t amask, uint32_t lane)
 {
 	const uint32_t bmask = (1u << p.bucket_bits) - 1u;
+	const uint64_t keep = l2_keep_policy();
 	bool active = lane < n;
 	uint2 e = make_uint2(0u, 0u);
 	if (active) e = wq[first + lane];
@@ -132,11 +176,12 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
 	bool my_hit = false;
 	while (__any_sync(FULL, active)) {
 		uint4 t = make_uint4(0u, 0u, 0u, 0u);
-		if (active) t = __ldg(p.tags + b);
-		/* slots of this bucket that carry my tag, up to the first free slot (tag != 0) */
-		const bool z0 = t.x == 0, z1 = z0 || t.y == 0, z2 = z1 || t.z == 0, z3 = z2 || t.w == 0;
-		uint32_t mm = (t.x == tag ? 1u : 0u) | (!z0 && t.y == tag ? 2u : 0u) | (!z1 && t.z == tag ? 4u : 0u) |
-		              (!z2 && t.w == tag ? 8u : 0u);
+		if (active) t = ldg_keep(p.tags + b, keep);
+		/* Slots fill in scan order and are never freed, so the occupied slots of a bucket are
+		 * a prefix of it: a tag (never 0) can only match an occupied slot, and the chain ends
+		 * in this bucket iff its last slot is free. */
+		uint32_t mm = (t.x == tag ? 1u : 0u) | (t.y == tag ? 2u : 0u) | (t.z == tag ? 4u : 0u) | (t.w == tag ? 8u : 0u);
+		const bool ends = t.w == 0;
 		if (!active) mm = 0;
 		uint32_t pend = __ballot_sync(FULL, mm != 0);
 		while (pend) { /* uniform loop over the lanes that have something to verify */
@@ -160,7 +205,7 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
 				}
 			}
 		}
-		if (z3) active = false; /* met a free slot: the chain ends here */
+		if (ends) active = false;
 		else b = (b + 1) & bmask;
 	}
 	/* warp-aggregated counter update: lanes that found the same counter elect one leader */
@@ -176,36 +221,39 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
 
 /* state a warp carries through the stream */
 struct Pipe {
-	uint32_t t;        /* next tile to scan                                       */
-	uint32_t c;        /* this lane's chunk in it                                 */
-	const uint4 *ptr;  /* its address                                             */
-	uint32_t cur;      /* that chunk, packed                                      */
-	uint4 wa, wb;      /* raw chunks of tiles t+1 and t+2: (wa, wb) when !odd, (wb, wa) when odd */
-	bool odd;
-	uint32_t qn;       /* entries in the candidate queue                          */
+	uint32_t t;        /* next tile to scan                                        */
+	uint32_t c;        /* this lane's chunk in it                                  */
+	const uint4 *ptr;  /* its address                                              */
+	uint32_t cur;      /* that chunk, packed                                       */
+	uint32_t carry;    /* lane 31's packed chunk of the previous tile: lane 0's left neighbour */
+	uint4 w0, w1, w2;  /* raw chunks in flight; buffer `phase` holds tile t+1      */
+	uint32_t phase;
+	uint32_t qn;       /* entries in the candidate queue                           */
 };
 
-/* one tile: pack the next tile's chunk out of `w`, scan the current one, then refill `w`
- * with the chunk three tiles on.  The refill is issued at the END, behind the vote/branch of
- * the last probe, into the registers just consumed: the assembler then neither hoists it
- * above the consumer nor needs a copy, and it has two whole tiles to arrive. */
+/* One tile.  `use` holds the raw chunk of tile t+1 (loaded three tiles ago); `fill` is the
+ * buffer consumed by the previous tile and is refilled first thing with tile t+3.  The
+ * anchors of a chunk end at its aligned offsets and reach back into the LEFT neighbour only
+ * (lane-1's chunk, or lane 31's of the previous tile), so nothing in the probes waits for a
+ * load; the only consumer of loaded data is the pack at the very end. */
 template <int S, bool CANON, bool INTERIOR>
-__device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 &w, const uint32_t *filter,
-                                          const uint32_t *masktab, uint2 *wq, uint32_t lane, uint32_t amask)
+__device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 &fill, const uint4 &use,
+                                          const uint32_t *filter, uint2 *wq, uint32_t lane, uint32_t lt_mask,
+                                          uint32_t amask)
 {
 	const uint32_t nw = p.filter_words, last = p.n_chunks - 1;
-	const int rc_shift = 32 - 2 * p.len;
-	if (INTERIOR) l2_prefetch(reinterpret_cast<const uint8_t *>(s.ptr) + 4096); /* this lane's chunk, 8 tiles on */
-	const uint32_t nx = pack16(w);
-	uint32_t right = 0;
-	if (S < 16) { /* an anchor may run into the next chunk: lane+1's, or lane 0's of the next tile */
-		right = __shfl_down_sync(FULL, s.cur, 1);
-		const uint32_t head = __shfl_sync(FULL, nx, 0);
-		if (lane == 31) right = head;
-	}
+	const int L = p.len, rc_shift = 32 - 2 * L;
+	fill = INTERIOR ? ld_stream(s.ptr + 96) : ld_stream(p.chunks + min(s.c + 96, last));
+	if (INTERIOR && p.pf_bytes) l2_prefetch(reinterpret_cast<const uint8_t *>(s.ptr) + p.pf_bytes); /* this lane's chunk, some tiles on */
+	/* one rotate serves both needs: lanes 1..31 get their left neighbour, lane 0 gets lane 31's
+	 * chunk, which is its left neighbour in the NEXT tile */
+	const uint32_t rot = __shfl_sync(FULL, s.cur, (lane + 31) & 31);
+	const uint32_t left = lane == 0 ? s.carry : rot;
 #pragma unroll
 	for (int j = 0; j < 16 / S; ++j) {
-		const uint32_t a = (j == 0 ? s.cur : __funnelshift_r(s.cur, right, 2 * j * S)) & amask;
+		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
+		const int sh = 2 * ((j + 1) * S - L); /* uniform at run time */
+		const uint32_t a = (sh >= 0 ? s.cur >> (sh & 31) : __funnelshift_r(left, s.cur, (sh + 32) & 31)) & amask;
 		uint32_t key = a;
 		if (CANON) { /* a * rc(a): vg_rc32 with the shift hoisted */
 			uint32_t r = __brev(a);
@@ -213,37 +261,44 @@ __device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 
 			key = a * ((r ^ 0xAAAAAAAAu) >> rc_shift);
 		}
 		const uint32_t word = filter[vg_filter_word(key, nw)];
-		const uint32_t m = masktab[vg_mask_index(key)];
-		bool hit = (~word & m) == 0;
+		const uint32_t h2 = vg_hash2(key);
+		const uint32_t m1 = __funnelshift_l(0u, 1u, h2 >> 27), m2 = __funnelshift_l(0u, 1u, h2 >> 22); /* 1 << (x & 31) */
+		bool hit = (~word & (m1 | m2)) == 0;
 		if (!INTERIOR) hit = hit && s.c <= last;
 		if (__any_sync(FULL, hit)) { /* queue the survivors, compacted */
 			const uint32_t votes = __ballot_sync(FULL, hit);
-			if (hit) wq[s.qn + __popc(votes & ((1u << lane) - 1u))] = make_uint2(a, s.c * (16 / S) + j);
+			if (hit) wq[s.qn + __popc(votes & lt_mask)] = make_uint2(a, s.c * (16 / S) + j + 1);
 			s.qn += __popc(votes);
 		}
 	}
-	s.cur = nx;
-	w = INTERIOR ? __ldcs(s.ptr + 96) : __ldcs(p.chunks + min(s.c + 96, last));
+	s.carry = rot; /* only lane 0's copy is ever used */
+	s.cur = pack16(use);
 	++s.t;
 	s.c += 32;
 	s.ptr += 32;
 }
 
 /* The hot loop: scan tiles until the span ends or 32 candidates are queued.  No calls, no
- * table walks.  INTERIOR: every address touched (loads up to tile t1+2, prefetch 8 tiles
- * ahead) is inside the range, so nothing is clamped or predicated. */
+ * table walks.  Three raw buffers rotate by a phase counter instead of by register copies.
+ * INTERIOR: every address touched (loads up to tile t1+2, prefetch some tiles further) is
+ * inside the range, so nothing is clamped or predicated. */
 template <int S, bool CANON, bool INTERIOR>
 __device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, const uint32_t *filter,
-                                           const uint32_t *masktab, uint2 *wq, uint32_t lane, uint32_t amask)
+                                           uint2 *wq, uint32_t lane, uint32_t lt_mask, uint32_t amask)
 {
 	for (;;) {
-		if (!s.odd) {
-			scan_tile<S, CANON, INTERIOR>(p, s, s.wa, filter, masktab, wq, lane, amask);
-			s.odd = true;
+		if (s.phase == 0) {
+			scan_tile<S, CANON, INTERIOR>(p, s, s.w2, s.w0, filter, wq, lane, lt_mask, amask);
+			s.phase = 1;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
-		scan_tile<S, CANON, INTERIOR>(p, s, s.wb, filter, masktab, wq, lane, amask);
-		s.odd = false;
+		if (s.phase == 1) {
+			scan_tile<S, CANON, INTERIOR>(p, s, s.w0, s.w1, filter, wq, lane, lt_mask, amask);
+			s.phase = 2;
+			if (s.t >= t1 || s.qn >= 32) break;
+		}
+		scan_tile<S, CANON, INTERIOR>(p, s, s.w1, s.w2, filter, wq, lane, lt_mask, amask);
+		s.phase = 0;
 		if (s.t >= t1 || s.qn >= 32) break;
 	}
 }
@@ -257,18 +312,17 @@ __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(con
 {
 	extern __shared__ uint32_t s_filter[];
 	const uint32_t nw = p.filter_words;
-	uint32_t *const s_masktab = s_filter + nw;
-	{ /* stage the filter and build the bit-pair table */
+	{ /* stage the filter */
 		const uint4 *src = reinterpret_cast<const uint4 *>(p.filter);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
 		for (uint32_t i = threadIdx.x; i < nw / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-		for (uint32_t i = threadIdx.x; i < VG_MASKTAB; i += blockDim.x) s_masktab[i] = vg_mask_entry(i);
 	}
 	__syncthreads();
 
 	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t amask = vg_mask32(p.len);
-	uint2 *const wq = reinterpret_cast<uint2 *>(s_masktab + VG_MASKTAB) + (threadIdx.x >> 5) * Launch<S>::kQueue;
+	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nw) + (threadIdx.x >> 5) * Launch<S>::kQueue;
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
 	const uint32_t n_warps = gridDim.x * warps_per_cta;
@@ -277,7 +331,7 @@ __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(con
 	Pipe s;
 	s.qn = 0;
 	s.t = 0;
-	s.odd = false;
+	s.phase = 0;
 	uint32_t t1 = 0, span = warp;
 	bool interior = false;
 
@@ -290,21 +344,27 @@ __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(con
 			 * to tile t1+7) lies inside the range.  Otherwise loads are clamped to the last
 			 * chunk: a chunk past the end is never scanned, and as a right neighbour it can only
 			 * create a false candidate, which the bounds check of the verification rejects. */
-			interior = (uint64_t)(t1 + 9) * 32 <= p.n_chunks;
+			interior = (uint64_t)(t1 + 34) * 32 <= p.n_chunks;
 			s.c = s.t * 32 + lane;
 			s.ptr = p.chunks + s.c;
-			if (interior) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * 128); /* 4 KiB */
+			if (interior && p.pf_bytes) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * (p.pf_bytes / 32));
 			/* register pipeline: tile t is scanned while t+1 is being packed and t+2 is in
 			 * flight; the L2 prefetch runs 8 tiles ahead of that */
-			s.cur = pack16(__ldcs(p.chunks + min(s.c, last)));
-			s.wa = __ldcs(p.chunks + min(s.c + 32, last));
-			s.wb = __ldcs(p.chunks + min(s.c + 64, last));
-			s.odd = false;
+			s.cur = pack16(ld_stream(p.chunks + min(s.c, last)));
+			s.w0 = ld_stream(p.chunks + min(s.c + 32, last));
+			s.w1 = ld_stream(p.chunks + min(s.c + 64, last));
+			s.phase = 0;
+			/* the chunk before the span: the last one of the previous span, or of the previous
+			 * launch range; nothing ('\n's) at the very start of the stream */
+			const uint32_t c0 = s.t * 32;
+			uint4 before = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+			if (c0 > 0 || p.range_lo > 0) before = __ldg(p.chunks + c0 - 1); /* chunks[-1] exists when range_lo > 0 */
+			s.carry = pack16(before);
 		}
 		const bool finished = s.t >= t1; /* no span left */
 		if (!finished) {
-			if (interior) scan_tiles<S, CANON, true>(p, s, t1, s_filter, s_masktab, wq, lane, amask);
-			else scan_tiles<S, CANON, false>(p, s, t1, s_filter, s_masktab, wq, lane, amask);
+			if (interior) scan_tiles<S, CANON, true>(p, s, t1, s_filter, wq, lane, lt_mask, amask);
+			else scan_tiles<S, CANON, false>(p, s, t1, s_filter, wq, lane, lt_mask, amask);
 		}
 		if (s.qn >= 32 || (finished && s.qn)) { /* the one place candidates are resolved */
 			const uint32_t n = min(s.qn, 32u);
@@ -388,7 +448,7 @@ static cudaError_t launch_one(const AnchorParams &p0, uint32_t filter_words, int
 {
 	AnchorParams p = p0;
 	const int threads = Launch<S>::kThreads;
-	const size_t smem = (size_t)filter_words * 4 + VG_MASKTAB * 4 + Launch<S>::kQueueBytes;
+	const size_t smem = (size_t)filter_words * 4 + Launch<S>::kQueueBytes;
 	static bool opted_in[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -434,6 +494,11 @@ cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream)
 		p.bucket_bits = a.bucket_bits;
 		p.k = a.k;
 		p.len = a.len;
+		{
+			static const char *env = getenv("VAFGPU_PF_TILES"); /* tuning knob: tiles of L2 prefetch lead, <= 32 */
+			int tiles = env ? atoi(env) : 8;
+			p.pf_bytes = (uint32_t)(tiles < 0 ? 0 : tiles > 32 ? 32 : tiles) * 512u;
+		}
 		cudaError_t e;
 #define GO(S) e = a.canon ? launch_one<S, true>(p, a.filter_words, n_sm, stream) : launch_one<S, false>(p, a.filter_words, n_sm, stream)
 		switch (a.stride) {

@@ -1,11 +1,14 @@
 /*
  * vafgpu_tables.cpp -- see vafgpu_tables.hpp.
  *
- * Why anchors.  A pattern k-mer occurring at stream offset p covers the aligned offset
- * q = ceil(p / S) * S and, because L <= k - S + 1, the whole anchor [q, q + L).  So it is
- * enough to look at one L-mer every S bases of the stream: if it is the anchor some
- * oriented pattern k-mer carries at offset o = q - p (0 <= o < S), the k-mer at q - o is
- * compared in full.  Every occurrence has exactly one (q, o), so nothing is counted twice.
+ * Why anchors.  A pattern k-mer occupying stream offsets [p, e), e = p + k, covers the
+ * aligned offset q = floor(e / S) * S and, because L <= k - S + 1, the whole L-mer
+ * [q - L, q) that ENDS there.  So it is enough to look at one L-mer every S bases of the
+ * stream: if it is the anchor some oriented pattern k-mer carries t = e - q bases before its
+ * end (0 <= t < S), the k-mer ending at q + t is compared in full.  Every occurrence has
+ * exactly one (q, t), so nothing is counted twice.  (Anchors end at aligned offsets, rather
+ * than start there, so that a chunk of the stream only needs its LEFT neighbour, which the
+ * kernel has already seen, never the next one, which may still be in flight.)
  * Both orientations of every canonical key are filed, which makes the forward k-mer of
  * the stream sufficient: canonical(x) is in the reference's map iff x or rc(x) is one of
  * its keys (vaf-counter.c:142-146,224,236).
@@ -94,9 +97,9 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 		for (int orient = 0; orient < 2; ++orient) {
 			uint64_t ok = orient ? r : f;
 			if (orient && r == f) break; /* its own reverse complement (even k only) */
-			for (int o = 0; o < S; ++o) {
-				uint32_t a = (uint32_t)(ok >> 2 * o) & amask;
-				items.push_back({ok, vals[i], (uint32_t)o, a});
+			for (int t = 0; t < S; ++t) { /* anchor = bases [k-t-L, k-t) of the oriented k-mer */
+				uint32_t a = (uint32_t)(ok >> 2 * (k - t - L)) & amask;
+				items.push_back({ok, vals[i], (uint32_t)t, a});
 				canon.insert(vg_filter_key(a, L, 1));
 				plain.insert(a);
 			}
@@ -116,11 +119,12 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	uint32_t nw = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, VG_MIN_FILTER_WORDS), budget);
 	nw = (nw + 3u) & ~3u;
 	out.filter.assign(nw, 0);
-	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_mask_entry(vg_mask_index(key));
+	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_filter_mask(key);
 
-	/* exact table at <= 1/3 load, buckets of four slots */
+	/* exact table at <= 1/6 load, buckets of four slots: a full home bucket (a second L2
+	 * round trip for the whole warp) is then rare */
 	uint32_t bits = 2;
-	while ((4ull << bits) < (uint64_t)items.size() * 3) ++bits;
+	while ((4ull << bits) < (uint64_t)items.size() * 6) ++bits;
 	out.bucket_bits = bits;
 	const size_t n_slots = (size_t)4 << bits;
 	out.tags.assign(n_slots, 0);

@@ -65,14 +65,15 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 	static const uint8_t NL[16] = {10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10};
 	for (uint64_t c = 0; c < n_chunks; ++c) {
 		uint32_t cur = pack16(bytes + 16 * c);
-		uint32_t nxt = pack16(c + 1 < n_chunks ? bytes + 16 * (c + 1) : NL);
+		uint32_t left = pack16(c > 0 ? bytes + 16 * (c - 1) : NL);
 		for (int j = 0; j < 16 / S; ++j) {
-			uint32_t a = (j == 0 ? cur : funnel_r(cur, nxt, 2 * j * S)) & amask;
+			const int s0 = (j + 1) * S - L; /* anchor = bases [s0, s0 + L) relative to the chunk */
+			uint32_t a = (s0 >= 0 ? cur >> 2 * s0 : funnel_r(left, cur, 2 * (s0 + 16))) & amask;
 			uint32_t key = vg_filter_key(a, L, t.canon);
-			uint32_t m = vg_mask_entry(vg_mask_index(key));
+			uint32_t m = vg_filter_mask(key);
 			if ((t.filter[vg_filter_word(key, nw)] & m) != m) continue;
 			++n_cand;
-			uint64_t q = 16 * c + (uint64_t)j * S;
+			uint64_t q = 16 * c + (uint64_t)(j + 1) * S; /* aligned end of the anchor */
 			bool open_slot = false;
 			for (uint32_t bk = vg_bucket_home(a, t.bucket_bits); !open_slot; bk = (bk + 1) & bmask) {
 				for (int i = 0; i < 4 && !open_slot; ++i) {
@@ -80,8 +81,9 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 					if (tag == 0) { open_slot = true; break; }
 					if (tag != vg_tag(a)) continue;
 					const vg_slot_t &e = t.slots[(size_t)bk * 4 + i];
-					if (((uint32_t)(e.okey >> 2 * e.off) & amask) != a || q < e.off || q - e.off + k > n_bytes) continue;
-					const uint8_t *b = bytes + (q - e.off);
+					const uint64_t end = q + e.off;
+					if (((uint32_t)(e.okey >> 2 * (k - e.off - L)) & amask) != a || end < (uint64_t)k || end > n_bytes) continue;
+					const uint8_t *b = bytes + (end - k);
 					uint64_t km = 0;
 					bool ok = true;
 					for (int x = 0; x < k; ++x) {

@@ -27,7 +27,7 @@
 /* launch geometry of the anchor kernel for stride S, shared with the table builder because
  * the candidate queues and the filter split one shared-memory budget */
 #define VG_THREADS(S) ((S) >= 4 ? 1024 : 256)              /* tiny k: fewer warps, deeper queues   */
-#define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)))         /* per warp: a drain's leftovers + one tile */
+#define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)) + 32)    /* per warp: a drain's leftovers + one tile, + 32 tag matches awaiting verification */
 #define VG_QUEUE_BYTES(S) ((VG_THREADS(S) / 32) * VG_QUEUE_ENTRIES(S) * 8)
 #define VG_FILTER_BUDGET_WORDS(S) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S)) / 4) & ~3))
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t pack16(uint4 w)
  * can produce on top of the < 32 entries left by the last drain. */
 template <int S> struct Launch {
 	static constexpr int kThreads = VG_THREADS(S);
-	static constexpr int kQueue = VG_QUEUE_ENTRIES(S);
+	static constexpr int kQueue = VG_QUEUE_ENTRIES(S); /* candidates + 32 verify entries */
 	static constexpr int kQueueBytes = VG_QUEUE_BYTES(S);
 };
 
@@ -136,85 +136,78 @@ __device__ __forceinline__ uint4 ldg_keep(const uint4 *ptr, uint64_t pol)
 	return v;
 }
 
-/* One (candidate, slot) pair whose tag matched, checked by the whole warp: the payload names
- * an oriented pattern k-mer and how far before its end the anchor ends; lane i compares raw
- * byte i of the k-mer's place in the stream with base i of the key.  Returns 1 (on every
- * lane) if the k-mer is there, and *val_out is its counter. */
-__device__ __forceinline__ uint32_t verify_coop(const AnchorParams &p, uint32_t slot, uint32_t anchor, uint32_t amask,
-                                                uint64_t q, uint32_t lane, uint32_t *val_out)
+/* Second stage: up to 32 (slot, anchor position) pairs whose tag matched, one per lane.  The
+ * payload names an oriented pattern k-mer and how far before its end the anchor ends; the k
+ * raw bytes of that place in the stream decide.  Batching them makes the two dependent L2
+ * round trips (payload, then bytes) happen once per 32 verifications instead of once each,
+ * and lets the counter update aggregate over the warp. */
+template <int S>
+__device__ __forceinline__ uint32_t verify_batch(const AnchorParams &p, const uint2 *vq, uint32_t n, uint32_t lane)
 {
-	const uint4 raw = ldg_keep(reinterpret_cast<const uint4 *>(p.slots) + slot, l2_keep_policy()); /* same address on all lanes */
-	const uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
-	const uint32_t t = raw.w;
-	const uint64_t end = q + t; /* the k-mer would occupy [end - k, end) */
-	*val_out = raw.z;
-	if (((uint32_t)(okey >> 2 * (p.k - (int)t - p.len)) & amask) != anchor || end < (uint64_t)p.k || end > p.n_bytes) return 0;
-	bool ok = true;
-	if (lane < (uint32_t)p.k) {
-		const uint32_t c = p.bytes[end - p.k + lane];
-		ok = is_base(c) && ((c >> 1) & 3u) == ((uint32_t)(okey >> 2 * lane) & 3u);
+	bool ok = false;
+	uint32_t val = 0;
+	if (lane < n) {
+		const uint2 e = vq[lane];
+		const uint4 raw = ldg_keep(reinterpret_cast<const uint4 *>(p.slots) + e.x, l2_keep_policy());
+		const uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
+		const uint64_t end = p.range_lo + (uint64_t)e.y * (uint32_t)S + raw.w; /* the k-mer would occupy [end - k, end) */
+		val = raw.z;
+		if (end >= (uint64_t)p.k && end <= p.n_bytes) {
+			/* if all k bases agree, the anchor (whose tag may lack a bit) agrees as well */
+			const uint8_t *b = p.bytes + (end - p.k);
+			ok = true;
+			for (int i = 0; i < p.k; ++i) {
+				const uint32_t c = b[i];
+				ok = ok && is_base(c) && ((c >> 1) & 3u) == ((uint32_t)(okey >> 2 * i) & 3u);
+			}
+		}
 	}
-	return __all_sync(FULL, ok) ? 1u : 0u;
+	/* warp-aggregated counter update: lanes that found the same counter elect one leader */
+	const uint32_t have = __ballot_sync(FULL, ok);
+	if (ok) {
+		const uint32_t peers = __match_any_sync(have, val);
+		if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&p.counts[val], (uint32_t)__popc(peers));
+	}
+	return __popc(have);
 }
 
-/* Resolve n <= 32 queued survivors of the filter, one per lane: fetch the anchor's home
- * bucket (four tags, one 16-byte load from L2); a free slot ends the search, a matching tag
- * (rare: the anchor really is one a pattern carries) is verified by the whole warp.
- * Returns the number of k-mer hits (same on every lane). */
+/* First stage: resolve n <= 32 queued survivors of the filter, one per lane.  Fetch the
+ * anchor's home bucket (four tags, one 16-byte load from L2).  Slots fill in scan order and
+ * are never freed, so the occupied slots of a bucket are a prefix of it: a tag (never 0) can
+ * only match an occupied slot, and the chain ends in this bucket iff its last slot is free.
+ * A matching tag (rare: the anchor really is one a pattern carries) goes to the verify queue. */
 template <int S>
 __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uint2 *wq, uint32_t first, uint32_t n,
-                                                uint32_t amask, uint32_t lane)
+                                                uint2 *vq, uint32_t &vn, uint32_t lane, uint32_t lt_mask)
 {
 	const uint32_t bmask = (1u << p.bucket_bits) - 1u;
 	const uint64_t keep = l2_keep_policy();
 	bool active = lane < n;
 	uint2 e = make_uint2(0u, 0u);
 	if (active) e = wq[first + lane];
-	const uint32_t anchor = e.x, tag = vg_tag(anchor);
-	uint32_t b = vg_bucket_home(anchor, p.bucket_bits);
-	uint32_t hits = 0, my_val = 0;
-	bool my_hit = false;
+	const uint32_t tag = vg_tag(e.x);
+	uint32_t b = vg_bucket_home(e.x, p.bucket_bits), hits = 0;
 	while (__any_sync(FULL, active)) {
 		uint4 t = make_uint4(0u, 0u, 0u, 0u);
 		if (active) t = ldg_keep(p.tags + b, keep);
-		/* Slots fill in scan order and are never freed, so the occupied slots of a bucket are
-		 * a prefix of it: a tag (never 0) can only match an occupied slot, and the chain ends
-		 * in this bucket iff its last slot is free. */
-		uint32_t mm = (t.x == tag ? 1u : 0u) | (t.y == tag ? 2u : 0u) | (t.z == tag ? 4u : 0u) | (t.w == tag ? 8u : 0u);
-		const bool ends = t.w == 0;
-		if (!active) mm = 0;
-		uint32_t pend = __ballot_sync(FULL, mm != 0);
-		while (pend) { /* uniform loop over the lanes that have something to verify */
-			const int src = __ffs(pend) - 1;
-			pend &= pend - 1;
-			uint32_t smm = __shfl_sync(FULL, mm, src);
-			const uint32_t sb = __shfl_sync(FULL, b, src);
-			const uint32_t sa = __shfl_sync(FULL, anchor, src);
-			const uint64_t sq = p.range_lo + (uint64_t)__shfl_sync(FULL, e.y, src) * (uint32_t)S;
-			while (smm) {
-				const int i = __ffs(smm) - 1;
-				smm &= smm - 1;
-				uint32_t val;
-				if (verify_coop(p, sb * 4 + i, sa, amask, sq, lane, &val)) {
-					++hits;
-					if (lane == (uint32_t)src) { /* remember it on the lane that found it */
-						if (my_hit) atomicAdd(&p.counts[my_val], 1u);
-						my_hit = true;
-						my_val = val;
-					}
+		const uint32_t tg[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const bool m = active && tg[i] == tag;
+			if (__any_sync(FULL, m)) {
+				const uint32_t votes = __ballot_sync(FULL, m);
+				if (vn + __popc(votes) > 32) { /* make room: run a full batch first */
+					__syncwarp();
+					hits += verify_batch<S>(p, vq, vn, lane);
+					vn = 0;
+					__syncwarp();
 				}
+				if (m) vq[vn + __popc(votes & lt_mask)] = make_uint2(b * 4 + i, e.y);
+				vn += __popc(votes);
 			}
 		}
-		if (ends) active = false;
+		if (t.w == 0) active = false;
 		else b = (b + 1) & bmask;
-	}
-	/* warp-aggregated counter update: lanes that found the same counter elect one leader */
-	const uint32_t have = __ballot_sync(FULL, my_hit);
-	if (have) {
-		if (my_hit) {
-			const uint32_t peers = __match_any_sync(have, my_val);
-			if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&p.counts[my_val], (uint32_t)__popc(peers));
-		}
 	}
 	return hits;
 }
@@ -323,6 +316,8 @@ __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(con
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t amask = vg_mask32(p.len);
 	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nw) + (threadIdx.x >> 5) * Launch<S>::kQueue;
+	uint2 *const vq = wq + Launch<S>::kQueue - 32; /* the last 32 entries: tag matches awaiting verification */
+	uint32_t vn = 0;
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
 	const uint32_t n_warps = gridDim.x * warps_per_cta;
@@ -371,10 +366,11 @@ __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(con
 			s.qn -= n;
 			n_cand += n;
 			__syncwarp();
-			n_hits += drain_queue<S>(p, wq, s.qn, n, amask, lane);
+			n_hits += drain_queue<S>(p, wq, s.qn, n, vq, vn, lane, lt_mask);
 			__syncwarp();
 		} else if (finished) break;
 	}
+	if (vn) n_hits += verify_batch<S>(p, vq, vn, lane);
 	if (lane == 0 && (n_cand | n_hits)) {
 		atomicAdd(&p.stats[ST_CANDIDATES], (unsigned long long)n_cand);
 		atomicAdd(&p.stats[ST_HITS], (unsigned long long)n_hits);

@@ -29,7 +29,7 @@
 #define VG_THREADS(S) ((S) >= 4 ? 1024 : 256)              /* tiny k: fewer warps, deeper queues   */
 #define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)) + 32)    /* per warp: a drain's leftovers + one tile, + 32 tag matches awaiting verification */
 #define VG_QUEUE_BYTES(S) ((VG_THREADS(S) / 32) * VG_QUEUE_ENTRIES(S) * 8)
-#define VG_FILTER_BUDGET_WORDS(S) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S)) / 4) & ~3))
+#define VG_FILTER_BUDGET_WORDS(S) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S) - 128) / 4) & ~3))
 
 /* exact-table slot: an oriented pattern k-mer (stream encoding) with the offset of the
  * anchor it is filed under.  16 bytes so one LDG.128 fetches it. */
@@ -83,9 +83,9 @@ VG_HD uint32_t vg_filter_key(uint32_t a, int L, int canon) { return canon ? a * 
 
 /* Blocked Bloom filter: one 32-bit word per key, two bits in it.  The word comes from the
  * top of one multiplicative hash, the two bit positions from the top ten bits of a second
- * one.  (A shared-memory table of bit pairs was tried: it saves three ALU slots per probe but
- * its bank conflicts made the L1 data path, already busy with the filter words and the
- * stream, the bottleneck -- profiles/r1_notes.md.) */
+ * and a third one.  On the device 1 << b comes from a 32-word shared-memory table: bank b
+ * holds entry b, so the look-up never conflicts, and unlike a shift it costs no slot of the
+ * integer ALU pipe, the kernel's scarcest resource. */
 VG_HD uint32_t vg_hash1(uint32_t key) { return key * 0x9E3779B1u; }
 VG_HD uint32_t vg_hash2(uint32_t key) { return key * 0x85EBCA6Bu; }
 VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
@@ -97,10 +97,11 @@ VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
 #endif
 }
 VG_HD uint32_t vg_filter_word(uint32_t key, uint32_t n_words) { return vg_mulhi(vg_hash1(key), n_words); }
+VG_HD uint32_t vg_hash3(uint32_t h2) { return h2 * 0xC2B2AE35u; }
 VG_HD uint32_t vg_filter_mask(uint32_t key)
 {
-	const uint32_t h = vg_hash2(key);
-	return (1u << (h >> 27)) | (1u << ((h >> 22) & 31u));
+	const uint32_t h2 = vg_hash2(key);
+	return (1u << (h2 >> 27)) | (1u << (vg_hash3(h2) >> 27));
 }
 
 /* exact table: buckets of four 32-bit tags (one LDG.128) with the 16-byte payloads in a

@@ -90,6 +90,9 @@ struct AnchorParams {
 	uint32_t bucket_bits;
 	int k, len;
 	uint32_t pf_bytes;     /* L2 prefetch distance ahead of the register pipeline, 0 = off */
+	uint32_t c4, c32;      /* the constants 4 and 32, passed as data so that index scaling and
+	                          top-5-bit extraction compile to IMAD / IMAD.HI (FMA pipe) instead of
+	                          LEA / SHF (integer ALU pipe) */
 };
 
 __device__ __forceinline__ void l2_prefetch(const void *ptr)
@@ -190,21 +193,22 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
 	while (__any_sync(FULL, active)) {
 		uint4 t = make_uint4(0u, 0u, 0u, 0u);
 		if (active) t = ldg_keep(p.tags + b, keep);
-		const uint32_t tg[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			const bool m = active && tg[i] == tag;
-			if (__any_sync(FULL, m)) {
-				const uint32_t votes = __ballot_sync(FULL, m);
-				if (vn + __popc(votes) > 32) { /* make room: run a full batch first */
-					__syncwarp();
-					hits += verify_batch<S>(p, vq, vn, lane);
-					vn = 0;
-					__syncwarp();
-				}
-				if (m) vq[vn + __popc(votes & lt_mask)] = make_uint2(b * 4 + i, e.y);
-				vn += __popc(votes);
+		uint32_t mm = (t.x == tag ? 1u : 0u) | (t.y == tag ? 2u : 0u) | (t.z == tag ? 4u : 0u) | (t.w == tag ? 8u : 0u);
+		if (!active) mm = 0;
+		while (__any_sync(FULL, mm != 0)) { /* rare: queue one matching slot per lane and round */
+			const bool m = mm != 0;
+			const uint32_t votes = __ballot_sync(FULL, m);
+			if (vn + __popc(votes) > 32) { /* make room: run a full batch first */
+				__syncwarp();
+				hits += verify_batch<S>(p, vq, vn, lane);
+				vn = 0;
+				__syncwarp();
 			}
+			if (m) {
+				vq[vn + __popc(votes & lt_mask)] = make_uint2(b * 4 + (uint32_t)(__ffs(mm) - 1), e.y);
+				mm &= mm - 1;
+			}
+			vn += __popc(votes);
 		}
 		if (t.w == 0) active = false;
 		else b = (b + 1) & bmask;
@@ -224,18 +228,27 @@ struct Pipe {
 	uint32_t qn;       /* entries in the candidate queue                           */
 };
 
+/* shared-memory word `idx` of the table at shared address `base`; idx * four is an IMAD */
+__device__ __forceinline__ uint32_t lds_word(uint32_t base, uint32_t idx, uint32_t four)
+{
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(idx * four + base));
+	return v;
+}
+
 /* One tile.  `use` holds the raw chunk of tile t+1 (loaded three tiles ago); `fill` is the
  * buffer consumed by the previous tile and is refilled first thing with tile t+3.  The
  * anchors of a chunk end at its aligned offsets and reach back into the LEFT neighbour only
  * (lane-1's chunk, or lane 31's of the previous tile), so nothing in the probes waits for a
- * load; the only consumer of loaded data is the pack at the very end. */
-template <int S, bool CANON, bool INTERIOR>
+ * load; the only consumer of loaded data is the pack at the very end.
+ *   LS  anchor length fixed at compile time (0 = take it from the parameters) */
+template <int S, bool CANON, int LS, bool INTERIOR>
 __device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 &fill, const uint4 &use,
-                                          const uint32_t *filter, uint2 *wq, uint32_t lane, uint32_t lt_mask,
-                                          uint32_t amask)
+                                          uint32_t filter, uint32_t bits, uint2 *wq, uint32_t lane, uint32_t lt_mask)
 {
 	const uint32_t nw = p.filter_words, last = p.n_chunks - 1;
-	const int L = p.len, rc_shift = 32 - 2 * L;
+	const int L = LS ? LS : p.len;
+	const uint32_t amask = vg_mask32(L);
 	fill = INTERIOR ? ld_stream(s.ptr + 96) : ld_stream(p.chunks + min(s.c + 96, last));
 	if (INTERIOR && p.pf_bytes) l2_prefetch(reinterpret_cast<const uint8_t *>(s.ptr) + p.pf_bytes); /* this lane's chunk, some tiles on */
 	/* one rotate serves both needs: lanes 1..31 get their left neighbour, lane 0 gets lane 31's
@@ -245,20 +258,24 @@ __device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 
 #pragma unroll
 	for (int j = 0; j < 16 / S; ++j) {
 		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
-		const int sh = 2 * ((j + 1) * S - L); /* uniform at run time */
-		const uint32_t a = (sh >= 0 ? s.cur >> (sh & 31) : __funnelshift_r(left, s.cur, (sh + 32) & 31)) & amask;
+		const int sh = 2 * ((j + 1) * S - L);
+		uint32_t a = sh >= 0 ? s.cur >> (sh & 31) : __funnelshift_r(left, s.cur, (sh + 32) & 31);
+		if (L < 16) a &= amask;
 		uint32_t key = a;
-		if (CANON) { /* a * rc(a): vg_rc32 with the shift hoisted */
+		if (CANON) { /* a * rc(a), see vg_rc32 */
 			uint32_t r = __brev(a);
 			r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
-			key = a * ((r ^ 0xAAAAAAAAu) >> rc_shift);
+			key = a * ((r ^ 0xAAAAAAAAu) >> (32 - 2 * L));
 		}
-		const uint32_t word = filter[vg_filter_word(key, nw)];
+		const uint32_t word = lds_word(filter, vg_filter_word(key, nw), p.c4);
 		const uint32_t h2 = vg_hash2(key);
-		const uint32_t m1 = __funnelshift_l(0u, 1u, h2 >> 27), m2 = __funnelshift_l(0u, 1u, h2 >> 22); /* 1 << (x & 31) */
+		const uint32_t m1 = lds_word(bits, __umulhi(h2, p.c32), p.c4);              /* 1 << (h2 >> 27) */
+		const uint32_t m2 = lds_word(bits, __umulhi(vg_hash3(h2), p.c32), p.c4);
 		bool hit = (~word & (m1 | m2)) == 0;
 		if (!INTERIOR) hit = hit && s.c <= last;
-		if (__any_sync(FULL, hit)) { /* queue the survivors, compacted */
+		/* queue the survivors, compacted.  Large panels: nearly every vote has a survivor, so
+		 * the branch around the push is not worth its two instructions */
+		if (CANON || __any_sync(FULL, hit)) {
 			const uint32_t votes = __ballot_sync(FULL, hit);
 			if (hit) wq[s.qn + __popc(votes & lt_mask)] = make_uint2(a, s.c * (16 / S) + j + 1);
 			s.qn += __popc(votes);
@@ -275,22 +292,22 @@ __device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 
  * table walks.  Three raw buffers rotate by a phase counter instead of by register copies.
  * INTERIOR: every address touched (loads up to tile t1+2, prefetch some tiles further) is
  * inside the range, so nothing is clamped or predicated. */
-template <int S, bool CANON, bool INTERIOR>
-__device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, const uint32_t *filter,
-                                           uint2 *wq, uint32_t lane, uint32_t lt_mask, uint32_t amask)
+template <int S, bool CANON, int LS, bool INTERIOR>
+__device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, uint32_t filter, uint32_t bits,
+                                           uint2 *wq, uint32_t lane, uint32_t lt_mask)
 {
 	for (;;) {
 		if (s.phase == 0) {
-			scan_tile<S, CANON, INTERIOR>(p, s, s.w2, s.w0, filter, wq, lane, lt_mask, amask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w2, s.w0, filter, bits, wq, lane, lt_mask);
 			s.phase = 1;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
 		if (s.phase == 1) {
-			scan_tile<S, CANON, INTERIOR>(p, s, s.w0, s.w1, filter, wq, lane, lt_mask, amask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w0, s.w1, filter, bits, wq, lane, lt_mask);
 			s.phase = 2;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
-		scan_tile<S, CANON, INTERIOR>(p, s, s.w1, s.w2, filter, wq, lane, lt_mask, amask);
+		scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w1, s.w2, filter, bits, wq, lane, lt_mask);
 		s.phase = 0;
 		if (s.t >= t1 || s.qn >= 32) break;
 	}
@@ -300,22 +317,24 @@ __device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint3
  * of 16 bytes = one 128-bit load per lane).
  *   CANON  the filter holds strand-symmetric keys, which halves its load for large panels;
  *          small panels file both orientations and skip the reverse complement. */
-template <int S, bool CANON>
+template <int S, bool CANON, int LS>
 __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(const __grid_constant__ AnchorParams p)
 {
-	extern __shared__ uint32_t s_filter[];
+	extern __shared__ uint32_t s_filter[]; /* filter words | 32-word bit table | candidate queues */
 	const uint32_t nw = p.filter_words;
 	{ /* stage the filter */
 		const uint4 *src = reinterpret_cast<const uint4 *>(p.filter);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
 		for (uint32_t i = threadIdx.x; i < nw / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+		if (threadIdx.x < 32) s_filter[nw + threadIdx.x] = 1u << threadIdx.x;
 	}
 	__syncthreads();
+	const uint32_t filter_sa = (uint32_t)__cvta_generic_to_shared(s_filter);
+	const uint32_t bits_sa = filter_sa + nw * 4;
 
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	const uint32_t amask = vg_mask32(p.len);
-	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nw) + (threadIdx.x >> 5) * Launch<S>::kQueue;
+	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nw + 32) + (threadIdx.x >> 5) * Launch<S>::kQueue;
 	uint2 *const vq = wq + Launch<S>::kQueue - 32; /* the last 32 entries: tag matches awaiting verification */
 	uint32_t vn = 0;
 	const uint32_t warps_per_cta = blockDim.x >> 5;
@@ -358,8 +377,8 @@ __global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(con
 		}
 		const bool finished = s.t >= t1; /* no span left */
 		if (!finished) {
-			if (interior) scan_tiles<S, CANON, true>(p, s, t1, s_filter, wq, lane, lt_mask, amask);
-			else scan_tiles<S, CANON, false>(p, s, t1, s_filter, wq, lane, lt_mask, amask);
+			if (interior) scan_tiles<S, CANON, LS, true>(p, s, t1, filter_sa, bits_sa, wq, lane, lt_mask);
+			else scan_tiles<S, CANON, LS, false>(p, s, t1, filter_sa, bits_sa, wq, lane, lt_mask);
 		}
 		if (s.qn >= 32 || (finished && s.qn)) { /* the one place candidates are resolved */
 			const uint32_t n = min(s.qn, 32u);
@@ -439,17 +458,17 @@ __global__ void __launch_bounds__(256) recipe_scan_kernel(const ScanArgs a)
 /* ------------------------------------------------------------------------------------ */
 /* launchers                                                                              */
 
-template <int S, bool CANON>
+template <int S, bool CANON, int LS>
 static cudaError_t launch_one(const AnchorParams &p0, uint32_t filter_words, int n_sm, cudaStream_t stream)
 {
 	AnchorParams p = p0;
 	const int threads = Launch<S>::kThreads;
-	const size_t smem = (size_t)filter_words * 4 + Launch<S>::kQueueBytes;
+	const size_t smem = (size_t)filter_words * 4 + 128 + Launch<S>::kQueueBytes;
 	static bool opted_in[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 64 && !opted_in[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(anchor_scan_kernel<S, CANON>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		cudaError_t e = cudaFuncSetAttribute(anchor_scan_kernel<S, CANON, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                     VG_SMEM_BUDGET);
 		if (e != cudaSuccess) return e;
 		opted_in[dev] = true;
@@ -460,7 +479,7 @@ static cudaError_t launch_one(const AnchorParams &p0, uint32_t filter_words, int
 	p.n_spans = (p.n_tiles + p.tiles_per_span - 1) / p.tiles_per_span;
 	uint32_t ctas = (p.n_spans + (threads / 32) - 1) / (threads / 32);
 	if (ctas > (uint32_t)n_sm) ctas = (uint32_t)n_sm;
-	anchor_scan_kernel<S, CANON><<<ctas, threads, smem, stream>>>(p);
+	anchor_scan_kernel<S, CANON, LS><<<ctas, threads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 
@@ -496,13 +515,16 @@ cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream)
 			p.pf_bytes = (uint32_t)(tiles < 0 ? 0 : tiles > 32 ? 32 : tiles) * 512u;
 		}
 		cudaError_t e;
-#define GO(S) e = a.canon ? launch_one<S, true>(p, a.filter_words, n_sm, stream) : launch_one<S, false>(p, a.filter_words, n_sm, stream)
+		p.c4 = 4;
+		p.c32 = 32;
+		/* the headline plans (k = 15, 21, 31) get the anchor length as a compile-time constant */
+#define GO(S, LS) e = a.canon ? launch_one<S, true, LS>(p, a.filter_words, n_sm, stream) : launch_one<S, false, LS>(p, a.filter_words, n_sm, stream)
 		switch (a.stride) {
-		case 1: GO(1); break;
-		case 2: GO(2); break;
-		case 4: GO(4); break;
-		case 8: GO(8); break;
-		case 16: GO(16); break;
+		case 1: GO(1, 0); break;
+		case 2: GO(2, 0); break;
+		case 4: if (a.len == 12) GO(4, 12); else GO(4, 0); break;
+		case 8: if (a.len == 14) GO(8, 14); else GO(8, 0); break;
+		case 16: if (a.len == 16) GO(16, 16); else GO(16, 0); break;
 		default: return cudaErrorInvalidValue;
 		}
 #undef GO

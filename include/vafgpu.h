@@ -43,6 +43,7 @@ extern "C" {
                                         with an NCCL all-reduce                            */
 
 typedef struct vafgpu_ctx vafgpu_ctx;
+typedef struct vafgpu_producer vafgpu_producer;
 
 typedef struct vafgpu_stats {
 	uint64_t n_reads;       /* reads accepted by vafgpu_add_read (len >= k)               */
@@ -87,9 +88,29 @@ int vafgpu_create(vafgpu_ctx **ctx, int k, const uint64_t *canon_keys, const uin
  * counted in the statistics, as in vaf-counter.c:494.  Bytes are canonicalised to
  * {A,C,G,T,N} while they are copied: for offsets below (len & ~15) by the reference's
  * low-nibble rule, for the tail by its strict table, so that the device sees exactly the
- * bases the Makefile-built reference sees.  One producer thread per context.
+ * bases the Makefile-built reference sees.  vafgpu_add_read and vafgpu_submit_stream share
+ * one implicit producer: call them from one thread at a time; reader threads that run side
+ * by side each use a producer of their own (below).
  */
 int vafgpu_add_read(vafgpu_ctx *ctx, const char *seq, size_t len);
+
+/*
+ * Parallel ingest: one producer per reader thread (one per input file or file slice).
+ * Replaces the single kseq reader of step 0 (vaf-counter.c:486-517; the reference parses
+ * with one thread, which bounds it end to end).  A producer packs its reads into a staging
+ * block of its own, taken from the context's pool (a producer waits while every block is
+ * being filled or is in flight: that back-pressure stands in for kt_pipeline's "at most
+ * three blocks", kthread.c:130-159); blocks go to the devices round-robin in the order
+ * they are taken.  Counting is additive, so the result does not depend on how reads are
+ * spread over producers.  Each producer is used by one thread at a time; different
+ * producers may be used concurrently.  vafgpu_producer_flush submits the partly filled
+ * block and adds the producer's read/base totals to the context's statistics; every
+ * producer must be flushed (or destroyed) before vafgpu_finish is called.
+ */
+int vafgpu_producer_create(vafgpu_ctx *ctx, vafgpu_producer **producer);
+int vafgpu_producer_add_read(vafgpu_producer *producer, const char *seq, size_t len);
+int vafgpu_producer_flush(vafgpu_producer *producer);
+int vafgpu_producer_destroy(vafgpu_producer *producer); /* flushes first */
 
 /*
  * Submit a host buffer that is already in stream form: reads separated by '\n', bytes

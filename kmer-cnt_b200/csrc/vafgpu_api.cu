@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -33,6 +35,7 @@ struct Block {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; /* copy start, copy end, kernel end */
 	bool in_flight = false;
+	bool owned = false; /* a producer is filling it */
 	size_t used = 0;
 };
 
@@ -75,13 +78,20 @@ struct vafgpu_ctx {
 	bool canon = false;
 	std::vector<Device> devs;
 	Nccl nccl;
-	/* producer state */
-	Block *cur = nullptr;
-	int cur_dev = 0;
+	std::mutex mu;    /* guards seq, block ownership, st and err: several producers may run */
 	uint64_t seq = 0; /* blocks handed out so far: round-robin over devices, then buffers */
-	std::vector<char> scratch;
 	vafgpu_stats st{};
 	std::string err;
+	vafgpu_producer *def = nullptr; /* the producer behind vafgpu_add_read / vafgpu_submit_stream */
+};
+
+/* One stream of reads being packed into staging blocks; one per reader thread. */
+struct vafgpu_producer {
+	vafgpu_ctx *c = nullptr;
+	Block *cur = nullptr;
+	int cur_dev = 0;
+	uint64_t n_reads = 0, n_bases = 0; /* added to the context's statistics at flush */
+	std::vector<char> scratch;
 };
 
 namespace {
@@ -93,8 +103,10 @@ int fail(vafgpu_ctx *c, int code, const char *fmt, ...)
 	va_start(ap, fmt);
 	vsnprintf(buf, sizeof buf, fmt, ap);
 	va_end(ap);
-	if (c) c->err = buf;
-	else g_create_error = buf;
+	if (c) {
+		std::lock_guard<std::mutex> lk(c->mu);
+		c->err = buf;
+	} else g_create_error = buf;
 	return code;
 }
 
@@ -105,51 +117,52 @@ int fail(vafgpu_ctx *c, int code, const char *fmt, ...)
 			return fail(c, VAFGPU_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while (0)
 
-/* the byte rules of the reference encoder, applied while copying (see vafgpu.h) */
-const char kNibbleRule[16 + 1] = "NANCTTNGNNNNNNNN"; /* vaf-counter.c:272-275 */
-
-struct StrictRule {
-	char t[256];
-	StrictRule()
-	{
-		memset(t, 'N', sizeof t);
-		t[0] = 'A', t[1] = 'C', t[2] = 'G', t[3] = 'T'; /* vaf-counter.c:74 */
-		t['A'] = t['a'] = 'A';
-		t['C'] = t['c'] = 'C';
-		t['G'] = t['g'] = 'G';
-		t['T'] = t['t'] = t['U'] = t['u'] = 'T';
-	}
-};
-const StrictRule kStrictRule;
-
-void account(vafgpu_ctx *c, Block &b)
-{
-	float ms = 0;
-	if (cudaEventElapsedTime(&ms, b.e0, b.e1) == cudaSuccess) c->st.h2d_ms += ms;
-	if (cudaEventElapsedTime(&ms, b.e1, b.e2) == cudaSuccess) c->st.kernel_ms += ms;
-}
-
 int wait_block(vafgpu_ctx *c, Block &b)
 {
 	if (!b.in_flight) return VAFGPU_OK;
 	CU(c, cudaEventSynchronize(b.e2));
-	account(c, b);
+	float h2d = 0, ker = 0;
+	cudaEventElapsedTime(&h2d, b.e0, b.e1);
+	cudaEventElapsedTime(&ker, b.e1, b.e2);
+	std::lock_guard<std::mutex> lk(c->mu);
+	c->st.h2d_ms += h2d;
+	c->st.kernel_ms += ker;
 	b.in_flight = false;
 	return VAFGPU_OK;
 }
 
-int acquire(vafgpu_ctx *c)
+/* next free staging block, round-robin over devices then buffers; blocks another producer
+ * is filling are skipped, a block still in flight is waited for (that is the back-pressure
+ * which replaces kt_pipeline's "at most three blocks") */
+int acquire(vafgpu_producer *p)
 {
+	vafgpu_ctx *c = p->c;
 	const size_t nd = c->devs.size();
-	const int di = (int)(c->seq % nd);
-	Device &d = c->devs[di];
-	Block &b = d.blocks[(c->seq / nd) % d.blocks.size()];
-	++c->seq;
-	int rc = wait_block(c, b);
+	Block *b = nullptr;
+	int di = 0;
+	for (;;) {
+		{
+			std::lock_guard<std::mutex> lk(c->mu);
+			const size_t total = nd * c->devs[0].blocks.size();
+			for (size_t tries = 0; tries < total && !b; ++tries) {
+				di = (int)(c->seq % nd);
+				Device &d = c->devs[di];
+				Block &cand = d.blocks[(c->seq / nd) % d.blocks.size()];
+				++c->seq;
+				if (!cand.owned) {
+					cand.owned = true;
+					b = &cand;
+				}
+			}
+		}
+		if (b) break;
+		std::this_thread::yield(); /* more producers than blocks: wait for one to be submitted */
+	}
+	int rc = wait_block(c, *b);
 	if (rc) return rc;
-	b.used = 0;
-	c->cur = &b;
-	c->cur_dev = di;
+	b->used = 0;
+	p->cur = b;
+	p->cur_dev = di;
 	return VAFGPU_OK;
 }
 
@@ -182,35 +195,41 @@ cudaError_t launch(const vafgpu_ctx *c, const Device &d, const ScanArgs &a, cuda
 }
 
 /* copy the current block to its device and scan it there, all on the block's stream */
-int submit_current(vafgpu_ctx *c)
+int submit_current(vafgpu_producer *p)
 {
-	Block *b = c->cur;
+	vafgpu_ctx *c = p->c;
+	Block *b = p->cur;
 	if (!b) return VAFGPU_OK;
-	c->cur = nullptr;
-	if (b->used == 0) return VAFGPU_OK;
-	Device &d = c->devs[c->cur_dev];
+	p->cur = nullptr;
 	size_t n = (b->used + 15) & ~(size_t)15;
-	memset(b->h + b->used, '\n', n - b->used);
-	CU(c, cudaSetDevice(d.ordinal));
-	CU(c, cudaEventRecord(b->e0, b->stream));
-	CU(c, cudaMemcpyAsync(b->d, b->h, n, cudaMemcpyHostToDevice, b->stream));
-	CU(c, cudaEventRecord(b->e1, b->stream));
-	CU(c, launch(c, d, scan_args(c, d, b->d, n, nullptr), b->stream));
-	CU(c, cudaEventRecord(b->e2, b->stream));
-	b->in_flight = true;
-	c->st.n_blocks++;
-	c->st.n_bytes += n;
+	if (b->used) {
+		Device &d = c->devs[p->cur_dev];
+		memset(b->h + b->used, '\n', n - b->used);
+		CU(c, cudaSetDevice(d.ordinal));
+		CU(c, cudaEventRecord(b->e0, b->stream));
+		CU(c, cudaMemcpyAsync(b->d, b->h, n, cudaMemcpyHostToDevice, b->stream));
+		CU(c, cudaEventRecord(b->e1, b->stream));
+		CU(c, launch(c, d, scan_args(c, d, b->d, n, nullptr), b->stream));
+		CU(c, cudaEventRecord(b->e2, b->stream));
+	}
+	std::lock_guard<std::mutex> lk(c->mu);
+	if (b->used) {
+		b->in_flight = true;
+		c->st.n_blocks++;
+		c->st.n_bytes += n;
+	}
+	b->owned = false;
 	return VAFGPU_OK;
 }
 
 /* room for `need` more bytes in the current block, submitting / acquiring as required */
-int ensure_room(vafgpu_ctx *c, size_t need)
+int ensure_room(vafgpu_producer *p, size_t need)
 {
-	if (c->cur && c->cur->used + need > c->block_bytes) {
-		int rc = submit_current(c);
+	if (p->cur && p->cur->used + need > p->c->block_bytes) {
+		int rc = submit_current(p);
 		if (rc) return rc;
 	}
-	if (!c->cur) return acquire(c);
+	if (!p->cur) return acquire(p);
 	return VAFGPU_OK;
 }
 
@@ -269,14 +288,6 @@ int vafgpu_plan(int k, int *stride, int *len)
 	if (stride) *stride = p.stride;
 	if (len) *len = p.len;
 	return VAFGPU_OK;
-}
-
-void vafgpu_canonicalise_read(const char *seq, size_t len, char *out, int simd_rule)
-{
-	const size_t body = simd_rule ? (len & ~(size_t)15) : 0; /* vaf-counter.c:278 */
-	size_t i = 0;
-	for (; i < body; ++i) out[i] = kNibbleRule[(unsigned char)seq[i] & 15];
-	for (; i < len; ++i) out[i] = kStrictRule.t[(unsigned char)seq[i]]; /* vaf-counter.c:288-290 */
 }
 
 const char *vafgpu_strerror(const vafgpu_ctx *ctx)
@@ -390,17 +401,38 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	return VAFGPU_OK;
 }
 
-int vafgpu_add_read(vafgpu_ctx *c, const char *seq, size_t len)
+/* the producer behind the single-producer entry points, made on first use */
+static vafgpu_producer *default_producer(vafgpu_ctx *c)
 {
-	if (!c || (!seq && len)) return VAFGPU_EINVAL;
+	if (!c->def) {
+		c->def = new (std::nothrow) vafgpu_producer;
+		if (c->def) c->def->c = c;
+	}
+	return c->def;
+}
+
+int vafgpu_producer_create(vafgpu_ctx *c, vafgpu_producer **out)
+{
+	if (!c || !out) return VAFGPU_EINVAL;
+	vafgpu_producer *p = new (std::nothrow) vafgpu_producer;
+	if (!p) return fail(c, VAFGPU_ENOMEM, "out of memory");
+	p->c = c;
+	*out = p;
+	return VAFGPU_OK;
+}
+
+int vafgpu_producer_add_read(vafgpu_producer *p, const char *seq, size_t len)
+{
+	if (!p || (!seq && len)) return VAFGPU_EINVAL;
+	vafgpu_ctx *c = p->c;
 	if (len < (size_t)c->k) return VAFGPU_OK; /* vaf-counter.c:494 */
-	c->st.n_reads++;
-	c->st.n_bases += len;
+	p->n_reads++;
+	p->n_bases += len;
 	const bool simd = true; /* the Makefile builds the reference with -mssse3 (Makefile:44) */
 	if (len + 1 <= c->block_bytes) {
-		int rc = ensure_room(c, len + 1);
+		int rc = ensure_room(p, len + 1);
 		if (rc) return rc;
-		Block *b = c->cur;
+		Block *b = p->cur;
 		vafgpu_canonicalise_read(seq, len, b->h + b->used, simd);
 		b->h[b->used + len] = '\n';
 		b->used += len + 1;
@@ -409,15 +441,15 @@ int vafgpu_add_read(vafgpu_ctx *c, const char *seq, size_t len)
 	/* a read longer than a block (a chromosome): canonicalise it whole, since the byte rule
 	 * depends on the offset within the read, then cut it into pieces that overlap by k-1
 	 * bases so that every k-mer lies in exactly one piece */
-	if (c->scratch.size() < len) c->scratch.resize(len);
-	vafgpu_canonicalise_read(seq, len, c->scratch.data(), simd);
+	if (p->scratch.size() < len) p->scratch.resize(len);
+	vafgpu_canonicalise_read(seq, len, p->scratch.data(), simd);
 	const size_t piece = c->block_bytes - 1, step = piece - (size_t)(c->k - 1);
 	for (size_t at = 0;; at += step) {
 		size_t n = len - at < piece ? len - at : piece;
-		int rc = ensure_room(c, n + 1);
+		int rc = ensure_room(p, n + 1);
 		if (rc) return rc;
-		Block *b = c->cur;
-		memcpy(b->h + b->used, c->scratch.data() + at, n);
+		Block *b = p->cur;
+		memcpy(b->h + b->used, p->scratch.data() + at, n);
 		b->h[b->used + n] = '\n';
 		b->used += n + 1;
 		if (at + n >= len) break;
@@ -425,11 +457,41 @@ int vafgpu_add_read(vafgpu_ctx *c, const char *seq, size_t len)
 	return VAFGPU_OK;
 }
 
+int vafgpu_producer_flush(vafgpu_producer *p)
+{
+	if (!p) return VAFGPU_EINVAL;
+	int rc = submit_current(p);
+	std::lock_guard<std::mutex> lk(p->c->mu);
+	p->c->st.n_reads += p->n_reads;
+	p->c->st.n_bases += p->n_bases;
+	p->n_reads = p->n_bases = 0;
+	return rc;
+}
+
+int vafgpu_producer_destroy(vafgpu_producer *p)
+{
+	if (!p) return VAFGPU_OK;
+	int rc = vafgpu_producer_flush(p);
+	if (p->c->def == p) p->c->def = nullptr;
+	delete p;
+	return rc;
+}
+
+int vafgpu_add_read(vafgpu_ctx *c, const char *seq, size_t len)
+{
+	if (!c) return VAFGPU_EINVAL;
+	vafgpu_producer *p = default_producer(c);
+	if (!p) return fail(c, VAFGPU_ENOMEM, "out of memory");
+	return vafgpu_producer_add_read(p, seq, len);
+}
+
 int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint64_t n_reads, uint64_t n_bases)
 {
 	if (!c || (!bytes && n_bytes)) return VAFGPU_EINVAL;
-	c->st.n_reads += n_reads;
-	c->st.n_bases += n_bases;
+	vafgpu_producer *p = default_producer(c);
+	if (!p) return fail(c, VAFGPU_ENOMEM, "out of memory");
+	p->n_reads += n_reads;
+	p->n_bases += n_bases;
 	/* page-locked caller memory is copied to the device as it is; pageable memory goes through
 	 * the pinned staging blocks */
 	cudaPointerAttributes attr;
@@ -438,11 +500,11 @@ int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint6
 	size_t at = 0;
 	while (at < n_bytes) {
 		/* close whatever add_read left open, then fill whole blocks straight from the caller */
-		int rc = submit_current(c);
+		int rc = submit_current(p);
 		if (rc) return rc;
-		rc = acquire(c);
+		rc = acquire(p);
 		if (rc) return rc;
-		Block *b = c->cur;
+		Block *b = p->cur;
 		size_t n = n_bytes - at, advance;
 		bool add_nl = false;
 		if (n > c->block_bytes) {
@@ -470,8 +532,8 @@ int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint6
 			continue; /* submitted at the top of the loop or after it */
 		}
 		/* zero-copy path: H2D from the caller's buffer, separator and padding written on the device */
-		Device &d = c->devs[c->cur_dev];
-		c->cur = nullptr;
+		Device &d = c->devs[p->cur_dev];
+		p->cur = nullptr;
 		const size_t n16 = (n + (add_nl ? 1 : 0) + 15) & ~(size_t)15;
 		CU(c, cudaSetDevice(d.ordinal));
 		CU(c, cudaEventRecord(b->e0, b->stream));
@@ -480,12 +542,16 @@ int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint6
 		CU(c, cudaEventRecord(b->e1, b->stream));
 		CU(c, launch(c, d, scan_args(c, d, b->d, n16, nullptr), b->stream));
 		CU(c, cudaEventRecord(b->e2, b->stream));
-		b->in_flight = true;
-		c->st.n_blocks++;
-		c->st.n_bytes += n16;
+		{
+			std::lock_guard<std::mutex> lk(c->mu);
+			b->in_flight = true;
+			b->owned = false;
+			c->st.n_blocks++;
+			c->st.n_bytes += n16;
+		}
 		at += advance;
 	}
-	return submit_current(c);
+	return vafgpu_producer_flush(p);
 }
 
 int vafgpu_count_device(vafgpu_ctx *c, int device, const void *d_bytes, size_t n_bytes, uint32_t *d_counts, void *stream)
@@ -496,6 +562,7 @@ int vafgpu_count_device(vafgpu_ctx *c, int device, const void *d_bytes, size_t n
 	CU(c, cudaSetDevice(d.ordinal));
 	cudaStream_t s = stream ? (cudaStream_t)stream : d.main_stream;
 	CU(c, launch(c, d, scan_args(c, d, (const uint8_t *)d_bytes, n_bytes, d_counts), s));
+	std::lock_guard<std::mutex> lk(c->mu);
 	c->st.n_blocks++;
 	c->st.n_bytes += n_bytes;
 	return VAFGPU_OK;
@@ -504,7 +571,7 @@ int vafgpu_count_device(vafgpu_ctx *c, int device, const void *d_bytes, size_t n
 int vafgpu_finish(vafgpu_ctx *c, uint32_t *counts, vafgpu_stats *stats)
 {
 	if (!c) return VAFGPU_EINVAL;
-	int rc = submit_current(c);
+	int rc = c->def ? vafgpu_producer_flush(c->def) : VAFGPU_OK;
 	if (rc) return rc;
 	for (Device &d : c->devs) {
 		CU(c, cudaSetDevice(d.ordinal));
@@ -586,6 +653,7 @@ void vafgpu_destroy(vafgpu_ctx *c)
 		if (d.comm && c->nccl.CommDestroy) c->nccl.CommDestroy(d.comm);
 		destroy_device(d);
 	}
+	delete c->def;
 	delete c;
 }
 

@@ -31,6 +31,8 @@ EXPORTS = (
     "vafgpu_create", "vafgpu_add_read", "vafgpu_submit_stream", "vafgpu_count_device",
     "vafgpu_finish", "vafgpu_reset", "vafgpu_destroy", "vafgpu_strerror", "vafgpu_plan",
     "vafgpu_canonicalise_read", "vafgpu_version",
+    "vafgpu_producer_create", "vafgpu_producer_add_read", "vafgpu_producer_flush",
+    "vafgpu_producer_destroy",
 )
 
 
@@ -89,6 +91,14 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.vafgpu_canonicalise_read.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int]
     lib.vafgpu_canonicalise_read.restype = None
     lib.vafgpu_version.restype = C.c_char_p
+    lib.vafgpu_producer_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.vafgpu_producer_create.restype = C.c_int
+    lib.vafgpu_producer_add_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.vafgpu_producer_add_read.restype = C.c_int
+    lib.vafgpu_producer_flush.argtypes = [C.c_void_p]
+    lib.vafgpu_producer_flush.restype = C.c_int
+    lib.vafgpu_producer_destroy.argtypes = [C.c_void_p]
+    lib.vafgpu_producer_destroy.restype = C.c_int
     _lib = lib
     return lib
 
@@ -134,6 +144,10 @@ class Engine:
     def add_read(self, seq: bytes) -> None:
         self._check(self._lib.vafgpu_add_read(self._h, seq, len(seq)))
 
+    def producer(self) -> "Producer":
+        """A producer for one reader thread (vafgpu_producer_*); flush or close it before finish()."""
+        return Producer(self)
+
     def submit_stream(self, buf, n_reads: int = 0, n_bases: int = 0) -> None:
         """buf: bytes, a numpy uint8 array, or (address, n_bytes) of host memory in stream form."""
         if isinstance(buf, tuple):
@@ -175,6 +189,32 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+class Producer:
+    """One reader thread's handle on an Engine (parallel ingest)."""
+
+    def __init__(self, engine: Engine):
+        self._e = engine
+        self._p = C.c_void_p()
+        engine._check(engine._lib.vafgpu_producer_create(engine._h, C.byref(self._p)))
+
+    def add_read(self, seq: bytes) -> None:
+        self._e._check(self._e._lib.vafgpu_producer_add_read(self._p, seq, len(seq)))
+
+    def flush(self) -> None:
+        self._e._check(self._e._lib.vafgpu_producer_flush(self._p))
+
+    def close(self) -> None:
+        if self._p:
+            p, self._p = self._p, C.c_void_p()
+            self._e._check(self._e._lib.vafgpu_producer_destroy(p))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 # ---------------------------------------------------------------------------------------------

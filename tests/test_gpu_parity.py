@@ -179,3 +179,55 @@ def test_uint32_counters_and_vaf_text(tmp_path, oracle, lib):
     exe = os.path.join(util.PKG, "vaf-counter")
     subprocess.run([exe, "-k", "21", "-p", pf, "-o", out, "-b", "100000", fq], check=True, capture_output=True)
     assert open(out).read() == vafgpu.format_vaf(pats, want)
+
+
+@pytest.mark.parametrize("merge", ["nccl", "host"])
+def test_all_visible_devices_round_robin_and_merge(tmp_path, oracle, lib, merge):
+    """Blocks are dealt round-robin over every visible GPU and the counter vectors merged with
+    one all-reduce (or on the host); with one GPU this is the plain path.  The result must not
+    depend on the number of devices (uint32 sums commute)."""
+    import torch
+    pats, reads, pf, want, _, keys, vals = case(tmp_path, oracle, 31, 21, 800, 40000, plant=0.7, jitter=25)
+    flags = vafgpu.F_HOST_MERGE if merge == "host" else 0
+    with vafgpu.Engine(21, keys, vals, len(pats), n_devices=0, block_bytes=1 << 16, flags=flags) as eng:
+        for r in reads[: len(reads) // 2]:
+            eng.add_read(r)
+        first, st = eng.finish()
+        for r in reads[len(reads) // 2:]:
+            eng.add_read(r)
+        total, st = eng.finish()      # a second finish after an all-reduce must still sum correctly
+    assert st["n_devices"] == torch.cuda.device_count()
+    w1, _, _ = oracle.count_reads(pf, 21, reads[: len(reads) // 2])
+    assert np.array_equal(first, w1)
+    assert np.array_equal(total, want)
+    assert st["n_blocks"] > 50
+
+
+@pytest.mark.parametrize("n_threads,n_buffers", [(4, 0), (6, 2)])
+def test_parallel_producers(tmp_path, oracle, lib, n_threads, n_buffers):
+    """Several reader threads, each with a producer of its own (more threads than staging blocks
+    in the second case): counting is additive, so the result equals the single-producer one and
+    the statistics add up."""
+    import threading
+    pats, reads, pf, want, _, keys, vals = case(tmp_path, oracle, 41, 21, 600, 30000, plant=0.7, jitter=25)
+    with vafgpu.Engine(21, keys, vals, len(pats), n_devices=1, block_bytes=1 << 15, n_buffers=n_buffers) as eng:
+        errors = []
+
+        def work(t):
+            try:
+                with eng.producer() as p:
+                    for r in reads[t::n_threads]:
+                        p.add_read(r)
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errors, errors
+        got, st = eng.finish()
+    assert np.array_equal(got, want)
+    assert st["n_reads"] == sum(1 for r in reads if len(r) >= 21)
+    assert st["n_bases"] == sum(len(r) for r in reads if len(r) >= 21)

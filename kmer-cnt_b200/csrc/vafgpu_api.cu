@@ -42,8 +42,10 @@ struct Block {
 struct Device {
 	int ordinal = 0;
 	int n_sm = 0;
+	uint64_t keep_policy = 0;
 	uint32_t *d_filter = nullptr;
-	uint32_t *d_tags = nullptr;
+	uint32_t *d_buckets = nullptr;
+	uint32_t *d_filter2 = nullptr;
 	vg_slot_t *d_slots = nullptr;
 	uint64_t *d_rkeys = nullptr;
 	uint32_t *d_rvals = nullptr;
@@ -74,8 +76,8 @@ struct vafgpu_ctx {
 	size_t n_counts = 0; /* 2 * n_patterns, at least 2 */
 	size_t block_bytes = 0;
 	Plan plan;
-	uint32_t filter_words = 0, bucket_bits = 0, rbits = 0;
-	bool canon = false;
+	uint32_t filter_words = 0, filter2_words = 0, n_buckets = 0, rbits = 0;
+	bool canon = false, defer = false;
 	std::vector<Device> devs;
 	Nccl nccl;
 	std::mutex mu;    /* guards seq, block ownership, st and err: several producers may run */
@@ -179,9 +181,13 @@ ScanArgs scan_args(const vafgpu_ctx *c, const Device &d, const uint8_t *bytes, s
 	a.canon = c->canon ? 1 : 0;
 	a.filter = d.d_filter;
 	a.filter_words = c->filter_words;
-	a.tags = d.d_tags;
+	a.defer = c->defer ? 1 : 0;
+	a.filter2 = d.d_filter2;
+	a.filter2_words = c->filter2_words;
+	a.buckets = d.d_buckets;
+	a.n_buckets = c->n_buckets;
 	a.slots = d.d_slots;
-	a.bucket_bits = c->bucket_bits;
+	a.keep_policy = d.keep_policy;
 	a.rkeys = d.d_rkeys;
 	a.rvals = d.d_rvals;
 	a.rbits = c->rbits;
@@ -267,7 +273,8 @@ void destroy_device(Device &d)
 	}
 	if (d.main_stream) cudaStreamDestroy(d.main_stream);
 	cudaFree(d.d_filter);
-	cudaFree(d.d_tags);
+	cudaFree(d.d_buckets);
+	cudaFree(d.d_filter2);
 	cudaFree(d.d_slots);
 	cudaFree(d.d_rkeys);
 	cudaFree(d.d_rvals);
@@ -332,8 +339,10 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	build_anchor_tables(k, keys, vals, n_entries, at);
 	c->plan = at.plan;
 	c->filter_words = (uint32_t)at.filter.size();
-	c->bucket_bits = at.bucket_bits;
+	c->filter2_words = (uint32_t)at.filter2.size();
+	c->n_buckets = at.n_buckets;
 	c->canon = at.canon;
+	c->defer = at.defer;
 	c->rbits = rt.bits;
 
 	int rc = VAFGPU_OK;
@@ -348,17 +357,24 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			if (prop.major != 10)
 				return fail(c, VAFGPU_ENOGPU, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", i, prop.name, prop.major, prop.minor);
 			d.n_sm = prop.multiProcessorCount;
-			CU(c, kernels_init_device(d.n_sm));
+			CU(c, kernels_make_policy(&d.keep_policy));
+			if (const char *env = getenv("VAFGPU_L2_PERSIST_MB")) { /* tuning knob: L2 set-aside for evict-last lines */
+				size_t want = (size_t)atoi(env) << 20;
+				if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+				CU(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+			}
 			CU(c, cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
 			CU(c, cudaMalloc(&d.d_filter, at.filter.size() * 4));
-			CU(c, cudaMalloc(&d.d_tags, at.tags.size() * 4));
+			CU(c, cudaMalloc(&d.d_filter2, at.filter2.size() * 4));
+			CU(c, cudaMalloc(&d.d_buckets, at.buckets.size() * 4));
 			CU(c, cudaMalloc(&d.d_slots, at.slots.size() * sizeof(vg_slot_t)));
 			CU(c, cudaMalloc(&d.d_rkeys, rt.keys.size() * 8));
 			CU(c, cudaMalloc(&d.d_rvals, rt.vals.size() * 4));
 			CU(c, cudaMalloc(&d.d_counts, c->n_counts * 4));
 			CU(c, cudaMalloc(&d.d_stats, ST_N * sizeof(unsigned long long)));
 			CU(c, cudaMemcpy(d.d_filter, at.filter.data(), at.filter.size() * 4, cudaMemcpyHostToDevice));
-			CU(c, cudaMemcpy(d.d_tags, at.tags.data(), at.tags.size() * 4, cudaMemcpyHostToDevice));
+			CU(c, cudaMemcpy(d.d_filter2, at.filter2.data(), at.filter2.size() * 4, cudaMemcpyHostToDevice));
+			CU(c, cudaMemcpy(d.d_buckets, at.buckets.data(), at.buckets.size() * 4, cudaMemcpyHostToDevice));
 			CU(c, cudaMemcpy(d.d_slots, at.slots.data(), at.slots.size() * sizeof(vg_slot_t), cudaMemcpyHostToDevice));
 			CU(c, cudaMemcpy(d.d_rkeys, rt.keys.data(), rt.keys.size() * 8, cudaMemcpyHostToDevice));
 			CU(c, cudaMemcpy(d.d_rvals, rt.vals.data(), rt.vals.size() * 4, cudaMemcpyHostToDevice));
@@ -396,7 +412,7 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	c->st.anchor_stride = c->plan.stride;
 	c->st.anchor_len = c->plan.len;
 	c->st.filter_bytes = c->filter_words * 4;
-	c->st.table_slots = 4u << c->bucket_bits;
+	c->st.table_slots = 3u * c->n_buckets;
 	*out = c;
 	return VAFGPU_OK;
 }

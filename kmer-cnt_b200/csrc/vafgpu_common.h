@@ -21,17 +21,29 @@
 #endif
 
 #define VG_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-#define VG_SMEM_BUDGET (227 * 1024) /* dynamic shared memory per CTA on sm_100: filter + candidate queues */
+#define VG_SMEM_BUDGET (227 * 1024) /* dynamic shared memory per CTA on sm_100: filter + bit-pair table + candidate queues */
 #define VG_MIN_FILTER_WORDS 1024u
+#define VG_PAIRS 992u               /* ordered pairs of distinct bit positions in a 32-bit word */
+#define VG_PAIR_TABLE_BYTES 4096
 
-/* launch geometry of the anchor kernel for stride S, shared with the table builder because
- * the candidate queues and the filter split one shared-memory budget */
-#define VG_THREADS(S) ((S) >= 4 ? 1024 : 256)              /* tiny k: fewer warps, deeper queues   */
-#define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)) + 32)    /* per warp: a drain's leftovers + one tile, + 32 tag matches awaiting verification */
-#define VG_QUEUE_BYTES(S) ((VG_THREADS(S) / 32) * VG_QUEUE_ENTRIES(S) * 8)
-#define VG_FILTER_BUDGET_WORDS(S) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S) - 128) / 4) & ~3))
+/* Launch geometry of the anchor kernel, shared with the table builder because the candidate
+ * queues and the filter split one shared-memory budget.
+ *   queue path    (small panels, or tiny k): survivors of the filter are rare; they are
+ *                 compacted into a per-warp queue and resolved 32 at a time;
+ *   deferred path (large panels, S >= 4): every tenth anchor survives, so each lane requests
+ *                 its survivor's home bucket from L2 straight away and looks at it one tile
+ *                 later; that needs registers, hence fewer threads. */
+#ifndef VG_THREADS_DEFER
+#define VG_THREADS_DEFER(S) ((S) >= 8 ? 1024 : 768)
+#endif
+#define VG_DEFER_OK(S) ((S) >= 4)
+#define VG_THREADS(S, DEFER) ((DEFER) ? VG_THREADS_DEFER(S) : (S) >= 4 ? 1024 : 256) /* tiny k: fewer warps, deeper queues */
+#define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)) + 32)  /* per warp: a drain's leftovers + one tile, + 32 tag matches awaiting verification */
+#define VG_QUEUE_BYTES(S, DEFER) ((VG_THREADS(S, DEFER) / 32) * VG_QUEUE_ENTRIES(S) * 8)
+#define VG_FILTER_BUDGET_WORDS(S, DEFER) \
+	((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S, DEFER) - VG_PAIR_TABLE_BYTES) / 4) & ~3))
 
-/* exact-table slot: an oriented pattern k-mer (stream encoding) with the offset of the
+/* exact-table payload: an oriented pattern k-mer (stream encoding) with the offset of the
  * anchor it is filed under.  16 bytes so one LDG.128 fetches it. */
 typedef struct {
 	uint64_t okey; /* oriented k-mer, VG_EMPTY_KEY if the slot is free */
@@ -81,13 +93,10 @@ VG_HD uint32_t vg_rc32(uint32_t x, int L)
  * compare-select (the integer ALU pipe is the scarce resource of the kernel). */
 VG_HD uint32_t vg_filter_key(uint32_t a, int L, int canon) { return canon ? a * vg_rc32(a, L) : a; }
 
-/* Blocked Bloom filter: one 32-bit word per key, two bits in it.  The word comes from the
- * top of one multiplicative hash, the two bit positions from the top ten bits of a second
- * and a third one.  On the device 1 << b comes from a 32-word shared-memory table: bank b
- * holds entry b, so the look-up never conflicts, and unlike a shift it costs no slot of the
- * integer ALU pipe, the kernel's scarcest resource. */
-VG_HD uint32_t vg_hash1(uint32_t key) { return key * 0x9E3779B1u; }
-VG_HD uint32_t vg_hash2(uint32_t key) { return key * 0x85EBCA6Bu; }
+/* One multiply chain places an anchor everywhere.  h = key * odd constant; the 64-bit product
+ * h * n_words gives the filter word (high half) and a second, well mixed 32-bit value (low
+ * half) whose top bits pick the bit pair and the home bucket of the exact table.  On the
+ * device this is IMAD, IMAD.WIDE, IMAD.HI, IMAD.HI: all on the FMA pipe. */
 VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)
@@ -96,23 +105,42 @@ VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
 	return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+VG_HD uint32_t vg_hash1(uint32_t key) { return key * 0x9E3779B1u; }
 VG_HD uint32_t vg_filter_word(uint32_t key, uint32_t n_words) { return vg_mulhi(vg_hash1(key), n_words); }
-VG_HD uint32_t vg_hash3(uint32_t h2) { return h2 * 0xC2B2AE35u; }
-VG_HD uint32_t vg_filter_mask(uint32_t key)
+VG_HD uint32_t vg_hash_lo(uint32_t key, uint32_t n_words) { return vg_hash1(key) * n_words; }
+
+/* Blocked Bloom filter: one 32-bit word per key, two distinct bits in it.  The pair comes
+ * from a 992-entry table (shared memory on the device): entry i * 31 + j names bits i and
+ * (j < i ? j : j + 1). */
+VG_HD uint32_t vg_pair_index(uint32_t lo) { return vg_mulhi(lo, VG_PAIRS); }
+VG_HD uint32_t vg_pair_frac(uint32_t lo) { return lo * VG_PAIRS; } /* the low half of the same product: where in the pair's cell lo falls */
+VG_HD uint32_t vg_pair_mask(uint32_t idx)
 {
-	const uint32_t h2 = vg_hash2(key);
-	return (1u << (h2 >> 27)) | (1u << (vg_hash3(h2) >> 27));
+	const uint32_t i = idx / 31u, j = idx % 31u;
+	return (1u << i) | (1u << (j < i ? j : j + 1u));
+}
+VG_HD uint32_t vg_filter_mask(uint32_t key, uint32_t n_words) { return vg_pair_mask(vg_pair_index(vg_hash_lo(key, n_words))); }
+
+/* Second filter level (large panels): the same two bits in a word of a much bigger array that
+ * lives in L2 (a few MB: >= 128 bits per key).  Only anchors that passed the on-chip filter
+ * look at it, one 4-byte load each; what passes both goes to the exact table.  The word comes
+ * from the part of the hash the pair did not use. */
+VG_HD uint32_t vg_filter2_word(uint32_t key, uint32_t n_words, uint32_t n_words2)
+{
+	return vg_mulhi(vg_pair_frac(vg_hash_lo(key, n_words)), n_words2);
 }
 
-/* exact table: buckets of four 32-bit tags (one LDG.128) with the 16-byte payloads in a
- * parallel array that is only touched when a tag matches.  Tag 0 marks a free slot; a slot
- * is filled at the first free position scanning on from the home bucket, so a lookup stops
- * at the first free slot it meets.  The tag keeps the low 31 bits of the forward anchor
- * (all of it for L <= 15); the payload decides. */
-VG_HD uint32_t vg_tag(uint32_t anchor) { return anchor | 0x80000000u; }
-VG_HD uint32_t vg_bucket_home(uint32_t anchor, uint32_t bucket_bits)
-{
-	return (anchor * 0xCC9E2D51u) >> (32 - bucket_bits);
-}
+/* Exact table: buckets of 16 bytes (one LDG.128) = three 32-bit tags + one control word.
+ *   tag   the forward anchor (low 31 bits | bit 31 when L = 16, so that it never equals
+ *         VG_FREE_TAG); occupied slots are a prefix of the bucket
+ *   ctrl  bits 0..30: index in the payload array of the bucket's first entry (the entries of
+ *         a bucket are consecutive there); bit 31: an entry that hashes to this bucket, or
+ *         passed through it, lives further on -- keep looking in the next bucket
+ * Entries are placed by linear probing over buckets from the home bucket, which both
+ * strands of an anchor share when the filter key is strand-symmetric.  The payload decides. */
+#define VG_FREE_TAG 0x7FFFFFFFu
+#define VG_CTRL_MORE 0x80000000u
+VG_HD uint32_t vg_tag(uint32_t anchor, int L) { return L >= 16 ? anchor | 0x80000000u : anchor; }
+VG_HD uint32_t vg_bucket_home(uint32_t lo, uint32_t n_buckets) { return vg_mulhi(lo, n_buckets); }
 
 #endif

@@ -61,14 +61,14 @@ __device__ __forceinline__ uint32_t pack16(uint4 w)
 /* ------------------------------------------------------------------------------------ */
 /* anchor-filter kernel                                                                   */
 
-/* Per-warp candidate queue in shared memory: survivors of the filter are compacted into it
- * and resolved 32 at a time, one per lane, so that the L2 round trips of the exact table
- * are taken by full warps and off the streaming loop.  It must absorb everything one tile
- * can produce on top of the < 32 entries left by the last drain. */
-template <int S> struct Launch {
-	static constexpr int kThreads = VG_THREADS(S);
+/* Per-warp candidate queue in shared memory: anchors that need the exact table walked are
+ * compacted into it and resolved 32 at a time, one per lane, off the streaming loop.  It
+ * must absorb everything one tile can produce on top of the < 32 entries left by the last
+ * drain. */
+template <int S, bool DEFER> struct Launch {
+	static constexpr int kThreads = VG_THREADS(S, DEFER);
 	static constexpr int kQueue = VG_QUEUE_ENTRIES(S); /* candidates + 32 verify entries */
-	static constexpr int kQueueBytes = VG_QUEUE_BYTES(S);
+	static constexpr int kQueueBytes = VG_QUEUE_BYTES(S, DEFER);
 };
 
 struct AnchorParams {
@@ -85,42 +85,35 @@ struct AnchorParams {
 	unsigned long long *stats;
 	const uint32_t *filter;
 	uint32_t filter_words;
-	const uint4 *tags;     /* buckets of four tags */
+	const uint32_t *filter2; /* second filter level, L2-resident (deferred form) */
+	uint32_t filter2_words;
+	const uint4 *buckets;  /* three tags + control word each */
+	uint32_t n_buckets;
 	const vg_slot_t *slots;
-	uint32_t bucket_bits;
 	int k, len;
-	uint32_t pf_bytes;     /* L2 prefetch distance ahead of the register pipeline, 0 = off */
-	uint32_t c4, c32;      /* the constants 4 and 32, passed as data so that index scaling and
-	                          top-5-bit extraction compile to IMAD / IMAD.HI (FMA pipe) instead of
-	                          LEA / SHF (integer ALU pipe) */
+	uint64_t keep;         /* L2 evict-last access policy (createpolicy), made once per device */
+	uint32_t c4;           /* the constant 4, passed as data so that index scaling compiles to
+	                          IMAD (FMA pipe) instead of LEA (integer ALU pipe) */
 };
+
+/* distance of the L2 prefetch ahead of the register pipeline, in bytes (8 tiles) */
+#ifndef VG_PF_BYTES
+#define VG_PF_BYTES 4096
+#endif
 
 __device__ __forceinline__ void l2_prefetch(const void *ptr)
 {
 	asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
-
-/* the stream load: read once, 16 bytes per lane.  VG_STREAM_LOAD picks the cache operator
- * (tuning knob kept while the kernel is being profiled). */
-#ifndef VG_STREAM_LOAD
-#define VG_STREAM_LOAD 0
-#endif
-__device__ __forceinline__ uint4 ld_stream(const uint4 *ptr)
+__device__ __forceinline__ void l2_prefetch_ahead(const void *ptr)
 {
-#if VG_STREAM_LOAD == 0
-	return __ldcs(ptr); /* ld.global.cs: evict-first in L1 and L2 */
-#elif VG_STREAM_LOAD == 1
-	return __ldg(ptr); /* ld.global.nc */
-#elif VG_STREAM_LOAD == 2
-	return __ldcg(ptr); /* ld.global.cg: L2 only */
-#elif VG_STREAM_LOAD == 3
-	uint4 v;
-	asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
-	return v;
-#else
-	return *ptr;
+#if VG_PF_BYTES > 0
+	asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(ptr), "n"(VG_PF_BYTES));
 #endif
 }
+
+/* the stream load: read once, 16 bytes per lane, evict-first in L1 and L2 */
+__device__ __forceinline__ uint4 ld_stream(const uint4 *ptr) { return __ldcs(ptr); }
 
 /* The exact table is hit at random while gigabytes stream past it: its lines are loaded
  * with an evict-last L2 policy so the stream (loaded evict-first) does not push them out. */
@@ -139,11 +132,27 @@ __device__ __forceinline__ uint4 ldg_keep(const uint4 *ptr, uint64_t pol)
 	return v;
 }
 
-/* Second stage: up to 32 (slot, anchor position) pairs whose tag matched, one per lane.  The
- * payload names an oriented pattern k-mer and how far before its end the anchor ends; the k
- * raw bytes of that place in the stream decide.  Batching them makes the two dependent L2
- * round trips (payload, then bytes) happen once per 32 verifications instead of once each,
- * and lets the counter update aggregate over the warp. */
+__device__ __forceinline__ uint32_t ldg_keep(const uint32_t *ptr, uint64_t pol)
+{
+	uint32_t v;
+	asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+	return v;
+}
+
+/* reverse complement of a packed word of 16 bases (stream encoding, complement = code ^ 2):
+ * bit reversal reverses the bases and swaps the two bits of each; swap them back and flip
+ * the high one */
+__device__ __forceinline__ uint32_t rc16(uint32_t x)
+{
+	const uint32_t r = __brev(x);
+	return (((r >> 1) & 0x55555555u) | ((r << 1) & 0xAAAAAAAAu)) ^ 0xAAAAAAAAu;
+}
+
+/* Second stage: up to 32 (payload index, anchor position) pairs whose tag matched, one per
+ * lane.  The payload names an oriented pattern k-mer and how far before its end the anchor
+ * ends; the k raw bytes of that place in the stream decide.  Batching them makes the two
+ * dependent L2 round trips (payload, then bytes) happen once per 32 verifications instead of
+ * once each, and lets the counter update aggregate over the warp. */
 template <int S>
 __device__ __forceinline__ uint32_t verify_batch(const AnchorParams &p, const uint2 *vq, uint32_t n, uint32_t lane)
 {
@@ -151,7 +160,7 @@ __device__ __forceinline__ uint32_t verify_batch(const AnchorParams &p, const ui
 	uint32_t val = 0;
 	if (lane < n) {
 		const uint2 e = vq[lane];
-		const uint4 raw = ldg_keep(reinterpret_cast<const uint4 *>(p.slots) + e.x, l2_keep_policy());
+		const uint4 raw = ldg_keep(reinterpret_cast<const uint4 *>(p.slots) + e.x, p.keep);
 		const uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
 		const uint64_t end = p.range_lo + (uint64_t)e.y * (uint32_t)S + raw.w; /* the k-mer would occupy [end - k, end) */
 		val = raw.z;
@@ -174,26 +183,30 @@ __device__ __forceinline__ uint32_t verify_batch(const AnchorParams &p, const ui
 	return __popc(have);
 }
 
-/* First stage: resolve n <= 32 queued survivors of the filter, one per lane.  Fetch the
- * anchor's home bucket (four tags, one 16-byte load from L2).  Slots fill in scan order and
- * are never freed, so the occupied slots of a bucket are a prefix of it: a tag (never 0) can
- * only match an occupied slot, and the chain ends in this bucket iff its last slot is free.
- * A matching tag (rare: the anchor really is one a pattern carries) goes to the verify queue. */
-template <int S>
+/* filter key of an anchor as the kernel's generic (slow) paths compute it */
+template <bool CANON> __device__ __forceinline__ uint32_t anchor_key(uint32_t a, int L)
+{
+	return CANON ? a * (rc16(a) >> (32 - 2 * L)) : a;
+}
+
+/* First stage: resolve n <= 32 queued anchors, one per lane.  Fetch the anchor's home bucket
+ * (three tags + control word, one 16-byte load from L2); a matching tag (rare: the anchor
+ * really is one a pattern carries) goes to the verify queue; the control word says whether
+ * entries of this chain live further on. */
+template <int S, bool CANON>
 __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uint2 *wq, uint32_t first, uint32_t n,
                                                 uint2 *vq, uint32_t &vn, uint32_t lane, uint32_t lt_mask)
 {
-	const uint32_t bmask = (1u << p.bucket_bits) - 1u;
-	const uint64_t keep = l2_keep_policy();
+	const uint64_t keep = p.keep;
 	bool active = lane < n;
 	uint2 e = make_uint2(0u, 0u);
 	if (active) e = wq[first + lane];
-	const uint32_t tag = vg_tag(e.x);
-	uint32_t b = vg_bucket_home(e.x, p.bucket_bits), hits = 0;
+	const uint32_t tag = vg_tag(e.x, p.len);
+	uint32_t b = vg_bucket_home(vg_hash_lo(anchor_key<CANON>(e.x, p.len), p.filter_words), p.n_buckets), hits = 0;
 	while (__any_sync(FULL, active)) {
-		uint4 t = make_uint4(0u, 0u, 0u, 0u);
-		if (active) t = ldg_keep(p.tags + b, keep);
-		uint32_t mm = (t.x == tag ? 1u : 0u) | (t.y == tag ? 2u : 0u) | (t.z == tag ? 4u : 0u) | (t.w == tag ? 8u : 0u);
+		uint4 t = make_uint4(VG_FREE_TAG, VG_FREE_TAG, VG_FREE_TAG, 0u);
+		if (active) t = ldg_keep(p.buckets + b, keep);
+		uint32_t mm = (t.x == tag ? 1u : 0u) | (t.y == tag ? 2u : 0u) | (t.z == tag ? 4u : 0u);
 		if (!active) mm = 0;
 		while (__any_sync(FULL, mm != 0)) { /* rare: queue one matching slot per lane and round */
 			const bool m = mm != 0;
@@ -205,26 +218,33 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
 				__syncwarp();
 			}
 			if (m) {
-				vq[vn + __popc(votes & lt_mask)] = make_uint2(b * 4 + (uint32_t)(__ffs(mm) - 1), e.y);
+				vq[vn + __popc(votes & lt_mask)] = make_uint2((t.w & ~VG_CTRL_MORE) + (uint32_t)(__ffs(mm) - 1), e.y);
 				mm &= mm - 1;
 			}
 			vn += __popc(votes);
 		}
-		if (t.w == 0) active = false;
-		else b = (b + 1) & bmask;
+		if (!(t.w & VG_CTRL_MORE)) active = false;
+		else b = b + 1 == p.n_buckets ? 0 : b + 1;
 	}
 	return hits;
 }
+
+/* deferred path: what a lane remembers of the survivors of the previous tile */
+template <int NA> struct Pending {
+	uint32_t w[NA];   /* their words of the second filter level, requested a tile ago     */
+	uint32_t pm[NA];  /* the two bits to find there                                       */
+	uint32_t a[NA];   /* the anchors                                                      */
+};
 
 /* state a warp carries through the stream */
 struct Pipe {
 	uint32_t t;        /* next tile to scan                                        */
 	uint32_t c;        /* this lane's chunk in it                                  */
-	const uint4 *ptr;  /* its address                                              */
 	uint32_t cur;      /* that chunk, packed                                       */
 	uint32_t carry;    /* lane 31's packed chunk of the previous tile: lane 0's left neighbour */
-	uint4 w0, w1, w2;  /* raw chunks in flight; buffer `phase` holds tile t+1      */
-	uint32_t phase;
+	uint32_t rcur, rcarry; /* reverse complements of the two (strand-symmetric keys only)  */
+	uint4 w0, w1, w2;  /* raw chunks in flight                                     */
+	uint32_t phase;    /* queue path: buffer `phase` holds tile t+1                */
 	uint32_t qn;       /* entries in the candidate queue                           */
 };
 
@@ -236,156 +256,419 @@ __device__ __forceinline__ uint32_t lds_word(uint32_t base, uint32_t idx, uint32
 	return v;
 }
 
-/* One tile.  `use` holds the raw chunk of tile t+1 (loaded three tiles ago); `fill` is the
- * buffer consumed by the previous tile and is refilled first thing with tile t+3.  The
- * anchors of a chunk end at its aligned offsets and reach back into the LEFT neighbour only
- * (lane-1's chunk, or lane 31's of the previous tile), so nothing in the probes waits for a
- * load; the only consumer of loaded data is the pack at the very end.
+/* The anchors of one chunk and their fate in the filter.  They end at the chunk's aligned
+ * offsets and reach back into the LEFT neighbour only (lane-1's chunk, or lane 31's of the
+ * previous tile), so nothing here waits for a load.
  *   LS  anchor length fixed at compile time (0 = take it from the parameters) */
-template <int S, bool CANON, int LS, bool INTERIOR>
-__device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 &fill, const uint4 &use,
-                                          uint32_t filter, uint32_t bits, uint2 *wq, uint32_t lane, uint32_t lt_mask)
+template <int S, bool CANON, int LS>
+__device__ __forceinline__ void probe_anchors(const AnchorParams &p, uint32_t cur, uint32_t left, uint32_t rcur, uint32_t rleft,
+                                              uint32_t filter, uint32_t pairs, uint32_t (&a)[16 / S], bool (&hit)[16 / S],
+                                              uint32_t (&lo)[16 / S])
 {
-	const uint32_t nw = p.filter_words, last = p.n_chunks - 1;
+	constexpr int NA = 16 / S;
+	const uint32_t nw = p.filter_words;
 	const int L = LS ? LS : p.len;
 	const uint32_t amask = vg_mask32(L);
-	fill = INTERIOR ? ld_stream(s.ptr + 96) : ld_stream(p.chunks + min(s.c + 96, last));
-	if (INTERIOR && p.pf_bytes) l2_prefetch(reinterpret_cast<const uint8_t *>(s.ptr) + p.pf_bytes); /* this lane's chunk, some tiles on */
+#pragma unroll
+	for (int j = 0; j < NA; ++j) {
+		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
+		const int sh = 2 * ((j + 1) * S - L);
+		a[j] = sh >= 0 ? cur >> (sh & 31) : __funnelshift_r(left, cur, (sh + 32) & 31);
+		if (L < 16 && !(sh >= 0 && sh + 2 * L == 32)) a[j] &= amask;
+		uint32_t key = a[j];
+		if (CANON) {
+			/* a * rc(a): the same for an anchor and its reverse complement.  rc(a) is a window of
+			 * the reverse-complemented words: base i of the chunk sits at 15 - i of rcur */
+			const int rsh = 2 * (16 - (j + 1) * S);
+			uint32_t r = rsh == 0 ? rcur : __funnelshift_r(rcur, rleft, rsh & 31);
+			if (L < 16) r &= amask;
+			key = a[j] * r;
+		}
+		const uint64_t prod = (uint64_t)vg_hash1(key) * nw;
+		lo[j] = (uint32_t)prod;
+		const uint32_t word = lds_word(filter, (uint32_t)(prod >> 32), p.c4);
+		const uint32_t pm = lds_word(pairs, vg_pair_index(lo[j]), p.c4);
+		hit[j] = (~word & pm) == 0;
+	}
+}
+
+/* the check of a pending survivor: did it pass the second filter level as well? */
+__device__ __forceinline__ bool passed2(uint32_t w, uint32_t pm) { return (~w & pm) == 0; }
+
+/* ---- queue path ---- */
+
+/* One tile.  `use` holds the raw chunk of tile t+1 (loaded three tiles ago); `fill` is the
+ * buffer consumed by the previous tile and is refilled first thing with tile t+3; the only
+ * consumer of loaded data is the pack at the very end. */
+template <int S, bool CANON, int LS, bool INTERIOR>
+__device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 &fill, const uint4 &use, uint32_t filter,
+                                          uint32_t pairs, uint2 *wq, uint32_t lane, uint32_t lt_mask)
+{
+	constexpr int NA = 16 / S;
+	const uint32_t last = p.n_chunks - 1;
+	fill = ld_stream(p.chunks + (INTERIOR ? s.c + 96 : min(s.c + 96, last)));
+	if (INTERIOR) l2_prefetch_ahead(p.chunks + s.c); /* this lane's chunk, some tiles on */
 	/* one rotate serves both needs: lanes 1..31 get their left neighbour, lane 0 gets lane 31's
 	 * chunk, which is its left neighbour in the NEXT tile */
 	const uint32_t rot = __shfl_sync(FULL, s.cur, (lane + 31) & 31);
 	const uint32_t left = lane == 0 ? s.carry : rot;
+	uint32_t rrot = 0, rleft = 0;
+	if (CANON && NA > 1) {
+		rrot = __shfl_sync(FULL, s.rcur, (lane + 31) & 31);
+		rleft = lane == 0 ? s.rcarry : rrot;
+	}
+	uint32_t a[NA], lo[NA];
+	bool hit[NA];
+	probe_anchors<S, CANON, LS>(p, s.cur, left, s.rcur, rleft, filter, pairs, a, hit, lo);
 #pragma unroll
-	for (int j = 0; j < 16 / S; ++j) {
-		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
-		const int sh = 2 * ((j + 1) * S - L);
-		uint32_t a = sh >= 0 ? s.cur >> (sh & 31) : __funnelshift_r(left, s.cur, (sh + 32) & 31);
-		if (L < 16) a &= amask;
-		uint32_t key = a;
-		if (CANON) { /* a * rc(a), see vg_rc32 */
-			uint32_t r = __brev(a);
-			r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
-			key = a * ((r ^ 0xAAAAAAAAu) >> (32 - 2 * L));
-		}
-		const uint32_t word = lds_word(filter, vg_filter_word(key, nw), p.c4);
-		const uint32_t h2 = vg_hash2(key);
-		const uint32_t m1 = lds_word(bits, __umulhi(h2, p.c32), p.c4);              /* 1 << (h2 >> 27) */
-		const uint32_t m2 = lds_word(bits, __umulhi(vg_hash3(h2), p.c32), p.c4);
-		bool hit = (~word & (m1 | m2)) == 0;
-		if (!INTERIOR) hit = hit && s.c <= last;
-		/* queue the survivors, compacted.  Large panels: nearly every vote has a survivor, so
-		 * the branch around the push is not worth its two instructions */
-		if (CANON || __any_sync(FULL, hit)) {
-			const uint32_t votes = __ballot_sync(FULL, hit);
-			if (hit) wq[s.qn + __popc(votes & lt_mask)] = make_uint2(a, s.c * (16 / S) + j + 1);
+	for (int j = 0; j < NA; ++j) {
+		if (!INTERIOR) hit[j] = hit[j] && s.c <= last;
+		/* queue the survivors, compacted */
+		if (__any_sync(FULL, hit[j])) {
+			const uint32_t votes = __ballot_sync(FULL, hit[j]);
+			if (hit[j]) wq[s.qn + __popc(votes & lt_mask)] = make_uint2(a[j], s.c * NA + j + 1);
 			s.qn += __popc(votes);
 		}
 	}
 	s.carry = rot; /* only lane 0's copy is ever used */
 	s.cur = pack16(use);
+	if (CANON) {
+		s.rcarry = rrot;
+		s.rcur = rc16(s.cur);
+	}
 	++s.t;
 	s.c += 32;
-	s.ptr += 32;
 }
 
-/* The hot loop: scan tiles until the span ends or 32 candidates are queued.  No calls, no
- * table walks.  Three raw buffers rotate by a phase counter instead of by register copies.
- * INTERIOR: every address touched (loads up to tile t1+2, prefetch some tiles further) is
- * inside the range, so nothing is clamped or predicated. */
+/* The hot loop of the queue path: scan tiles until the span ends or 32 candidates are queued.
+ * No calls, no table walks.  Three raw buffers rotate by a phase counter instead of by
+ * register copies.  INTERIOR: every address touched (loads up to tile t1+2, prefetch some
+ * tiles further) is inside the range, so nothing is clamped or predicated. */
 template <int S, bool CANON, int LS, bool INTERIOR>
-__device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, uint32_t filter, uint32_t bits,
+__device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, uint32_t filter, uint32_t pairs,
                                            uint2 *wq, uint32_t lane, uint32_t lt_mask)
 {
 	for (;;) {
 		if (s.phase == 0) {
-			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w2, s.w0, filter, bits, wq, lane, lt_mask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w2, s.w0, filter, pairs, wq, lane, lt_mask);
 			s.phase = 1;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
 		if (s.phase == 1) {
-			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w0, s.w1, filter, bits, wq, lane, lt_mask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w0, s.w1, filter, pairs, wq, lane, lt_mask);
 			s.phase = 2;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
-		scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w1, s.w2, filter, bits, wq, lane, lt_mask);
+		scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w1, s.w2, filter, pairs, wq, lane, lt_mask);
 		s.phase = 0;
 		if (s.t >= t1 || s.qn >= 32) break;
 	}
 }
 
+/* ---- deferred path ---- */
+
+/* what the tiles of a span share; the members a tile needs every time are pinned to
+ * registers (opaque to ptxas, which would otherwise re-read them from the constant bank, or
+ * recompute them, once per tile) */
+struct DeferCtx {
+	uint32_t filter, pairs; /* shared-memory addresses */
+	uint32_t nw, four, nw2, rot_lane;
+	const uint4 *chunks;
+	const uint32_t *filter2;
+	uint64_t keep;
+	uint2 *wq, *vq;
+	uint32_t lane, lt_mask;
+	uint32_t vn, n_cand, n_hits;
+};
+/* a value ptxas must keep in a register: it went through shared memory and came back by a
+ * volatile load, which cannot be repeated */
+__device__ __forceinline__ uint32_t pin(uint32_t v, uint32_t scratch_sa)
+{
+	asm volatile("st.volatile.shared.u32 [%1], %0;\n\tld.volatile.shared.u32 %0, [%1];" : "+r"(v) : "r"(scratch_sa) : "memory");
+	return v;
+}
+template <typename T> __device__ __forceinline__ const T *pin(const T *v, uint32_t scratch_sa)
+{
+	unsigned long long u = reinterpret_cast<unsigned long long>(v);
+	asm volatile("st.volatile.shared.u64 [%1], %0;\n\tld.volatile.shared.u64 %0, [%1];" : "+l"(u) : "r"(scratch_sa) : "memory");
+	return reinterpret_cast<const T *>(u);
+}
+
+/* the rare branch of the deferred path: queue the flagged anchors of the tile whose lane
+ * chunk is `c`; the caller leaves the streaming loop when 32 are waiting */
+template <int S, int LS>
+__device__ __forceinline__ void defer_slow(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, uint32_t c, DeferCtx &x)
+{
+	constexpr int NA = 16 / S;
+#pragma unroll
+	for (int j = 0; j < NA; ++j) {
+		const bool flag = passed2(pd.w[j], pd.pm[j]);
+		const uint32_t votes = __ballot_sync(FULL, flag);
+		if (flag) x.wq[s.qn + __popc(votes & x.lt_mask)] = make_uint2(pd.a[j], c * NA + j + 1);
+		s.qn += __popc(votes);
+	}
+}
+
+template <int S, int LS>
+__device__ __forceinline__ void defer_check(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, uint32_t c, DeferCtx &x)
+{
+	constexpr int NA = 16 / S;
+	bool any = false;
+#pragma unroll
+	for (int j = 0; j < NA; ++j) any = any || passed2(pd.w[j], pd.pm[j]);
+	if (__any_sync(FULL, any)) defer_slow<S, LS>(p, s, pd, c, x);
+}
+
+/* the probes of one tile, waiting for their turn at the second filter level: the anchors,
+ * their bit pairs, and the word to fetch for those that passed the first level
+ * (VG_NO_WORD otherwise) */
+#define VG_NO_WORD 0xFFFFFFFFu
+template <int NA> struct Probed {
+	uint32_t a[NA], pm[NA], word2[NA];
+};
+
+/* probe the anchors of the tile in s.cur */
+template <int S, int LS, bool INTERIOR>
+__device__ __forceinline__ void defer_probe(const AnchorParams &p, Pipe &s, Probed<16 / S> &nx, DeferCtx &x)
+{
+	constexpr int NA = 16 / S;
+	const int L = LS ? LS : p.len;
+	const uint32_t amask = vg_mask32(L);
+	/* one rotate serves both needs: lanes 1..31 get their left neighbour, lane 0 gets lane 31's
+	 * chunk, which is its left neighbour in the NEXT tile */
+	const uint32_t rot = __shfl_sync(FULL, s.cur, x.rot_lane);
+	const uint32_t left = x.lane == 0 ? s.carry : rot;
+	uint32_t rrot = 0, rleft = 0;
+	if (NA > 1) {
+		rrot = __shfl_sync(FULL, s.rcur, x.rot_lane);
+		rleft = x.lane == 0 ? s.rcarry : rrot;
+	}
+#pragma unroll
+	for (int j = 0; j < NA; ++j) {
+		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
+		const int sh = 2 * ((j + 1) * S - L);
+		uint32_t a = sh >= 0 ? s.cur >> (sh & 31) : __funnelshift_r(left, s.cur, (sh + 32) & 31);
+		if (L < 16 && !(sh >= 0 && sh + 2 * L == 32)) a &= amask;
+		/* a * rc(a): the same for an anchor and its reverse complement.  rc(a) is a window of
+		 * the reverse-complemented words: base i of the chunk sits at 15 - i of rcur */
+		const int rsh = 2 * (16 - (j + 1) * S);
+		uint32_t r = rsh == 0 ? s.rcur : __funnelshift_r(s.rcur, rleft, rsh & 31);
+		if (L < 16) r &= amask;
+		const uint64_t prod = (uint64_t)vg_hash1(a * r) * x.nw;
+		const uint32_t lo = (uint32_t)prod;
+		const uint32_t word = lds_word(x.filter, (uint32_t)(prod >> 32), x.four);
+		const uint32_t pm = lds_word(x.pairs, vg_pair_index(lo), x.four);
+		bool hit = (~word & pm) == 0;
+		if (!INTERIOR) hit = hit && s.c <= p.n_chunks - 1;
+		nx.a[j] = a;
+nx.pm[j] = pm;
+		nx.word2[j] = hit ? vg_mulhi(vg_pair_frac(lo), x.nw2) : VG_NO_WORD;
+	}
+	s.carry = rot; /* only lane 0's copy is ever used */
+	s.rcarry = rrot;
+}
+
+/* One step of the deferred path's software pipeline.  On entry the probes of tile k-1 are in
+ * `nx`, the second-level words its predecessor's survivors asked for are in flight in `pd`,
+ * s.c is the lane's chunk of tile k (raw in `use`, loaded a step ago).  ptxas tracks every
+ * global load of this kernel with ONE scoreboard, so whoever waits for a load waits for all
+ * loads issued so far.  The step is therefore arranged around a single wait:
+ *   first everything that consumes a load: the words of tile k-2's survivors are looked at,
+ *     tile k is packed;
+ *   then every new load: the words for tile k-1's survivors, and the refill of the raw buffer
+ *     the previous step packed (tile k+1; the L2 prefetch runs further ahead);
+ *   then the probes of tile k, which carry over to the next step.
+ * Each load so gets one whole step to arrive.  (The refill sits behind the previous step's
+ * closing branch, not next to the pack that emptied its buffer: there ptxas hoists it above
+ * the pack's last reads and then needs a temporary -- and a copy that waits for the load.) */
+template <int S, int LS, bool INTERIOR>
+__device__ __forceinline__ void defer_step(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, Probed<16 / S> &nx, uint4 &fill,
+                                           const uint4 &use, DeferCtx &x)
+{
+	constexpr int NA = 16 / S;
+	const uint32_t last = p.n_chunks - 1;
+	/* everything that consumes a load first ... */
+	defer_check<S, LS>(p, s, pd, s.c - 64, x);
+	s.cur = pack16(use);
+	s.rcur = rc16(s.cur);
+	/* ... then every new load.  A lane without a survivor keeps the word of an older one.  That
+	 * can only cause a false alarm (the stale word happens to hold the new pair), never a miss:
+	 * an anchor some pattern carries passes the first level, so its word is fetched afresh; and
+	 * whatever is flagged is resolved exactly by drain_queue. */
+#pragma unroll
+	for (int j = 0; j < NA; ++j) {
+		pd.a[j] = nx.a[j];
+		pd.pm[j] = nx.pm[j];
+		if (nx.word2[j] != VG_NO_WORD) pd.w[j] = ldg_keep(x.filter2 + nx.word2[j], x.keep);
+	}
+	fill = ld_stream(x.chunks + (INTERIOR ? s.c + 32 : min(s.c + 32, last)));
+	if (INTERIOR) l2_prefetch_ahead(x.chunks + s.c + 32);
+	defer_probe<S, LS, INTERIOR>(p, s, nx, x);
+	++s.t;
+	s.c += 32;
+}
+
+/* The hot loop of the deferred path: tiles from s.t up to t1, or until 32 anchors are queued
+ * for the resolver (the caller runs it and comes back).  s.cur and s.w0 hold tiles s.t and
+ * s.t + 1 on entry, s.c is the lane's chunk of tile s.t, pd is empty.  The pipeline probes one
+ * tile past the last one whose buckets it requests (that tile is probed again by whoever scans
+ * it).  On return tiles up to s.t - 1 are done except for the buckets in pd (tile s.t - 1,
+ * lane chunk s.c - 32), which the caller looks at. */
+template <int S, int LS, bool INTERIOR>
+__device__ __forceinline__ void defer_span(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, uint32_t t1, DeferCtx &x)
+{
+	constexpr int NA = 16 / S;
+	Probed<NA> nx;
+	defer_probe<S, LS, INTERIOR>(p, s, nx, x); /* tile s.t */
+	++s.t;
+	s.c += 32;
+	/* from here s.t counts probed tiles; a step probes tile s.t and requests the buckets of tile s.t - 1 */
+	for (;;) {
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w1, s.w0, x);
+		if (s.t > t1 || s.qn >= 32) break;
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w0, s.w1, x);
+		if (s.t > t1 || s.qn >= 32) break;
+	}
+	/* back to "s.t = next tile to scan": the last probed tile (s.t - 1) has no buckets requested */
+	--s.t;
+	s.c -= 32;
+}
+
 /* The streaming kernel.  One CTA per SM, persistent over spans of tiles (a tile = 32 chunks
  * of 16 bytes = one 128-bit load per lane).
  *   CANON  the filter holds strand-symmetric keys, which halves its load for large panels;
- *          small panels file both orientations and skip the reverse complement. */
-template <int S, bool CANON, int LS>
-__global__ void __launch_bounds__(Launch<S>::kThreads, 1) anchor_scan_kernel(const __grid_constant__ AnchorParams p)
+ *          small panels file both orientations and skip the reverse complement
+ *   DEFER  survivors request their home bucket at once and inspect it during the next tile;
+ *          only tag matches and chained buckets (both rare) go to the queue */
+template <int S, bool CANON, bool DEFER, int LS>
+__global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_kernel(const __grid_constant__ AnchorParams p)
 {
-	extern __shared__ uint32_t s_filter[]; /* filter words | 32-word bit table | candidate queues */
+	extern __shared__ uint32_t s_filter[]; /* filter words | bit-pair table | candidate queues */
+	using LC = Launch<S, DEFER>;
+	constexpr int NA = 16 / S;
 	const uint32_t nw = p.filter_words;
 	{ /* stage the filter */
 		const uint4 *src = reinterpret_cast<const uint4 *>(p.filter);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
 		for (uint32_t i = threadIdx.x; i < nw / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-		if (threadIdx.x < 32) s_filter[nw + threadIdx.x] = 1u << threadIdx.x;
+		for (uint32_t i = threadIdx.x; i < VG_PAIRS; i += blockDim.x) s_filter[nw + i] = vg_pair_mask(i);
 	}
 	__syncthreads();
 	const uint32_t filter_sa = (uint32_t)__cvta_generic_to_shared(s_filter);
-	const uint32_t bits_sa = filter_sa + nw * 4;
+	const uint32_t pairs_sa = filter_sa + nw * 4;
 
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nw + 32) + (threadIdx.x >> 5) * Launch<S>::kQueue;
-	uint2 *const vq = wq + Launch<S>::kQueue - 32; /* the last 32 entries: tag matches awaiting verification */
-	uint32_t vn = 0;
+	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nw + VG_PAIR_TABLE_BYTES / 4) + (threadIdx.x >> 5) * LC::kQueue;
+	uint2 *const vq = wq + LC::kQueue - 32; /* the last 32 entries: tag matches awaiting verification */
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
 	const uint32_t n_warps = gridDim.x * warps_per_cta;
 	const uint32_t last = p.n_chunks - 1;
-	uint32_t n_cand = 0, n_hits = 0;
 	Pipe s;
 	s.qn = 0;
 	s.t = 0;
 	s.phase = 0;
-	uint32_t t1 = 0, span = warp;
+	s.rcur = s.rcarry = 0;
+	uint32_t t1 = 0;
 	bool interior = false;
 
+	/* open span number `span`: prime the register pipeline (tile t is scanned while t+1 is being
+	 * packed and t+2 is in flight; the L2 prefetch runs 8 tiles ahead of that) */
+	auto open_span = [&](uint32_t t0, uint32_t t_end) {
+		s.t = t0;
+		t1 = t_end;
+		/* Interior span: everything the pipeline touches (loads up to tile t1+2, prefetch 8 tiles
+		 * beyond) lies inside the range.  Otherwise loads are clamped to the last chunk: a
+		 * chunk past the end is never scanned, and as a right neighbour it can only create a
+		 * false candidate, which the bounds check of the verification rejects. */
+		interior = (uint64_t)(t1 + 5 + VG_PF_BYTES / 512) * 32 <= p.n_chunks;
+		s.c = s.t * 32 + lane;
+		if (interior && VG_PF_BYTES) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * (VG_PF_BYTES / 32));
+		s.cur = pack16(ld_stream(p.chunks + min(s.c, last)));
+		s.w0 = ld_stream(p.chunks + min(s.c + 32, last));
+		if (!DEFER) s.w1 = ld_stream(p.chunks + min(s.c + 64, last));
+		s.phase = 0;
+		/* the chunk before the span: the last one of the previous span, or of the previous
+		 * launch range; nothing ('\n's) at the very start of the stream */
+		const uint32_t c0 = s.t * 32;
+		uint4 before = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+		if (c0 > 0 || p.range_lo > 0) before = __ldg(p.chunks + c0 - 1); /* chunks[-1] exists when range_lo > 0 */
+		s.carry = pack16(before);
+		if (CANON) {
+			s.rcur = rc16(s.cur);
+			s.rcarry = rc16(s.carry);
+		}
+	};
+
+	if (DEFER) {
+		DeferCtx x;
+		const uint32_t z = (uint32_t)__cvta_generic_to_shared(vq + lane); /* scratch: this lane's verify-queue entry, not in use yet */
+		x.filter = pin(filter_sa, z), x.pairs = pin(pairs_sa, z), x.keep = p.keep, x.wq = wq, x.vq = vq, x.lane = lane, x.lt_mask = lt_mask;
+		x.nw = pin(nw, z), x.four = pin(p.c4, z), x.nw2 = pin(p.filter2_words, z), x.rot_lane = pin((lane + 31) & 31, z);
+		x.chunks = pin(p.chunks, z), x.filter2 = pin(p.filter2, z);
+		x.vn = x.n_cand = x.n_hits = 0;
+		Pending<NA> pd;
+#pragma unroll
+		for (int j = 0; j < NA; ++j) {
+			pd.w[j] = pd.a[j] = 0;
+			pd.pm[j] = 1;
+		}
+		auto drain_full = [&]() {
+			while (s.qn >= 32) {
+				s.qn -= 32;
+				x.n_cand += 32;
+				__syncwarp();
+				x.n_hits += drain_queue<S, true>(p, wq, s.qn, 32, vq, x.vn, lane, lt_mask);
+				__syncwarp();
+			}
+		};
+		for (uint32_t span = warp; span < p.n_spans; span += n_warps) {
+			open_span(span * p.tiles_per_span, min((span + 1) * p.tiles_per_span, p.n_tiles));
+			for (;;) {
+				if (interior) defer_span<S, LS, true>(p, s, pd, t1, x);
+				else defer_span<S, LS, false>(p, s, pd, t1, x);
+				/* the survivors of the last tile scanned; the queue takes one tile's worth above 31 entries */
+				drain_full();
+				defer_check<S, LS>(p, s, pd, s.c - 32, x);
+				drain_full();
+#pragma unroll
+				for (int j = 0; j < NA; ++j) pd.w[j] = 0;
+				if (s.t >= t1) break;
+				open_span(s.t, t1); /* back into the span where the resolver interrupted it */
+			}
+		}
+		if (s.qn) {
+			x.n_cand += s.qn;
+			__syncwarp();
+			x.n_hits += drain_queue<S, true>(p, wq, 0, s.qn, vq, x.vn, lane, lt_mask);
+			__syncwarp();
+		}
+		if (x.vn) x.n_hits += verify_batch<S>(p, vq, x.vn, lane);
+		if (lane == 0 && (x.n_cand | x.n_hits)) {
+			atomicAdd(&p.stats[ST_CANDIDATES], (unsigned long long)x.n_cand);
+			atomicAdd(&p.stats[ST_HITS], (unsigned long long)x.n_hits);
+		}
+		return;
+	}
+
+	uint32_t vn = 0, n_cand = 0, n_hits = 0, span = warp;
 	for (;;) {
-		if (s.t >= t1 && span < p.n_spans) { /* open the next span */
-			s.t = span * p.tiles_per_span;
-			t1 = min(s.t + p.tiles_per_span, p.n_tiles);
+		if (s.t >= t1 && span < p.n_spans) {
+			open_span(span * p.tiles_per_span, min((span + 1) * p.tiles_per_span, p.n_tiles));
 			span += n_warps;
-			/* Interior span: everything the pipeline touches (loads up to tile t1+1, prefetch up
-			 * to tile t1+7) lies inside the range.  Otherwise loads are clamped to the last
-			 * chunk: a chunk past the end is never scanned, and as a right neighbour it can only
-			 * create a false candidate, which the bounds check of the verification rejects. */
-			interior = (uint64_t)(t1 + 34) * 32 <= p.n_chunks;
-			s.c = s.t * 32 + lane;
-			s.ptr = p.chunks + s.c;
-			if (interior && p.pf_bytes) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * (p.pf_bytes / 32));
-			/* register pipeline: tile t is scanned while t+1 is being packed and t+2 is in
-			 * flight; the L2 prefetch runs 8 tiles ahead of that */
-			s.cur = pack16(ld_stream(p.chunks + min(s.c, last)));
-			s.w0 = ld_stream(p.chunks + min(s.c + 32, last));
-			s.w1 = ld_stream(p.chunks + min(s.c + 64, last));
-			s.phase = 0;
-			/* the chunk before the span: the last one of the previous span, or of the previous
-			 * launch range; nothing ('\n's) at the very start of the stream */
-			const uint32_t c0 = s.t * 32;
-			uint4 before = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
-			if (c0 > 0 || p.range_lo > 0) before = __ldg(p.chunks + c0 - 1); /* chunks[-1] exists when range_lo > 0 */
-			s.carry = pack16(before);
 		}
 		const bool finished = s.t >= t1; /* no span left */
 		if (!finished) {
-			if (interior) scan_tiles<S, CANON, LS, true>(p, s, t1, filter_sa, bits_sa, wq, lane, lt_mask);
-			else scan_tiles<S, CANON, LS, false>(p, s, t1, filter_sa, bits_sa, wq, lane, lt_mask);
+			if (interior) scan_tiles<S, CANON, LS, true>(p, s, t1, filter_sa, pairs_sa, wq, lane, lt_mask);
+			else scan_tiles<S, CANON, LS, false>(p, s, t1, filter_sa, pairs_sa, wq, lane, lt_mask);
 		}
 		if (s.qn >= 32 || (finished && s.qn)) { /* the one place candidates are resolved */
 			const uint32_t n = min(s.qn, 32u);
 			s.qn -= n;
 			n_cand += n;
 			__syncwarp();
-			n_hits += drain_queue<S>(p, wq, s.qn, n, vq, vn, lane, lt_mask);
+			n_hits += drain_queue<S, CANON>(p, wq, s.qn, n, vq, vn, lane, lt_mask);
 			__syncwarp();
 		} else if (finished) break;
 	}
@@ -458,32 +741,55 @@ __global__ void __launch_bounds__(256) recipe_scan_kernel(const ScanArgs a)
 /* ------------------------------------------------------------------------------------ */
 /* launchers                                                                              */
 
-template <int S, bool CANON, int LS>
-static cudaError_t launch_one(const AnchorParams &p0, uint32_t filter_words, int n_sm, cudaStream_t stream)
+template <int S, bool CANON, bool DEFER, int LS>
+static cudaError_t launch_one(const AnchorParams &p0, int n_sm, cudaStream_t stream)
 {
 	AnchorParams p = p0;
-	const int threads = Launch<S>::kThreads;
-	const size_t smem = (size_t)filter_words * 4 + 128 + Launch<S>::kQueueBytes;
+	const int threads = Launch<S, DEFER>::kThreads;
+	const size_t smem = (size_t)p.filter_words * 4 + VG_PAIR_TABLE_BYTES + Launch<S, DEFER>::kQueueBytes;
 	static bool opted_in[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 64 && !opted_in[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(anchor_scan_kernel<S, CANON, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		cudaError_t e = cudaFuncSetAttribute(anchor_scan_kernel<S, CANON, DEFER, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                     VG_SMEM_BUDGET);
 		if (e != cudaSuccess) return e;
 		opted_in[dev] = true;
 	}
 	const uint32_t resident_warps = (uint32_t)n_sm * (threads / 32);
 	uint32_t tps = p.n_tiles / (resident_warps * 4u);
-	p.tiles_per_span = tps < 1 ? 1 : (tps > 64 ? 64 : tps);
+	static const uint32_t cap = getenv("VAFGPU_SPAN_CAP") ? (uint32_t)atoi(getenv("VAFGPU_SPAN_CAP")) : 64u; /* tuning knob */
+	p.tiles_per_span = tps < 1 ? 1 : (tps > cap ? cap : tps);
 	p.n_spans = (p.n_tiles + p.tiles_per_span - 1) / p.tiles_per_span;
 	uint32_t ctas = (p.n_spans + (threads / 32) - 1) / (threads / 32);
 	if (ctas > (uint32_t)n_sm) ctas = (uint32_t)n_sm;
-	anchor_scan_kernel<S, CANON, LS><<<ctas, threads, smem, stream>>>(p);
+	anchor_scan_kernel<S, CANON, DEFER, LS><<<ctas, threads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 
-cudaError_t kernels_init_device(int) { return cudaSuccess; }
+__global__ void make_policy_kernel(uint64_t *out) { *out = l2_keep_policy(); }
+
+cudaError_t kernels_make_policy(uint64_t *policy)
+{
+	uint64_t *d = nullptr;
+	cudaError_t e = cudaMalloc(&d, sizeof *d);
+	if (e != cudaSuccess) return e;
+	make_policy_kernel<<<1, 1>>>(d);
+	e = cudaMemcpy(policy, d, sizeof *d, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	return e;
+}
+
+template <int S, int LS>
+static cudaError_t launch_plan(const AnchorParams &p, const ScanArgs &a, int n_sm, cudaStream_t stream)
+{
+	if (a.canon && a.defer) {
+		if constexpr (VG_DEFER_OK(S)) return launch_one<S, true, true, LS>(p, n_sm, stream);
+		else return cudaErrorInvalidValue;
+	}
+	if (a.canon) return launch_one<S, true, false, LS>(p, n_sm, stream);
+	return launch_one<S, false, false, LS>(p, n_sm, stream);
+}
 
 cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream)
 {
@@ -504,30 +810,25 @@ cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream)
 		p.stats = a.stats;
 		p.filter = a.filter;
 		p.filter_words = a.filter_words;
-		p.tags = reinterpret_cast<const uint4 *>(a.tags);
+		p.filter2 = a.filter2;
+		p.filter2_words = a.filter2_words;
+		p.buckets = reinterpret_cast<const uint4 *>(a.buckets);
+		p.n_buckets = a.n_buckets;
 		p.slots = a.slots;
-		p.bucket_bits = a.bucket_bits;
 		p.k = a.k;
 		p.len = a.len;
-		{
-			static const char *env = getenv("VAFGPU_PF_TILES"); /* tuning knob: tiles of L2 prefetch lead, <= 32 */
-			int tiles = env ? atoi(env) : 8;
-			p.pf_bytes = (uint32_t)(tiles < 0 ? 0 : tiles > 32 ? 32 : tiles) * 512u;
-		}
-		cudaError_t e;
+		p.keep = a.keep_policy;
 		p.c4 = 4;
-		p.c32 = 32;
+		cudaError_t e;
 		/* the headline plans (k = 15, 21, 31) get the anchor length as a compile-time constant */
-#define GO(S, LS) e = a.canon ? launch_one<S, true, LS>(p, a.filter_words, n_sm, stream) : launch_one<S, false, LS>(p, a.filter_words, n_sm, stream)
 		switch (a.stride) {
-		case 1: GO(1, 0); break;
-		case 2: GO(2, 0); break;
-		case 4: if (a.len == 12) GO(4, 12); else GO(4, 0); break;
-		case 8: if (a.len == 14) GO(8, 14); else GO(8, 0); break;
-		case 16: if (a.len == 16) GO(16, 16); else GO(16, 0); break;
+		case 1: e = launch_plan<1, 0>(p, a, n_sm, stream); break;
+		case 2: e = launch_plan<2, 0>(p, a, n_sm, stream); break;
+		case 4: e = a.len == 12 ? launch_plan<4, 12>(p, a, n_sm, stream) : launch_plan<4, 0>(p, a, n_sm, stream); break;
+		case 8: e = a.len == 14 ? launch_plan<8, 14>(p, a, n_sm, stream) : launch_plan<8, 0>(p, a, n_sm, stream); break;
+		case 16: e = a.len == 16 ? launch_plan<16, 16>(p, a, n_sm, stream) : launch_plan<16, 0>(p, a, n_sm, stream); break;
 		default: return cudaErrorInvalidValue;
 		}
-#undef GO
 		if (e != cudaSuccess) return e;
 	}
 	return cudaSuccess;

@@ -22,20 +22,24 @@ struct ScanArgs {
 	int k;
 	/* anchor-filter kernel */
 	int stride, len;
-	int canon;             /* the filter holds canonical anchors */
+	int canon;             /* the filter holds strand-symmetric keys */
+	int defer;             /* deferred-lookup form (shared-memory split computed for it) */
 	const uint32_t *filter;
 	uint32_t filter_words;
-	const uint32_t *tags;
+	const uint32_t *filter2; /* second filter level (deferred form), L2-resident */
+	uint32_t filter2_words;
+	const uint32_t *buckets; /* exact table: four words per bucket */
+	uint32_t n_buckets;    /* one more, empty, bucket follows the table               */
 	const vg_slot_t *slots;
-	uint32_t bucket_bits;
+	uint64_t keep_policy;  /* from kernels_make_policy() on this device               */
 	/* recipe kernel */
 	const uint64_t *rkeys;
 	const uint32_t *rvals;
 	uint32_t rbits;
 };
 
-/* one-time per-device set-up (shared-memory opt-in); returns cudaSuccess or the error */
-cudaError_t kernels_init_device(int n_sm);
+/* one-time per-device set-up: the L2 evict-last access policy the table loads carry */
+cudaError_t kernels_make_policy(uint64_t *policy);
 
 /* asynchronous launches on `stream` */
 cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream);

@@ -16,6 +16,7 @@
 #include "vafgpu_tables.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <unordered_set>
 
 namespace vafgpu {
@@ -107,33 +108,60 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	}
 	out.n_entries = (uint32_t)items.size();
 
-	/* Filter: two bits per key in one 32-bit word.  A panel small enough to get >= 64 bits
+	/* Filter: two bits per key in one 32-bit word.  A panel small enough to get >= 24 bits
 	 * per key with both orientations filed keeps them (the kernel then hashes the forward
 	 * anchor as it is); a large panel files strand-symmetric keys, halving the load of the
-	 * filter at the price of a reverse complement per anchor in the kernel. */
-	const uint32_t budget = VG_FILTER_BUDGET_WORDS(S);
-	out.canon = (uint64_t)plain.size() * 24 > (uint64_t)budget * 32; /* < 24 bits per key */
+	 * filter at the price of a reverse complement per chunk in the kernel, and, its filter
+	 * letting every tenth anchor through, is scanned by the deferred-lookup form of the kernel. */
+	out.canon = (uint64_t)plain.size() * 24 > (uint64_t)VG_FILTER_BUDGET_WORDS(S, 0) * 32;
+	out.defer = out.canon && VG_DEFER_OK(S);
+	out.threads = VG_THREADS(S, out.defer);
+	const uint32_t budget = VG_FILTER_BUDGET_WORDS(S, out.defer);
 	const std::unordered_set<uint32_t> &fkeys = out.canon ? canon : plain;
 	out.n_filter_keys = (uint32_t)fkeys.size();
 	uint64_t want = (uint64_t)out.n_filter_keys * 2;
 	uint32_t nw = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, VG_MIN_FILTER_WORDS), budget);
 	nw = (nw + 3u) & ~3u;
 	out.filter.assign(nw, 0);
-	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_filter_mask(key);
+	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_filter_mask(key, nw);
+	/* second level: 4 words (128 bits) per key, at least a page */
+	const uint32_t nw2 = out.defer ? (uint32_t)std::max<uint64_t>(1024, (uint64_t)out.n_filter_keys * 4) : 4;
+	out.filter2.assign(nw2, 0);
+	if (out.defer)
+		for (uint32_t key : fkeys) out.filter2[vg_filter2_word(key, nw, nw2)] |= vg_filter_mask(key, nw);
 
-	/* exact table at <= 1/6 load, buckets of four slots: a full home bucket (a second L2
-	 * round trip for the whole warp) is then rare */
-	uint32_t bits = 2;
-	while ((4ull << bits) < (uint64_t)items.size() * 6) ++bits;
-	out.bucket_bits = bits;
-	const size_t n_slots = (size_t)4 << bits;
-	out.tags.assign(n_slots, 0);
-	out.slots.assign(n_slots, vg_slot_t{VG_EMPTY_KEY, 0, 0});
-	for (const Item &it : items) {
-		size_t s = (size_t)vg_bucket_home(it.anchor, bits) * 4;
-		while (out.tags[s]) s = (s + 1) & (n_slots - 1);
-		out.tags[s] = vg_tag(it.anchor);
-		out.slots[s] = vg_slot_t{it.okey, it.val, it.off};
+	/* exact table at <= 1/6 load, buckets of three tags: a full home bucket (a second L2
+	 * round trip) is then rare.  Items are placed in the order they were generated, so a
+	 * bucket's entries are consecutive in the payload array if we emit payloads bucket by
+	 * bucket afterwards. */
+	const char *bf = getenv("VAFGPU_BUCKET_FACTOR"); /* tuning knob */
+	const uint32_t nb = (uint32_t)std::max<uint64_t>(64, (uint64_t)items.size() * (bf ? atoi(bf) : 2));
+	out.n_buckets = nb;
+	std::vector<uint32_t> fill(nb, 0), where(items.size());
+	std::vector<uint8_t> more(nb, 0);
+	for (size_t i = 0; i < items.size(); ++i) {
+		const uint32_t key = vg_filter_key(items[i].anchor, L, out.canon);
+		uint32_t b = vg_bucket_home(vg_hash_lo(key, nw), nb);
+		while (fill[b] == 3) {
+			more[b] = 1;
+			b = b + 1 == nb ? 0 : b + 1;
+		}
+		++fill[b];
+		where[i] = b;
+	}
+	out.buckets.assign((size_t)(nb + 1) * 4, VG_FREE_TAG); /* + the empty bucket lanes without a survivor fetch */
+	out.buckets[(size_t)nb * 4 + 3] = 0;
+	out.slots.assign(items.size() ? items.size() : 1, vg_slot_t{VG_EMPTY_KEY, 0, 0});
+	uint32_t base = 0;
+	for (uint32_t b = 0; b < nb; ++b) {
+		out.buckets[(size_t)b * 4 + 3] = base | (more[b] ? VG_CTRL_MORE : 0u);
+		base += fill[b];
+		fill[b] = 0; /* reused as the number of entries emitted so far */
+	}
+	for (size_t i = 0; i < items.size(); ++i) {
+		const uint32_t b = where[i], pos = fill[b]++;
+		out.buckets[(size_t)b * 4 + pos] = vg_tag(items[i].anchor, L);
+		out.slots[(out.buckets[(size_t)b * 4 + 3] & ~VG_CTRL_MORE) + pos] = vg_slot_t{items[i].okey, items[i].val, items[i].off};
 	}
 }
 

@@ -34,9 +34,12 @@ struct AnchorTables {
 	std::vector<uint32_t> filter; /* blocked Bloom filter over the anchors                 */
 	bool canon = false;           /* filter keys are canonical anchors (large panels) rather
 	                                 than both orientations of every anchor (small panels)  */
-	uint32_t bucket_bits = 2;     /* the exact table has 4 << bucket_bits slots             */
-	std::vector<uint32_t> tags;   /* vg_tag(forward anchor), 0 = free                      */
-	std::vector<vg_slot_t> slots; /* payload of the slot with the same index              */
+	bool defer = false;           /* scanned by the deferred-lookup form of the kernel       */
+	int threads = 0;              /* CTA size the shared-memory split was computed for      */
+	std::vector<uint32_t> filter2;/* second level of the filter, L2-resident (deferred form) */
+	uint32_t n_buckets = 0;       /* buckets of the exact table                             */
+	std::vector<uint32_t> buckets;/* four words per bucket: three tags + control word        */
+	std::vector<vg_slot_t> slots; /* payloads, a bucket's entries consecutive               */
 	uint32_t n_entries = 0;       /* (oriented key, offset) pairs filed                  */
 	uint32_t n_filter_keys = 0;   /* distinct keys in the filter                         */
 };

@@ -20,7 +20,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvafgpu.so")
+LIB_PATH = os.environ.get("VAFGPU_LIB") or os.path.join(_HERE, "libvafgpu.so")  # VAFGPU_LIB: a differently tuned build (development)
 
 F_REFERENCE_RECIPE = 1
 F_HOST_MERGE = 2

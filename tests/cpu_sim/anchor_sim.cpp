@@ -54,10 +54,10 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 	AnchorTables t;
 	build_anchor_tables(k, keys, vals, n, t);
 	const int S = t.plan.stride, L = t.plan.len;
-	const uint32_t amask = vg_mask32(L), bmask = (1u << t.bucket_bits) - 1;
+	const uint32_t amask = vg_mask32(L);
 	const uint32_t nw = (uint32_t)t.filter.size();
 	if (info) {
-		info[0] = S, info[1] = L, info[2] = nw, info[3] = t.bucket_bits;
+		info[0] = S, info[1] = L, info[2] = nw, info[3] = t.n_buckets;
 		info[4] = t.n_entries, info[5] = t.n_filter_keys | (t.canon ? 0x80000000u : 0);
 	}
 	uint64_t n_cand = 0;
@@ -70,17 +70,15 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 			const int s0 = (j + 1) * S - L; /* anchor = bases [s0, s0 + L) relative to the chunk */
 			uint32_t a = (s0 >= 0 ? cur >> 2 * s0 : funnel_r(left, cur, 2 * (s0 + 16))) & amask;
 			uint32_t key = vg_filter_key(a, L, t.canon);
-			uint32_t m = vg_filter_mask(key);
+			uint32_t m = vg_filter_mask(key, nw);
 			if ((t.filter[vg_filter_word(key, nw)] & m) != m) continue;
 			++n_cand;
 			uint64_t q = 16 * c + (uint64_t)(j + 1) * S; /* aligned end of the anchor */
-			bool open_slot = false;
-			for (uint32_t bk = vg_bucket_home(a, t.bucket_bits); !open_slot; bk = (bk + 1) & bmask) {
-				for (int i = 0; i < 4 && !open_slot; ++i) {
-					uint32_t tag = t.tags[(size_t)bk * 4 + i];
-					if (tag == 0) { open_slot = true; break; }
-					if (tag != vg_tag(a)) continue;
-					const vg_slot_t &e = t.slots[(size_t)bk * 4 + i];
+			for (uint32_t bk = vg_bucket_home(vg_hash_lo(key, nw), t.n_buckets);; bk = bk + 1 == t.n_buckets ? 0 : bk + 1) {
+				const uint32_t ctrl = t.buckets[(size_t)bk * 4 + 3];
+				for (int i = 0; i < 3; ++i) {
+					if (t.buckets[(size_t)bk * 4 + i] != vg_tag(a, L)) continue;
+					const vg_slot_t &e = t.slots[(ctrl & ~VG_CTRL_MORE) + i];
 					const uint64_t end = q + e.off;
 					if (((uint32_t)(e.okey >> 2 * (k - e.off - L)) & amask) != a || end < (uint64_t)k || end > n_bytes) continue;
 					const uint8_t *b = bytes + (end - k);
@@ -92,6 +90,7 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 					}
 					if (ok && km == e.okey) ++counts[e.val];
 				}
+				if (!(ctrl & VG_CTRL_MORE)) break;
 			}
 		}
 	}

@@ -338,7 +338,7 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	build_recipe_table(k, keys, vals, n_entries, n_patterns, rt);
 	build_anchor_tables(k, keys, vals, n_entries, at);
 	c->plan = at.plan;
-	c->filter_words = (uint32_t)at.filter.size();
+	c->filter_words = at.filter_words;
 	c->filter2_words = (uint32_t)at.filter2.size();
 	c->n_buckets = at.n_buckets;
 	c->canon = at.canon;

@@ -23,8 +23,11 @@
 #define VG_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define VG_SMEM_BUDGET (227 * 1024) /* dynamic shared memory per CTA on sm_100: filter + bit-pair table + candidate queues */
 #define VG_MIN_FILTER_WORDS 1024u
+#ifndef VG_PAIR_ALU
+#define VG_PAIR_ALU 1               /* bit pair of a key: made with shifts (1) or read from a shared-memory table (0) */
+#endif
 #define VG_PAIRS 992u               /* ordered pairs of distinct bit positions in a 32-bit word */
-#define VG_PAIR_TABLE_BYTES 4096
+#define VG_PAIR_TABLE_BYTES (VG_PAIR_ALU ? 0 : 4096)
 
 /* Launch geometry of the anchor kernel, shared with the table builder because the candidate
  * queues and the filter split one shared-memory budget.
@@ -109,17 +112,24 @@ VG_HD uint32_t vg_hash1(uint32_t key) { return key * 0x9E3779B1u; }
 VG_HD uint32_t vg_filter_word(uint32_t key, uint32_t n_words) { return vg_mulhi(vg_hash1(key), n_words); }
 VG_HD uint32_t vg_hash_lo(uint32_t key, uint32_t n_words) { return vg_hash1(key) * n_words; }
 
-/* Blocked Bloom filter: one 32-bit word per key, two distinct bits in it.  The pair comes
- * from a 992-entry table (shared memory on the device): entry i * 31 + j names bits i and
- * (j < i ? j : j + 1). */
+/* Blocked Bloom filter: one 32-bit word per key, two bits in it (the same bit twice for one key
+ * in 32).  VG_PAIR_ALU: the bit positions are the top two 5-bit fields of `lo` and the mask is
+ * made with four shifts; otherwise the pair comes from a 992-entry table (shared memory on
+ * the device): entry i * 31 + j names bits i and (j < i ? j : j + 1). */
 VG_HD uint32_t vg_pair_index(uint32_t lo) { return vg_mulhi(lo, VG_PAIRS); }
-VG_HD uint32_t vg_pair_frac(uint32_t lo) { return lo * VG_PAIRS; } /* the low half of the same product: where in the pair's cell lo falls */
 VG_HD uint32_t vg_pair_mask(uint32_t idx)
 {
 	const uint32_t i = idx / 31u, j = idx % 31u;
 	return (1u << i) | (1u << (j < i ? j : j + 1u));
 }
-VG_HD uint32_t vg_filter_mask(uint32_t key, uint32_t n_words) { return vg_pair_mask(vg_pair_index(vg_hash_lo(key, n_words))); }
+#if VG_PAIR_ALU
+VG_HD uint32_t vg_lo_mask(uint32_t lo) { return (1u << (lo >> 27)) | (1u << ((lo >> 22) & 31u)); }
+VG_HD uint32_t vg_pair_frac(uint32_t lo) { return lo << 10; } /* the bits of lo the pair did not use */
+#else
+VG_HD uint32_t vg_lo_mask(uint32_t lo) { return vg_pair_mask(vg_pair_index(lo)); }
+VG_HD uint32_t vg_pair_frac(uint32_t lo) { return lo * VG_PAIRS; } /* the low half of the same product: where in the pair's cell lo falls */
+#endif
+VG_HD uint32_t vg_filter_mask(uint32_t key, uint32_t n_words) { return vg_lo_mask(vg_hash_lo(key, n_words)); }
 
 /* Second filter level (large panels): the same two bits in a word of a much bigger array that
  * lives in L2 (a few MB: >= 128 bits per key).  Only anchors that passed the on-chip filter

@@ -256,6 +256,17 @@ __device__ __forceinline__ uint32_t lds_word(uint32_t base, uint32_t idx, uint32
 	return v;
 }
 
+/* the two filter bits of an anchor whose hash tail is `lo` */
+__device__ __forceinline__ uint32_t pair_mask(uint32_t pairs, uint32_t lo, uint32_t four)
+{
+#if VG_PAIR_ALU
+	/* shf.l.wrap takes the shift amount modulo 32, so the second field needs no masking */
+	return (1u << (lo >> 27)) | __funnelshift_l(0u, 1u, lo >> 22);
+#else
+	return lds_word(pairs, vg_pair_index(lo), four);
+#endif
+}
+
 /* The anchors of one chunk and their fate in the filter.  They end at the chunk's aligned
  * offsets and reach back into the LEFT neighbour only (lane-1's chunk, or lane 31's of the
  * previous tile), so nothing here waits for a load.
@@ -287,7 +298,7 @@ __device__ __forceinline__ void probe_anchors(const AnchorParams &p, uint32_t cu
 		const uint64_t prod = (uint64_t)vg_hash1(key) * nw;
 		lo[j] = (uint32_t)prod;
 		const uint32_t word = lds_word(filter, (uint32_t)(prod >> 32), p.c4);
-		const uint32_t pm = lds_word(pairs, vg_pair_index(lo[j]), p.c4);
+		const uint32_t pm = pair_mask(pairs, lo[j], p.c4);
 		hit[j] = (~word & pm) == 0;
 	}
 }
@@ -429,20 +440,16 @@ template <int NA> struct Probed {
 
 /* probe the anchors of the tile in s.cur */
 template <int S, int LS, bool INTERIOR>
-__device__ __forceinline__ void defer_probe(const AnchorParams &p, Pipe &s, Probed<16 / S> &nx, DeferCtx &x)
+__device__ __forceinline__ void defer_probe(const AnchorParams &p, Pipe &s, Probed<16 / S> &nx, uint32_t rot, uint32_t rrot, DeferCtx &x)
 {
 	constexpr int NA = 16 / S;
 	const int L = LS ? LS : p.len;
 	const uint32_t amask = vg_mask32(L);
-	/* one rotate serves both needs: lanes 1..31 get their left neighbour, lane 0 gets lane 31's
-	 * chunk, which is its left neighbour in the NEXT tile */
-	const uint32_t rot = __shfl_sync(FULL, s.cur, x.rot_lane);
+	/* rot / rrot: s.cur / s.rcur rotated by one lane.  One rotate serves both needs: lanes 1..31
+	 * get their left neighbour, lane 0 gets lane 31's chunk, which is its left neighbour in the
+	 * NEXT tile */
 	const uint32_t left = x.lane == 0 ? s.carry : rot;
-	uint32_t rrot = 0, rleft = 0;
-	if (NA > 1) {
-		rrot = __shfl_sync(FULL, s.rcur, x.rot_lane);
-		rleft = x.lane == 0 ? s.rcarry : rrot;
-	}
+	const uint32_t rleft = x.lane == 0 ? s.rcarry : rrot;
 #pragma unroll
 	for (int j = 0; j < NA; ++j) {
 		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
@@ -457,7 +464,7 @@ __device__ __forceinline__ void defer_probe(const AnchorParams &p, Pipe &s, Prob
 		const uint64_t prod = (uint64_t)vg_hash1(a * r) * x.nw;
 		const uint32_t lo = (uint32_t)prod;
 		const uint32_t word = lds_word(x.filter, (uint32_t)(prod >> 32), x.four);
-		const uint32_t pm = lds_word(x.pairs, vg_pair_index(lo), x.four);
+		const uint32_t pm = pair_mask(x.pairs, lo, x.four);
 		bool hit = (~word & pm) == 0;
 		if (!INTERIOR) hit = hit && s.c <= p.n_chunks - 1;
 		nx.a[j] = a;
@@ -503,7 +510,11 @@ __device__ __forceinline__ void defer_step(const AnchorParams &p, Pipe &s, Pendi
 	}
 	fill = ld_stream(x.chunks + (INTERIOR ? s.c + 32 : min(s.c + 32, last)));
 	if (INTERIOR) l2_prefetch_ahead(x.chunks + s.c + 32);
-	defer_probe<S, LS, INTERIOR>(p, s, nx, x);
+	{
+		const uint32_t rot = __shfl_sync(FULL, s.cur, x.rot_lane);
+		const uint32_t rrot = NA > 1 ? __shfl_sync(FULL, s.rcur, x.rot_lane) : 0u;
+		defer_probe<S, LS, INTERIOR>(p, s, nx, rot, rrot, x);
+	}
 	++s.t;
 	s.c += 32;
 }
@@ -519,7 +530,11 @@ __device__ __forceinline__ void defer_span(const AnchorParams &p, Pipe &s, Pendi
 {
 	constexpr int NA = 16 / S;
 	Probed<NA> nx;
-	defer_probe<S, LS, INTERIOR>(p, s, nx, x); /* tile s.t */
+	{
+		const uint32_t rot = __shfl_sync(FULL, s.cur, x.rot_lane);
+		const uint32_t rrot = NA > 1 ? __shfl_sync(FULL, s.rcur, x.rot_lane) : 0u;
+		defer_probe<S, LS, INTERIOR>(p, s, nx, rot, rrot, x); /* tile s.t */
+	}
 	++s.t;
 	s.c += 32;
 	/* from here s.t counts probed tiles; a step probes tile s.t and requests the buckets of tile s.t - 1 */
@@ -546,20 +561,23 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 	extern __shared__ uint32_t s_filter[]; /* filter words | bit-pair table | candidate queues */
 	using LC = Launch<S, DEFER>;
 	constexpr int NA = 16 / S;
-	const uint32_t nw = p.filter_words;
+	const uint32_t nw = p.filter_words;        /* odd: what the hash is taken modulo */
+	const uint32_t nwp = (nw + 3u) & ~3u;      /* the array is padded to whole 16-byte units */
 	{ /* stage the filter */
 		const uint4 *src = reinterpret_cast<const uint4 *>(p.filter);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
-		for (uint32_t i = threadIdx.x; i < nw / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-		for (uint32_t i = threadIdx.x; i < VG_PAIRS; i += blockDim.x) s_filter[nw + i] = vg_pair_mask(i);
+		for (uint32_t i = threadIdx.x; i < nwp / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+#if !VG_PAIR_ALU
+		for (uint32_t i = threadIdx.x; i < VG_PAIRS; i += blockDim.x) s_filter[nwp + i] = vg_pair_mask(i);
+#endif
 	}
 	__syncthreads();
 	const uint32_t filter_sa = (uint32_t)__cvta_generic_to_shared(s_filter);
-	const uint32_t pairs_sa = filter_sa + nw * 4;
+	const uint32_t pairs_sa = filter_sa + nwp * 4;
 
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nw + VG_PAIR_TABLE_BYTES / 4) + (threadIdx.x >> 5) * LC::kQueue;
+	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nwp + VG_PAIR_TABLE_BYTES / 4) + (threadIdx.x >> 5) * LC::kQueue;
 	uint2 *const vq = wq + LC::kQueue - 32; /* the last 32 entries: tag matches awaiting verification */
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
@@ -746,7 +764,7 @@ static cudaError_t launch_one(const AnchorParams &p0, int n_sm, cudaStream_t str
 {
 	AnchorParams p = p0;
 	const int threads = Launch<S, DEFER>::kThreads;
-	const size_t smem = (size_t)p.filter_words * 4 + VG_PAIR_TABLE_BYTES + Launch<S, DEFER>::kQueueBytes;
+	const size_t smem = (size_t)((p.filter_words + 3u) & ~3u) * 4 + VG_PAIR_TABLE_BYTES + Launch<S, DEFER>::kQueueBytes;
 	static bool opted_in[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);

@@ -121,8 +121,11 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	out.n_filter_keys = (uint32_t)fkeys.size();
 	uint64_t want = (uint64_t)out.n_filter_keys * 2;
 	uint32_t nw = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, VG_MIN_FILTER_WORDS), budget);
-	nw = (nw + 3u) & ~3u;
-	out.filter.assign(nw, 0);
+	/* an odd word count: key -> hash * nw mod 2^32 (vg_hash_lo) is then a bijection, so every
+	 * bit of it is usable further down the chain; the array is padded to whole 16-byte units */
+	nw = (nw & ~3u) - 1u;
+	out.filter_words = nw;
+	out.filter.assign((nw + 3u) & ~3u, 0);
 	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_filter_mask(key, nw);
 	/* second level: 4 words (128 bits) per key, at least a page */
 	const uint32_t nw2 = out.defer ? (uint32_t)std::max<uint64_t>(1024, (uint64_t)out.n_filter_keys * 4) : 4;

@@ -31,7 +31,8 @@ struct RecipeTable {
 /* Structures of the anchor-filter kernel. */
 struct AnchorTables {
 	Plan plan;
-	std::vector<uint32_t> filter; /* blocked Bloom filter over the anchors                 */
+	std::vector<uint32_t> filter; /* blocked Bloom filter over the anchors (padded to x4)   */
+	uint32_t filter_words = 0;    /* words it hashes into: odd                              */
 	bool canon = false;           /* filter keys are canonical anchors (large panels) rather
 	                                 than both orientations of every anchor (small panels)  */
 	bool defer = false;           /* scanned by the deferred-lookup form of the kernel       */

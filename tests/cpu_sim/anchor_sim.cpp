@@ -55,7 +55,7 @@ uint64_t sim_anchor_count(int k, const uint64_t *keys, const uint32_t *vals, uin
 	build_anchor_tables(k, keys, vals, n, t);
 	const int S = t.plan.stride, L = t.plan.len;
 	const uint32_t amask = vg_mask32(L);
-	const uint32_t nw = (uint32_t)t.filter.size();
+	const uint32_t nw = t.filter_words;
 	if (info) {
 		info[0] = S, info[1] = L, info[2] = nw, info[3] = t.n_buckets;
 		info[4] = t.n_entries, info[5] = t.n_filter_keys | (t.canon ? 0x80000000u : 0);

@@ -6,7 +6,8 @@
  * The host keeps what the reference keeps on the host -- option parsing, the pattern file,
  * the first-insert-wins k-mer map, FASTA/FASTQ parsing, the VAF writer -- and hands every
  * parsed read to the GPU engine instead of the kt_pipeline extract/lookup steps.
- *   -t  is accepted for compatibility; the lookup it used to parallelise runs on the GPU
+ *   -t  is the number of host reader threads (the lookup it used to parallelise runs on the
+ *       GPU); -t 1 reads every file with the one sequential reader
  *   -b  is the staging block size in bases, as in the reference
  * Environment: CUDA_VISIBLE_DEVICES selects the GPUs (all visible ones are used);
  *              VAFGPU_RECIPE=1 runs the literal on-device recipe (verification mode).
@@ -20,7 +21,7 @@
 #include <unistd.h>
 
 #include "../../include/vafgpu.h"
-#include "fastx.h"
+#include "ingest.h"
 
 typedef struct { /* one line of patterns.txt, vaf-counter.c:92-103 */
 	char chr[256];
@@ -126,39 +127,6 @@ static uint32_t build_key_list(const pattern_db_t *db, int k, uint64_t **keys_ou
 	return n;
 }
 
-typedef struct {
-	uint64_t seqs, bases;
-} file_totals_t;
-
-/* one input file: the step-0 loop of vaf-counter.c:486-517 feeding the engine.  The
- * reference closes a block when it holds >= block_len bases or the reader returns < 0, and
- * stops the file when a block comes out empty; reproduced so that a malformed FASTQ record
- * ends (or does not end) the file at the same place. */
-static int count_file(vafgpu_ctx *ctx, const char *fn, int k, int block_len, file_totals_t *tot)
-{
-	fastx_t *fx = fastx_open(fn);
-	if (!fx) return 0; /* vaf-counter.c:557: silently skipped */
-	for (;;) {
-		long l, sum_len = 0;
-		const char *s;
-		while ((l = fastx_next(fx, &s)) >= 0) {
-			if (l < k) continue;
-			if (vafgpu_add_read(ctx, s, (size_t)l) != VAFGPU_OK) {
-				fprintf(stderr, "Error: %s\n", vafgpu_strerror(ctx));
-				fastx_close(fx);
-				return -1;
-			}
-			sum_len += l;
-			tot->seqs++;
-			tot->bases += (uint64_t)l;
-			if (sum_len >= block_len) break;
-		}
-		if (sum_len == 0) break;
-	}
-	fastx_close(fx);
-	return 0;
-}
-
 int main(int argc, char *argv[])
 {
 	int c, k = 21, n_thread = 4, block_size = 10000000, verbose = 0, n_collisions = 0;
@@ -228,18 +196,20 @@ int main(int argc, char *argv[])
 
 	fprintf(stderr, "[M::%s] Counting k-mers in FASTQ files with %d threads...\n", __func__, n_thread);
 	t0 = now();
-	for (int i = optind; i < argc; ++i) {
-		file_totals_t tot = {0, 0};
-		double tf = now();
-		fprintf(stderr, "[M::%s] Processing %s...\n", __func__, argv[i]);
-		if (count_file(ctx, argv[i], k, block_size, &tot) != 0) return 1;
-		if (verbose) {
-			double el = now() - tf;
+	/* the reference walks the files one after the other with one reader (vaf-counter.c:647-650);
+	 * here -t readers share them, large plain FASTQ files cut into slices (ingest.h) */
+	int n_files = argc - optind;
+	ingest_file_t *per_file = (ingest_file_t *)calloc((size_t)n_files, sizeof *per_file);
+	for (int i = optind; i < argc; ++i) fprintf(stderr, "[M::%s] Processing %s...\n", __func__, argv[i]);
+	if (ingest_files(ctx, n_files, argv + optind, k, block_size, n_thread, per_file) != 0) return 1;
+	if (verbose)
+		for (int i = 0; i < n_files; ++i) {
+			const ingest_file_t *f = &per_file[i];
+			if (!f->opened) continue;
 			fprintf(stderr, "[V::%s] Processed %s: %llu sequences, %llu bases in %.2f sec (%.2f Mbases/sec)\n",
-			        "count_fastq_kmers", argv[i], (unsigned long long)tot.seqs, (unsigned long long)tot.bases, el,
-			        tot.bases / el / 1e6);
+			        "count_fastq_kmers", argv[optind + i], (unsigned long long)f->seqs, (unsigned long long)f->bases, f->seconds,
+			        f->seconds > 0 ? f->bases / f->seconds / 1e6 : 0.0);
 		}
-	}
 	uint32_t *counts = (uint32_t *)calloc((size_t)2 * (db->n > 0 ? db->n : 1), 4);
 	if (vafgpu_finish(ctx, counts, &st) != VAFGPU_OK) {
 		fprintf(stderr, "Error: %s\n", vafgpu_strerror(ctx));
@@ -300,11 +270,12 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "\nMemory:\n");
 		fprintf(stderr, "  Patterns:              %d\n", db->n);
 		fprintf(stderr, "  Hash table entries:    %u\n", n_keys);
-		fprintf(stderr, "  Threads:               %d workers (host parser: 1)\n", n_thread);
+		fprintf(stderr, "  Threads:               %d readers\n", n_thread);
 		fprintf(stderr, "==============================\n");
 	}
 	vafgpu_destroy(ctx);
 	free(counts);
+	free(per_file);
 	free(keys);
 	free(vals);
 	free(db->a);

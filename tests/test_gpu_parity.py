@@ -231,3 +231,25 @@ def test_parallel_producers(tmp_path, oracle, lib, n_threads, n_buffers):
     assert np.array_equal(got, want)
     assert st["n_reads"] == sum(1 for r in reads if len(r) >= 21)
     assert st["n_bases"] == sum(len(r) for r in reads if len(r) >= 21)
+
+
+@pytest.mark.parametrize("threads", [1, 4, 9])
+def test_cli_parallel_ingest_is_byte_identical(tmp_path, oracle, lib, threads):
+    """vaf-counter -t N: several reader threads over slices of a plain FASTQ, a gzip file and a
+    FASTA file at once; the VAF file does not depend on N (and equals the oracle's)."""
+    import gzip
+    pats, reads, pf, want, _, keys, vals = case(tmp_path, oracle, 77, 21, 300, 30000, plant=0.6, jitter=30, n_rate=0.01)
+    a, b, c = str(tmp_path / "a.fq"), str(tmp_path / "b.fq.gz"), str(tmp_path / "c.fa")
+    util.write_fastq(a, reads[:20000])
+    util.write_fastq(str(tmp_path / "b.fq"), reads[20000:26000])
+    with open(str(tmp_path / "b.fq"), "rb") as fi, gzip.open(b, "wb") as fo:
+        fo.write(fi.read())
+    util.write_fastq(c, reads[26000:], fasta=True, line=60)
+    out = str(tmp_path / "o.vaf")
+    exe = os.path.join(util.PKG, "vaf-counter")
+    env = dict(os.environ, VAFGPU_SLICE_BYTES="200000")
+    r = subprocess.run([exe, "-k", "21", "-t", str(threads), "-v", "-p", pf, "-o", out, "-b", "100000", a, b, c],
+                       check=True, capture_output=True, env=env)
+    assert open(out).read() == vafgpu.format_vaf(pats, want)
+    n_ok = sum(1 for x in reads if len(x) >= 21)
+    assert ("Sequences processed:   %d" % n_ok).encode() in r.stderr

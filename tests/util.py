@@ -37,6 +37,41 @@ def build_sim() -> str:
     return out
 
 
+def build_ingest_stub() -> str:
+    """tests/_build/libingest_stub.so: host/ingest.c + host/fastx.c over a stand-in engine (test-only)."""
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    out = os.path.join(BUILD_DIR, "libingest_stub.so")
+    srcs = [os.path.join(ROOT, "tests", "cpu_sim", "ingest_stub.c"), os.path.join(PKG, "host", "ingest.c"),
+            os.path.join(PKG, "host", "fastx.c")]
+    deps = srcs + [os.path.join(PKG, "host", "ingest.h"), os.path.join(PKG, "host", "fastx.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-o", out] + srcs + ["-lz", "-lpthread"], check=True)
+    return out
+
+
+def stub_ingest(files, k, block_len, n_threads, slice_bytes=None):
+    """Run host/ingest.c over `files`; returns (digest tuple, per-file seqs, per-file bases, per-file slices)."""
+    lib = C.CDLL(build_ingest_stub())
+    lib.stub_ingest.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    n = len(files)
+    arr = (C.c_char_p * n)(*[f.encode() for f in files])
+    out = (C.c_uint64 * (4 + 3 * n))()
+    old = os.environ.get("VAFGPU_SLICE_BYTES")
+    if slice_bytes:
+        os.environ["VAFGPU_SLICE_BYTES"] = str(slice_bytes)
+    try:
+        rc = lib.stub_ingest(n, arr, k, block_len, n_threads, out)
+    finally:
+        if slice_bytes:
+            if old is None:
+                del os.environ["VAFGPU_SLICE_BYTES"]
+            else:
+                os.environ["VAFGPU_SLICE_BYTES"] = old
+    assert rc == 0
+    o = list(out)
+    return tuple(o[:4]), o[4:4 + n], o[4 + n:4 + 2 * n], [x & 0xFFFFFFFF for x in o[4 + 2 * n:]]
+
+
 class VoPattern(C.Structure):
     _fields_ = [("chr", C.c_char * 256), ("start", C.c_int), ("end", C.c_int), ("rsid", C.c_char * 256),
                 ("ref", C.c_char), ("alt", C.c_char), ("ref_kmer", C.c_char * 128), ("alt_kmer", C.c_char * 128),

@@ -31,6 +31,7 @@ import argparse
 import gzip
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -362,21 +363,21 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clk = ClockSampler(phys_index)
-        with clk:
+        with clk:  # clocks are sampled over both timed loops (each lasts only tens of milliseconds)
             e0.record()
             for _ in range(args.steps):
                 step()
             e1.record()
             barrier()
-        ms = e0.elapsed_time(e1)
-        # the dominant kernel alone (no counter reset, no collective), for the roofline
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(args.steps):
-            eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
-        k1.record()
-        barrier()
-        kernel_ms = k0.elapsed_time(k1) / (args.steps * launches_per_step)
+            ms = e0.elapsed_time(e1)
+            # the dominant kernel alone (no counter reset, no collective), for the roofline
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for _ in range(args.steps):
+                eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
+            k1.record()
+            barrier()
+            kernel_ms = k0.elapsed_time(k1) / (args.steps * launches_per_step)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -495,6 +496,23 @@ def main():
         assert ours_txt == ref_txt, "VAF text differs from the reference's on the sample"
         assert open(os.path.join(tmp, "refn.vaf")).read() == ref_txt
         parity["vaf_bytes_vs_%s_on_%d_reads" % (kind, len(reads))] = "identical"
+        # the vaf-counter command line of this repo on the same file: same bytes out, timed the same
+        # way (whole process, which for a sample this small is mostly CUDA start-up) and by its own
+        # clock around the counting phase; -t is the number of host reader threads
+        cli_exe = os.path.join(PKG, "vaf-counter")
+        cli = {}
+        for th in sorted({1, ncpu}):
+            out_vaf = os.path.join(tmp, "cli%d.vaf" % th)
+            t0 = time.perf_counter()
+            r = subprocess.run([cli_exe, "-k", str(K), "-t", str(th), "-v", "-p", pattern_file, "-o", out_vaf, fq],
+                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+            wall = time.perf_counter() - t0
+            assert open(out_vaf).read() == ref_txt, "CLI output differs from the reference's at -t %d" % th
+            m = re.search(rb"K-mer counting:\s+([0-9.]+) sec", r.stderr)
+            cli["t%d" % th] = {"whole_process_gbases_s": bases / wall / 1e9,
+                               "counting_phase_gbases_s": bases / max(float(m.group(1)), 1e-9) / 1e9 if m else None}
+        parity["cli_vaf_bytes_vs_%s" % kind] = "identical at -t 1 and -t %d" % ncpu
+        cpu["this_repo_cli_same_file"] = cli
         try:
             import util
             want, _, _ = util.Oracle().count_reads(pattern_file, K, reads)
@@ -521,12 +539,12 @@ def main():
                               "vafgpu_finish" % (e2e_reads, args.reads)},
             "gpu_launches": int(args.steps * launches_per_step),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "anchor_scan_kernel<8,true>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "anchor_scan_kernel<S=8,CANON,DEFER,L=14>",
                          "algorithmic_bytes_per_launch": algo_bytes_per_launch, "ms_per_launch": kernel_ms},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
             "parity": parity,
-            "stats": {"hits_per_step": hits_per_step, "filter_survivors_per_base":
+            "stats": {"hits_per_step": hits_per_step, "resolver_entries_per_base":
                       st_kernel["n_candidates"] / max(st_kernel["n_bytes"], 1), "anchor_stride": st_kernel["anchor_stride"],
                       "anchor_len": st_kernel["anchor_len"], "filter_bytes": st_kernel["filter_bytes"],
                       "pattern_collisions": n_coll},

@@ -80,7 +80,8 @@ struct AnchorParams {
 	uint32_t n_chunks;     /* chunks in the range, < 2^28                               */
 	uint32_t n_tiles;      /* 32 chunks each */
 	uint32_t tiles_per_span;
-	uint32_t n_spans;
+	uint32_t n_spans;      /* n_full_spans of tiles_per_span tiles, then shorter ones of tail_tiles */
+	uint32_t n_full_spans, tail_tiles;
 	uint32_t *counts;
 	unsigned long long *stats;
 	const uint32_t *filter;
@@ -99,6 +100,9 @@ struct AnchorParams {
 /* distance of the L2 prefetch ahead of the register pipeline, in bytes (8 tiles) */
 #ifndef VG_PF_BYTES
 #define VG_PF_BYTES 4096
+#endif
+#ifndef VG_PF_CLAMP
+#define VG_PF_CLAMP 1
 #endif
 
 __device__ __forceinline__ void l2_prefetch(const void *ptr)
@@ -312,13 +316,17 @@ __device__ __forceinline__ bool passed2(uint32_t w, uint32_t pm) { return (~w & 
  * buffer consumed by the previous tile and is refilled first thing with tile t+3; the only
  * consumer of loaded data is the pack at the very end. */
 template <int S, bool CANON, int LS, bool INTERIOR>
-__device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint4 &fill, const uint4 &use, uint32_t filter,
+__device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint32_t t1, uint4 &fill, const uint4 &use, uint32_t filter,
                                           uint32_t pairs, uint2 *wq, uint32_t lane, uint32_t lt_mask)
 {
 	constexpr int NA = 16 / S;
 	const uint32_t last = p.n_chunks - 1;
 	fill = ld_stream(p.chunks + (INTERIOR ? s.c + 96 : min(s.c + 96, last)));
-	if (INTERIOR) l2_prefetch_ahead(p.chunks + s.c); /* this lane's chunk, some tiles on */
+#if VG_PF_CLAMP /* prefetch inside the span only: the next span's owner prefetches its own start */
+	if (INTERIOR && s.t + VG_PF_BYTES / 512 < t1) l2_prefetch_ahead(p.chunks + s.c); /* this lane's chunk, some tiles on */
+#else
+	if (INTERIOR) l2_prefetch_ahead(p.chunks + s.c);
+#endif
 	/* one rotate serves both needs: lanes 1..31 get their left neighbour, lane 0 gets lane 31's
 	 * chunk, which is its left neighbour in the NEXT tile */
 	const uint32_t rot = __shfl_sync(FULL, s.cur, (lane + 31) & 31);
@@ -361,16 +369,16 @@ __device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint3
 {
 	for (;;) {
 		if (s.phase == 0) {
-			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w2, s.w0, filter, pairs, wq, lane, lt_mask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w2, s.w0, filter, pairs, wq, lane, lt_mask);
 			s.phase = 1;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
 		if (s.phase == 1) {
-			scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w0, s.w1, filter, pairs, wq, lane, lt_mask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w0, s.w1, filter, pairs, wq, lane, lt_mask);
 			s.phase = 2;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
-		scan_tile<S, CANON, LS, INTERIOR>(p, s, s.w1, s.w2, filter, pairs, wq, lane, lt_mask);
+		scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w1, s.w2, filter, pairs, wq, lane, lt_mask);
 		s.phase = 0;
 		if (s.t >= t1 || s.qn >= 32) break;
 	}
@@ -490,7 +498,7 @@ nx.pm[j] = pm;
  * the pack's last reads and then needs a temporary -- and a copy that waits for the load.) */
 template <int S, int LS, bool INTERIOR>
 __device__ __forceinline__ void defer_step(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, Probed<16 / S> &nx, uint4 &fill,
-                                           const uint4 &use, DeferCtx &x)
+                                           const uint4 &use, uint32_t t1, DeferCtx &x)
 {
 	constexpr int NA = 16 / S;
 	const uint32_t last = p.n_chunks - 1;
@@ -509,7 +517,11 @@ __device__ __forceinline__ void defer_step(const AnchorParams &p, Pipe &s, Pendi
 		if (nx.word2[j] != VG_NO_WORD) pd.w[j] = ldg_keep(x.filter2 + nx.word2[j], x.keep);
 	}
 	fill = ld_stream(x.chunks + (INTERIOR ? s.c + 32 : min(s.c + 32, last)));
+#if VG_PF_CLAMP /* prefetch inside the span only: the next span's owner prefetches its own start */
+	if (INTERIOR && s.t + 1 + VG_PF_BYTES / 512 < t1) l2_prefetch_ahead(x.chunks + s.c + 32);
+#else
 	if (INTERIOR) l2_prefetch_ahead(x.chunks + s.c + 32);
+#endif
 	{
 		const uint32_t rot = __shfl_sync(FULL, s.cur, x.rot_lane);
 		const uint32_t rrot = NA > 1 ? __shfl_sync(FULL, s.rcur, x.rot_lane) : 0u;
@@ -539,14 +551,27 @@ __device__ __forceinline__ void defer_span(const AnchorParams &p, Pipe &s, Pendi
 	s.c += 32;
 	/* from here s.t counts probed tiles; a step probes tile s.t and requests the buckets of tile s.t - 1 */
 	for (;;) {
-		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w1, s.w0, x);
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w1, s.w0, t1, x);
 		if (s.t > t1 || s.qn >= 32) break;
-		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w0, s.w1, x);
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w0, s.w1, t1, x);
 		if (s.t > t1 || s.qn >= 32) break;
 	}
 	/* back to "s.t = next tile to scan": the last probed tile (s.t - 1) has no buckets requested */
 	--s.t;
 	s.c -= 32;
+}
+
+/* Spans: warps take spans warp, warp + n_warps, ... so that at any time the resident warps read
+ * one window of the stream that moves through it (kind to DRAM pages and the TLB).  All spans
+ * but those of the last round have tiles_per_span tiles; what is left for the last round is cut
+ * into one equal share per warp, so that nobody idles while others work off a full span. */
+__device__ __forceinline__ uint32_t span_begin(const AnchorParams &p, uint32_t span)
+{
+	return span < p.n_full_spans ? span * p.tiles_per_span : p.n_full_spans * p.tiles_per_span + (span - p.n_full_spans) * p.tail_tiles;
+}
+__device__ __forceinline__ uint32_t span_end(const AnchorParams &p, uint32_t span)
+{
+	return min(span_begin(p, span) + (span < p.n_full_spans ? p.tiles_per_span : p.tail_tiles), p.n_tiles);
 }
 
 /* The streaming kernel.  One CTA per SM, persistent over spans of tiles (a tile = 32 chunks
@@ -642,7 +667,7 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 			}
 		};
 		for (uint32_t span = warp; span < p.n_spans; span += n_warps) {
-			open_span(span * p.tiles_per_span, min((span + 1) * p.tiles_per_span, p.n_tiles));
+			open_span(span_begin(p, span), span_end(p, span));
 			for (;;) {
 				if (interior) defer_span<S, LS, true>(p, s, pd, t1, x);
 				else defer_span<S, LS, false>(p, s, pd, t1, x);
@@ -673,7 +698,7 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 	uint32_t vn = 0, n_cand = 0, n_hits = 0, span = warp;
 	for (;;) {
 		if (s.t >= t1 && span < p.n_spans) {
-			open_span(span * p.tiles_per_span, min((span + 1) * p.tiles_per_span, p.n_tiles));
+			open_span(span_begin(p, span), span_end(p, span));
 			span += n_warps;
 		}
 		const bool finished = s.t >= t1; /* no span left */
@@ -775,10 +800,19 @@ static cudaError_t launch_one(const AnchorParams &p0, int n_sm, cudaStream_t str
 		opted_in[dev] = true;
 	}
 	const uint32_t resident_warps = (uint32_t)n_sm * (threads / 32);
-	uint32_t tps = p.n_tiles / (resident_warps * 4u);
 	static const uint32_t cap = getenv("VAFGPU_SPAN_CAP") ? (uint32_t)atoi(getenv("VAFGPU_SPAN_CAP")) : 64u; /* tuning knob */
-	p.tiles_per_span = tps < 1 ? 1 : (tps > cap ? cap : tps);
-	p.n_spans = (p.n_tiles + p.tiles_per_span - 1) / p.tiles_per_span;
+	uint32_t tps = (p.n_tiles + resident_warps * 4u - 1) / (resident_warps * 4u);
+	if (tps < 1) tps = 1;
+	if (tps <= cap) { /* small input: at most four spans per warp, the last one possibly short */
+		p.tiles_per_span = p.tail_tiles = tps;
+		p.n_spans = p.n_full_spans = (p.n_tiles + tps - 1) / tps;
+	} else { /* whole rounds of full spans, then one round of equal shares of the rest */
+		p.tiles_per_span = cap;
+		p.n_full_spans = p.n_tiles / (resident_warps * cap) * resident_warps;
+		const uint32_t rest = p.n_tiles - p.n_full_spans * cap;
+		p.tail_tiles = rest ? (rest + resident_warps - 1) / resident_warps : 1;
+		p.n_spans = p.n_full_spans + (rest + p.tail_tiles - 1) / p.tail_tiles;
+	}
 	uint32_t ctas = (p.n_spans + (threads / 32) - 1) / (threads / 32);
 	if (ctas > (uint32_t)n_sm) ctas = (uint32_t)n_sm;
 	anchor_scan_kernel<S, CANON, DEFER, LS><<<ctas, threads, smem, stream>>>(p);
@@ -823,7 +857,7 @@ cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream)
 		p.range_lo = lo;
 		p.n_chunks = (uint32_t)(n / 16);
 		p.n_tiles = (p.n_chunks + 31) / 32;
-		p.tiles_per_span = p.n_spans = 0;
+		p.tiles_per_span = p.n_spans = p.n_full_spans = p.tail_tiles = 0;
 		p.counts = a.counts;
 		p.stats = a.stats;
 		p.filter = a.filter;

@@ -186,7 +186,10 @@ int main(int argc, char *argv[])
 	unsigned flags = 0;
 	const char *env = getenv("VAFGPU_RECIPE");
 	if (env && atoi(env)) flags |= VAFGPU_F_REFERENCE_RECIPE;
-	if (vafgpu_create(&ctx, k, keys, vals, n_keys, (uint32_t)db->n, block_size > 0 ? (size_t)block_size : 0, 0, 0, flags) != VAFGPU_OK) {
+	/* staging blocks per device: one for every reader to fill plus two in flight */
+	int n_buffers = n_thread > 1 ? n_thread + 2 : 3;
+	if (n_buffers > 66) n_buffers = 66;
+	if (vafgpu_create(&ctx, k, keys, vals, n_keys, (uint32_t)db->n, block_size > 0 ? (size_t)block_size : 0, n_buffers, 0, flags) != VAFGPU_OK) {
 		fprintf(stderr, "Error: failed to create k-mer map: %s\n", vafgpu_strerror(NULL));
 		return 1;
 	}

@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -325,6 +326,16 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	if (block_bytes > ((size_t)1 << 34)) return fail(nullptr, VAFGPU_EINVAL, "block_bytes too large");
 	if (n_buffers <= 0) n_buffers = 3;
 
+	const bool timing = getenv("VAFGPU_TIMING") != nullptr; /* start-up breakdown on stderr */
+	auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double tt = tnow();
+	auto lap = [&](const char *what) {
+		if (timing) {
+			double t = tnow();
+			fprintf(stderr, "[vafgpu] %-28s %8.1f ms\n", what, (t - tt) * 1e3);
+			tt = t;
+		}
+	};
 	vafgpu_ctx *c = new (std::nothrow) vafgpu_ctx;
 	if (!c) return fail(nullptr, VAFGPU_ENOMEM, "out of memory");
 	c->k = k;
@@ -335,8 +346,10 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 
 	RecipeTable rt;
 	AnchorTables at;
+	lap("device count");
 	build_recipe_table(k, keys, vals, n_entries, n_patterns, rt);
 	build_anchor_tables(k, keys, vals, n_entries, at);
+	lap("host tables");
 	c->plan = at.plan;
 	c->filter_words = at.filter_words;
 	c->filter2_words = (uint32_t)at.filter2.size();
@@ -357,7 +370,9 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			if (prop.major != 10)
 				return fail(c, VAFGPU_ENOGPU, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", i, prop.name, prop.major, prop.minor);
 			d.n_sm = prop.multiProcessorCount;
+			lap("context");
 			CU(c, kernels_make_policy(&d.keep_policy));
+			lap("module load + policy kernel");
 			if (const char *env = getenv("VAFGPU_L2_PERSIST_MB")) { /* tuning knob: L2 set-aside for evict-last lines */
 				size_t want = (size_t)atoi(env) << 20;
 				if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
@@ -380,6 +395,7 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			CU(c, cudaMemcpy(d.d_rvals, rt.vals.data(), rt.vals.size() * 4, cudaMemcpyHostToDevice));
 			CU(c, cudaMemset(d.d_counts, 0, c->n_counts * 4));
 			CU(c, cudaMemset(d.d_stats, 0, ST_N * sizeof(unsigned long long)));
+			lap("tables to device");
 			d.blocks.resize(n_buffers);
 			for (Block &b : d.blocks) {
 				CU(c, cudaHostAlloc(&b.h, block_bytes + 64, cudaHostAllocPortable));
@@ -389,6 +405,7 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 				CU(c, cudaEventCreate(&b.e1));
 				CU(c, cudaEventCreate(&b.e2));
 			}
+			lap("staging blocks");
 			return VAFGPU_OK;
 		}();
 	}

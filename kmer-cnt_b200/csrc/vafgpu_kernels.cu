@@ -800,7 +800,7 @@ static cudaError_t launch_one(const AnchorParams &p0, int n_sm, cudaStream_t str
 		opted_in[dev] = true;
 	}
 	const uint32_t resident_warps = (uint32_t)n_sm * (threads / 32);
-	static const uint32_t cap = getenv("VAFGPU_SPAN_CAP") ? (uint32_t)atoi(getenv("VAFGPU_SPAN_CAP")) : 64u; /* tuning knob */
+	static const uint32_t cap = getenv("VAFGPU_SPAN_CAP") ? (uint32_t)atoi(getenv("VAFGPU_SPAN_CAP")) : 256u; /* tuning knob */
 	uint32_t tps = (p.n_tiles + resident_warps * 4u - 1) / (resident_warps * 4u);
 	if (tps < 1) tps = 1;
 	if (tps <= cap) { /* small input: at most four spans per warp, the last one possibly short */

@@ -1,0 +1,133 @@
+/*
+ * kcgpu.h -- C ABI of the full k-mer counting mode (the kc-c4 path of gerbenvoshol/kmer-cnt)
+ * on B200.  Part of libvafgpu.so.
+ *
+ * What it replaces, in kc-c4.c of the reference: count_seq_buf (kc-c4.c:74-90: rolling forward
+ * and reverse-complement words over the strict base table kc-c4.c:21-38, canonical minimum,
+ * the invertible hash64 of kc-c4.c:40-50), c4x_insert_buf / worker_for (kc-c4.c:64-72,116-128:
+ * one khashl set per hash suffix, a 10-bit saturating count in the low bits of the key) and
+ * worker_hist / print_hist (kc-c4.c:186-215: 256 bins of min(count, 255)).
+ *
+ * hash64 is a bijection on 2k-bit words, so the reference's tables hold exactly one entry per
+ * distinct canonical k-mer; the histogram is a function of the multiset of canonical k-mers and
+ * of nothing else.  Here one open-addressing table per GPU holds the reference's own slot word
+ * (hash bits << 10 | count).  With several GPUs a k-mer belongs to GPU hash64(k-mer) mod n (the
+ * reference's partition by hash suffix, kc-c4.c:66, generalised from 2^p tables to n owners).
+ * Two ways to get it there:
+ *   fused    kcgpu_set_owners(): the counting kernel itself adds every k-mer to its owner's
+ *            table, over NVLink peer memory for the other GPUs (no exchange buffers);
+ *   staged   kcgpu_extract_device() files hashed k-mers per owner, the caller exchanges the
+ *            lists (NCCL all-to-all), kcgpu_insert_device() adds what arrived.
+ *
+ * Plain C types only; 0 on success or a negative VAFGPU_E* code (vafgpu.h); no CPU fallback:
+ * kcgpu_create fails with VAFGPU_ENOGPU without an sm_100 device.
+ */
+#ifndef KCGPU_H
+#define KCGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "vafgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kcgpu_ctx kcgpu_ctx;
+
+#define KCGPU_MAX_OWNERS 16
+#define KCGPU_IPC_HANDLE_BYTES 64
+
+typedef struct kcgpu_stats {
+	uint64_t n_reads;     /* reads accepted by kcgpu_add_read (len >= k)                      */
+	uint64_t n_bases;
+	uint64_t n_blocks;    /* kernel launches over stream blocks                                */
+	uint64_t n_kmers;     /* k-mer instances this context's kernels extracted or inserted      */
+	uint64_t n_distinct;  /* slots this context's kernels claimed (in any owner's table)       */
+	uint64_t n_overflow;  /* k-mers lost because a table region was full: counts incomplete    */
+	uint64_t n_dropped;   /* k-mers that did not fit the lists of kcgpu_extract_device         */
+	uint64_t table_slots;
+	double   kernel_ms;   /* kernels behind kcgpu_add_read (CUDA events on their streams)      */
+	double   h2d_ms;
+} kcgpu_stats;
+
+/* sm_100 devices visible to this process (0 if there is none) */
+int kcgpu_device_count(void);
+
+/*
+ * One context = one table on one device.  table_slots is rounded up to a power of two
+ * (at least 4096); 0 = the largest power of two that fits in 3/4 of the device's free memory
+ * (8 bytes per slot).  block_bytes: size of each pinned staging block behind kcgpu_add_read
+ * (0 = 16 MiB).
+ */
+int kcgpu_create(kcgpu_ctx **ctx, int k, uint64_t table_slots, size_t block_bytes, int device);
+
+/*
+ * Hand one parsed read to the engine: replaces the per-read copy of step 0 and steps 1 and 2
+ * (kc-c4.c:133-180).  Reads shorter than k are dropped (kc-c4.c:141).  Bytes are classified by
+ * the reference's strict table (kc-c4.c:21-38): A C G T U in either case and the bytes 0..3
+ * are bases, everything else ends a k-mer.  One producer thread per context.
+ */
+int kcgpu_add_read(kcgpu_ctx *ctx, const char *seq, size_t len);
+
+/*
+ * Count a stream that is already resident on the context's device: reads separated by '\n',
+ * 16-byte aligned, n_bytes a multiple of 16; bytes other than A C G T U (either case) end a
+ * k-mer.  Fused extract + insert, into the tables named by kcgpu_set_owners (default: this
+ * context's own).  `stream` is a cudaStream_t (NULL = the context's own).  Asynchronous.
+ */
+int kcgpu_count_device(kcgpu_ctx *ctx, const void *d_bytes, size_t n_bytes, void *stream);
+
+/*
+ * The two halves of kcgpu_count_device, for an exchange by collective: extract hashes every
+ * canonical k-mer of the stream and files it under its owner, hash mod n_parts:
+ * d_keys[part * cap_per_part + i], i < d_part_counts[part] (uint32, the caller zeroes them;
+ * entries beyond cap_per_part are dropped, the count still runs on, and kcgpu_stats.n_dropped
+ * reports them).  After the exchange, insert adds n hashed k-mers, all owned by `my_part` of
+ * `n_parts`, to the context's table.  Both asynchronous on `stream`.
+ */
+int kcgpu_extract_device(kcgpu_ctx *ctx, const void *d_bytes, size_t n_bytes, int n_parts,
+                         uint64_t *d_keys, size_t cap_per_part, uint32_t *d_part_counts, void *stream);
+int kcgpu_insert_device(kcgpu_ctx *ctx, const uint64_t *d_hashed_keys, size_t n, int n_parts, void *stream);
+
+/*
+ * Several GPUs, fused form.  The table of this context as a device pointer and as a CUDA IPC
+ * handle (KCGPU_IPC_HANDLE_BYTES bytes) for another process; kcgpu_ipc_open maps a peer's
+ * table into this process.  kcgpu_set_owners names the table of every owner (all of the same
+ * size as this context's; tables[my_part] may be NULL = this context's own); from then on this
+ * context's kernels add a k-mer to tables[hash mod n_parts].  kcgpu_link does all of it for
+ * contexts of one process (peer access enabled both ways) and makes kcgpu_sync /
+ * kcgpu_histogram of any member wait for all of them.
+ */
+int kcgpu_table(kcgpu_ctx *ctx, void **d_table, uint64_t *table_slots);
+int kcgpu_ipc_export(kcgpu_ctx *ctx, void *handle);
+int kcgpu_ipc_open(kcgpu_ctx *ctx, const void *handle, void **d_peer_table);
+int kcgpu_set_owners(kcgpu_ctx *ctx, int n_parts, int my_part, void *const *tables);
+int kcgpu_link(kcgpu_ctx *const *ctxs, int n);
+
+/* Submit what kcgpu_add_read has staged and wait for every kernel of this context (and of the
+ * contexts linked to it).  Across processes the caller adds its own barrier. */
+int kcgpu_sync(kcgpu_ctx *ctx);
+
+/*
+ * kcgpu_sync, then the histogram of kc-c4.c:186-215 over this context's table: hist[c] = number
+ * of distinct canonical k-mers seen min(c, 255) times, counts saturating at 1023 first as in
+ * kc-c4.c:125 (hist[0] is 0).  With several owners the per-context histograms are summed by
+ * the caller (they partition the k-mers).  Counting can go on afterwards.
+ */
+int kcgpu_histogram(kcgpu_ctx *ctx, uint64_t hist[256], kcgpu_stats *stats);
+
+/* Empty the table and the statistics (asynchronous on the context's stream). */
+int kcgpu_reset(kcgpu_ctx *ctx);
+
+void kcgpu_destroy(kcgpu_ctx *ctx);
+const char *kcgpu_strerror(const kcgpu_ctx *ctx);
+
+/* the reference's hash (kc-c4.c:40-50) on the host, exported for tests */
+uint64_t kcgpu_hash64(uint64_t key, int k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,507 @@
+/*
+ * kcgpu_api.cu -- the C ABI of include/kcgpu.h: one table per context, pinned staging blocks
+ * with a stream each (the copy of block i+1 overlaps the kernel of block i, which replaces
+ * kt_pipeline's three steps, kc-c4.c:130-183), peer tables for the fused several-GPU form.
+ * Host logic only; the kernels are in kcgpu_kernels.cu.
+ */
+#include "../../include/kcgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kcgpu_kernels.cuh"
+
+using namespace kcgpu;
+
+namespace {
+
+thread_local std::string g_kc_create_error;
+
+struct KcBlock {
+	char *h = nullptr;
+	uint8_t *d = nullptr;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; /* copy start, copy end, kernel end */
+	bool in_flight = false;
+	size_t used = 0;
+};
+
+} // namespace
+
+struct kcgpu_ctx {
+	int k = 0, device = 0, n_sm = 0;
+	uint64_t n_slots = 0;
+	uint32_t region_bits = 0, rslot_bits = 0;
+	uint64_t *d_table = nullptr;
+	unsigned long long *d_stats = nullptr, *d_hist = nullptr;
+	cudaStream_t main_stream = nullptr;
+	size_t block_bytes = 0;
+	std::vector<KcBlock> blocks;
+	size_t next_block = 0;
+	KcBlock *cur = nullptr;
+	std::vector<char> scratch;
+	uint32_t n_parts = 1, my_part = 0;
+	uint64_t *tables[KC_MAX_PARTS] = {};
+	std::vector<void *> ipc_mapped;
+	std::vector<kcgpu_ctx *> group; /* contexts linked in this process, this one included */
+	kcgpu_stats st{};
+	std::string err;
+};
+
+namespace {
+
+int kfail(kcgpu_ctx *c, int code, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (c) c->err = buf;
+	else g_kc_create_error = buf;
+	return code;
+}
+
+#define KCU(c, call)                                                                              \
+	do {                                                                                          \
+		cudaError_t e_ = (call);                                                                  \
+		if (e_ != cudaSuccess)                                                                    \
+			return kfail(c, VAFGPU_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+int kc_wait_block(kcgpu_ctx *c, KcBlock &b)
+{
+	if (!b.in_flight) return VAFGPU_OK;
+	KCU(c, cudaEventSynchronize(b.e2));
+	float h2d = 0, ker = 0;
+	cudaEventElapsedTime(&h2d, b.e0, b.e1);
+	cudaEventElapsedTime(&ker, b.e1, b.e2);
+	c->st.h2d_ms += h2d;
+	c->st.kernel_ms += ker;
+	b.in_flight = false;
+	return VAFGPU_OK;
+}
+
+CountArgs count_args(const kcgpu_ctx *c, const void *bytes, size_t n)
+{
+	CountArgs a{};
+	a.bytes = static_cast<const uint8_t *>(bytes);
+	a.n_bytes = n;
+	a.k = c->k;
+	a.n_parts = c->n_parts;
+	a.region_bits = c->region_bits;
+	a.rslot_bits = c->rslot_bits;
+	for (uint32_t i = 0; i < c->n_parts; ++i) a.tables[i] = c->tables[i];
+	a.stats = c->d_stats;
+	return a;
+}
+
+int kc_submit_current(kcgpu_ctx *c)
+{
+	KcBlock *b = c->cur;
+	if (!b) return VAFGPU_OK;
+	c->cur = nullptr;
+	if (!b->used) return VAFGPU_OK;
+	const size_t n = (b->used + 15) & ~(size_t)15;
+	memset(b->h + b->used, '\n', n - b->used);
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, cudaEventRecord(b->e0, b->stream));
+	KCU(c, cudaMemcpyAsync(b->d, b->h, n, cudaMemcpyHostToDevice, b->stream));
+	KCU(c, cudaEventRecord(b->e1, b->stream));
+	KCU(c, launch_count(count_args(c, b->d, n), b->stream));
+	KCU(c, cudaEventRecord(b->e2, b->stream));
+	b->in_flight = true;
+	c->st.n_blocks++;
+	return VAFGPU_OK;
+}
+
+int kc_ensure_room(kcgpu_ctx *c, size_t need)
+{
+	if (c->cur && c->cur->used + need > c->block_bytes) {
+		int rc = kc_submit_current(c);
+		if (rc) return rc;
+	}
+	if (!c->cur) {
+		KcBlock &b = c->blocks[c->next_block];
+		c->next_block = (c->next_block + 1) % c->blocks.size();
+		int rc = kc_wait_block(c, b); /* back-pressure: at most blocks.size() blocks in flight */
+		if (rc) return rc;
+		b.used = 0;
+		c->cur = &b;
+	}
+	return VAFGPU_OK;
+}
+
+int kc_sync_one(kcgpu_ctx *c)
+{
+	int rc = kc_submit_current(c);
+	if (rc) return rc;
+	KCU(c, cudaSetDevice(c->device));
+	for (KcBlock &b : c->blocks) {
+		rc = kc_wait_block(c, b);
+		if (rc) return rc;
+	}
+	KCU(c, cudaStreamSynchronize(c->main_stream));
+	return VAFGPU_OK;
+}
+
+int kc_read_stats(kcgpu_ctx *c)
+{
+	unsigned long long s[KC_ST_N];
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, cudaMemcpy(s, c->d_stats, sizeof s, cudaMemcpyDeviceToHost));
+	c->st.n_kmers = s[KC_ST_KMERS];
+	c->st.n_distinct = s[KC_ST_NEW];
+	c->st.n_overflow = s[KC_ST_OVERFLOW];
+	c->st.n_dropped = s[KC_ST_DROPPED];
+	return VAFGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+uint64_t kcgpu_hash64(uint64_t key, int k)
+{
+	if (k < 1 || k > 31) return 0;
+	return kc_hash64(key, (1ULL << 2 * k) - 1);
+}
+
+int kcgpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+const char *kcgpu_strerror(const kcgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_kc_create_error.c_str(); }
+
+int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, size_t block_bytes, int device)
+{
+	if (!out) return kfail(nullptr, VAFGPU_EINVAL, "ctx is NULL");
+	*out = nullptr;
+	if (k < 1 || k > 31) return kfail(nullptr, VAFGPU_EINVAL, "k = %d is outside 1..31", k);
+	int visible = 0;
+	cudaError_t ce = cudaGetDeviceCount(&visible);
+	if (ce != cudaSuccess || visible < 1)
+		return kfail(nullptr, VAFGPU_ENOGPU, "no CUDA device: %s", ce == cudaSuccess ? "count is 0" : cudaGetErrorString(ce));
+	if (device < 0 || device >= visible) return kfail(nullptr, VAFGPU_EINVAL, "device %d of %d", device, visible);
+	if (block_bytes == 0) block_bytes = (size_t)16 << 20;
+	if (block_bytes < 4096) block_bytes = 4096;
+	if (block_bytes > ((size_t)1 << 34)) return kfail(nullptr, VAFGPU_EINVAL, "block_bytes too large");
+
+	kcgpu_ctx *c = new (std::nothrow) kcgpu_ctx;
+	if (!c) return kfail(nullptr, VAFGPU_ENOMEM, "out of memory");
+	c->k = k;
+	c->device = device;
+	c->block_bytes = block_bytes;
+	int rc = [&]() -> int {
+		cudaDeviceProp prop;
+		KCU(c, cudaSetDevice(device));
+		KCU(c, cudaGetDeviceProperties(&prop, device));
+		if (prop.major != 10)
+			return kfail(c, VAFGPU_ENOGPU, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", device, prop.name,
+			             prop.major, prop.minor);
+		c->n_sm = prop.multiProcessorCount;
+		c->region_bits = kc_region_bits(k);
+		const uint64_t min_slots = (uint64_t)4096 > ((uint64_t)16 << c->region_bits) ? (uint64_t)4096 : ((uint64_t)16 << c->region_bits);
+		if (table_slots == 0) {
+			size_t free_b = 0, total_b = 0;
+			KCU(c, cudaMemGetInfo(&free_b, &total_b));
+			const uint64_t budget = (uint64_t)free_b / 4 * 3 / 8;
+			table_slots = min_slots;
+			while (table_slots * 2 <= budget) table_slots *= 2;
+		}
+		uint64_t n = min_slots;
+		while (n < table_slots) {
+			if (n >> 40) return kfail(c, VAFGPU_EINVAL, "table_slots too large");
+			n *= 2;
+		}
+		c->n_slots = n;
+		uint32_t bits = 0;
+		while ((1ull << bits) < n) ++bits;
+		c->rslot_bits = bits - c->region_bits;
+		KCU(c, cudaMalloc(&c->d_table, n * 8));
+		KCU(c, cudaMalloc(&c->d_stats, KC_ST_N * sizeof(unsigned long long)));
+		KCU(c, cudaMalloc(&c->d_hist, 256 * sizeof(unsigned long long)));
+		KCU(c, cudaMemset(c->d_table, 0, n * 8));
+		KCU(c, cudaMemset(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long)));
+		KCU(c, cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking));
+		c->blocks.resize(3);
+		for (KcBlock &b : c->blocks) {
+			KCU(c, cudaHostAlloc(&b.h, block_bytes + 64, cudaHostAllocPortable));
+			KCU(c, cudaMalloc(&b.d, block_bytes + 64));
+			KCU(c, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+			KCU(c, cudaEventCreate(&b.e0));
+			KCU(c, cudaEventCreate(&b.e1));
+			KCU(c, cudaEventCreate(&b.e2));
+		}
+		KCU(c, cudaDeviceSynchronize());
+		return VAFGPU_OK;
+	}();
+	if (rc != VAFGPU_OK) {
+		g_kc_create_error = c->err;
+		kcgpu_destroy(c);
+		return rc;
+	}
+	c->tables[0] = c->d_table;
+	c->group.push_back(c);
+	c->st.table_slots = c->n_slots;
+	*out = c;
+	return VAFGPU_OK;
+}
+
+int kcgpu_add_read(kcgpu_ctx *c, const char *seq, size_t len)
+{
+	if (!c || (!seq && len)) return VAFGPU_EINVAL;
+	if (len < (size_t)c->k) return VAFGPU_OK; /* kc-c4.c:141 */
+	c->st.n_reads++;
+	c->st.n_bases += len;
+	if (len + 1 <= c->block_bytes) {
+		int rc = kc_ensure_room(c, len + 1);
+		if (rc) return rc;
+		KcBlock *b = c->cur;
+		vafgpu_canonicalise_read(seq, len, b->h + b->used, 0); /* strict table: kc-c4.c:21-38 */
+		b->h[b->used + len] = '\n';
+		b->used += len + 1;
+		return VAFGPU_OK;
+	}
+	/* a read longer than a block (a chromosome): pieces that overlap by k-1 bases, so that
+	 * every k-mer lies in exactly one piece */
+	if (c->scratch.size() < len) c->scratch.resize(len);
+	vafgpu_canonicalise_read(seq, len, c->scratch.data(), 0);
+	const size_t piece = c->block_bytes - 1, step = piece - (size_t)(c->k - 1);
+	for (size_t at = 0;; at += step) {
+		const size_t n = len - at < piece ? len - at : piece;
+		int rc = kc_ensure_room(c, n + 1);
+		if (rc) return rc;
+		KcBlock *b = c->cur;
+		memcpy(b->h + b->used, c->scratch.data() + at, n);
+		b->h[b->used + n] = '\n';
+		b->used += n + 1;
+		if (at + n >= len) break;
+	}
+	return VAFGPU_OK;
+}
+
+int kcgpu_count_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, void *stream)
+{
+	if (!c) return VAFGPU_EINVAL;
+	if (((uintptr_t)d_bytes & 15) || (n_bytes & 15))
+		return kfail(c, VAFGPU_EINVAL, "device stream must be 16-byte aligned and a multiple of 16 bytes");
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, launch_count(count_args(c, d_bytes, n_bytes), stream ? (cudaStream_t)stream : c->main_stream));
+	c->st.n_blocks++;
+	return VAFGPU_OK;
+}
+
+int kcgpu_extract_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, int n_parts, uint64_t *d_keys,
+                         size_t cap_per_part, uint32_t *d_part_counts, void *stream)
+{
+	if (!c) return VAFGPU_EINVAL;
+	if (n_parts < 1 || n_parts > KC_MAX_PARTS) return kfail(c, VAFGPU_EINVAL, "n_parts = %d is outside 1..%d", n_parts, KC_MAX_PARTS);
+	if (((uintptr_t)d_bytes & 15) || (n_bytes & 15))
+		return kfail(c, VAFGPU_EINVAL, "device stream must be 16-byte aligned and a multiple of 16 bytes");
+	if (!d_keys || !d_part_counts) return kfail(c, VAFGPU_EINVAL, "output lists are NULL");
+	if (cap_per_part >= ((size_t)1 << 32)) return kfail(c, VAFGPU_EINVAL, "cap_per_part must be below 2^32");
+	CountArgs a = count_args(c, d_bytes, n_bytes);
+	a.n_parts = (uint32_t)n_parts;
+	a.out_keys = d_keys;
+	a.cap_per_part = cap_per_part;
+	a.part_counts = d_part_counts;
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, launch_extract(a, stream ? (cudaStream_t)stream : c->main_stream));
+	c->st.n_blocks++;
+	return VAFGPU_OK;
+}
+
+int kcgpu_insert_device(kcgpu_ctx *c, const uint64_t *d_hashed_keys, size_t n, int n_parts, void *stream)
+{
+	if (!c) return VAFGPU_EINVAL;
+	if (n_parts < 1 || n_parts > KC_MAX_PARTS) return kfail(c, VAFGPU_EINVAL, "n_parts = %d is outside 1..%d", n_parts, KC_MAX_PARTS);
+	if (n && !d_hashed_keys) return kfail(c, VAFGPU_EINVAL, "keys are NULL");
+	InsertArgs a{};
+	a.hashed = d_hashed_keys;
+	a.n = n;
+	a.n_parts = (uint32_t)n_parts;
+	a.region_bits = c->region_bits;
+	a.rslot_bits = c->rslot_bits;
+	a.table = c->d_table;
+	a.stats = c->d_stats;
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, launch_insert(a, stream ? (cudaStream_t)stream : c->main_stream));
+	return VAFGPU_OK;
+}
+
+int kcgpu_table(kcgpu_ctx *c, void **d_table, uint64_t *table_slots)
+{
+	if (!c) return VAFGPU_EINVAL;
+	if (d_table) *d_table = c->d_table;
+	if (table_slots) *table_slots = c->n_slots;
+	return VAFGPU_OK;
+}
+
+int kcgpu_ipc_export(kcgpu_ctx *c, void *handle)
+{
+	if (!c || !handle) return VAFGPU_EINVAL;
+	static_assert(sizeof(cudaIpcMemHandle_t) == KCGPU_IPC_HANDLE_BYTES, "IPC handle size");
+	cudaIpcMemHandle_t h;
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, cudaIpcGetMemHandle(&h, c->d_table));
+	memcpy(handle, &h, sizeof h);
+	return VAFGPU_OK;
+}
+
+int kcgpu_ipc_open(kcgpu_ctx *c, const void *handle, void **d_peer_table)
+{
+	if (!c || !handle || !d_peer_table) return VAFGPU_EINVAL;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof h);
+	void *p = nullptr;
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	c->ipc_mapped.push_back(p);
+	*d_peer_table = p;
+	return VAFGPU_OK;
+}
+
+int kcgpu_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *tables)
+{
+	if (!c) return VAFGPU_EINVAL;
+	if (n_parts < 1 || n_parts > KC_MAX_PARTS || my_part < 0 || my_part >= n_parts || !tables)
+		return kfail(c, VAFGPU_EINVAL, "owner %d of %d", my_part, n_parts);
+	int rc = kc_sync_one(c); /* nothing of this context may still be running with the old owners */
+	if (rc) return rc;
+	for (int i = 0; i < n_parts; ++i) {
+		if (!tables[i] && i != my_part) return kfail(c, VAFGPU_EINVAL, "table of owner %d is NULL", i);
+		c->tables[i] = tables[i] ? static_cast<uint64_t *>(tables[i]) : c->d_table;
+	}
+	c->n_parts = (uint32_t)n_parts;
+	c->my_part = (uint32_t)my_part;
+	return VAFGPU_OK;
+}
+
+int kcgpu_link(kcgpu_ctx *const *ctxs, int n)
+{
+	if (!ctxs || n < 1 || n > KC_MAX_PARTS) return VAFGPU_EINVAL;
+	for (int i = 0; i < n; ++i) {
+		if (!ctxs[i]) return VAFGPU_EINVAL;
+		if (ctxs[i]->n_slots != ctxs[0]->n_slots || ctxs[i]->k != ctxs[0]->k)
+			return kfail(ctxs[i], VAFGPU_EINVAL, "linked contexts must share k and the table size");
+	}
+	for (int i = 0; i < n; ++i) {
+		kcgpu_ctx *c = ctxs[i];
+		KCU(c, cudaSetDevice(c->device));
+		for (int j = 0; j < n; ++j) {
+			if (ctxs[j]->device == c->device) continue;
+			int ok = 0;
+			KCU(c, cudaDeviceCanAccessPeer(&ok, c->device, ctxs[j]->device));
+			if (!ok) return kfail(c, VAFGPU_ECUDA, "device %d cannot reach device %d's memory", c->device, ctxs[j]->device);
+			cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+			if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+			else if (e != cudaSuccess) return kfail(c, VAFGPU_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+		}
+	}
+	std::vector<void *> tables(n);
+	for (int i = 0; i < n; ++i) tables[i] = ctxs[i]->d_table;
+	for (int i = 0; i < n; ++i) {
+		int rc = kcgpu_set_owners(ctxs[i], n, i, tables.data());
+		if (rc) return rc;
+		ctxs[i]->group.assign(ctxs, ctxs + n);
+	}
+	return VAFGPU_OK;
+}
+
+int kcgpu_sync(kcgpu_ctx *c)
+{
+	if (!c) return VAFGPU_EINVAL;
+	for (kcgpu_ctx *m : c->group) {
+		int rc = kc_sync_one(m);
+		if (rc) {
+			if (m != c) c->err = m->err;
+			return rc;
+		}
+	}
+	return VAFGPU_OK;
+}
+
+int kcgpu_histogram(kcgpu_ctx *c, uint64_t hist[256], kcgpu_stats *stats)
+{
+	if (!c) return VAFGPU_EINVAL;
+	int rc = kcgpu_sync(c);
+	if (rc) return rc;
+	KCU(c, cudaSetDevice(c->device));
+	if (hist) {
+		KCU(c, cudaMemsetAsync(c->d_hist, 0, 256 * sizeof(unsigned long long), c->main_stream));
+		KCU(c, launch_histogram(c->d_table, c->n_slots, c->d_hist, c->n_sm, c->main_stream));
+		unsigned long long h[256];
+		KCU(c, cudaMemcpyAsync(h, c->d_hist, sizeof h, cudaMemcpyDeviceToHost, c->main_stream));
+		KCU(c, cudaStreamSynchronize(c->main_stream));
+		for (int i = 0; i < 256; ++i) hist[i] = h[i];
+		hist[0] = 0;
+	}
+	if (stats) {
+		rc = kc_read_stats(c);
+		if (rc) return rc;
+		*stats = c->st;
+	}
+	return VAFGPU_OK;
+}
+
+int kcgpu_reset(kcgpu_ctx *c)
+{
+	if (!c) return VAFGPU_EINVAL;
+	int rc = kcgpu_sync(c);
+	if (rc) return rc;
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, cudaMemsetAsync(c->d_table, 0, c->n_slots * 8, c->main_stream));
+	KCU(c, cudaMemsetAsync(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long), c->main_stream));
+	const uint64_t slots = c->st.table_slots;
+	c->st = kcgpu_stats{};
+	c->st.table_slots = slots;
+	return VAFGPU_OK;
+}
+
+void kcgpu_destroy(kcgpu_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	for (kcgpu_ctx *m : c->group) /* the others must not wait for a context that is gone */
+		if (m != c) {
+			for (size_t i = 0; i < m->group.size(); ++i)
+				if (m->group[i] == c) {
+					m->group.erase(m->group.begin() + i);
+					break;
+				}
+		}
+	for (KcBlock &b : c->blocks) {
+		if (b.stream) cudaStreamSynchronize(b.stream);
+		if (b.h) cudaFreeHost(b.h);
+		if (b.d) cudaFree(b.d);
+		if (b.e0) cudaEventDestroy(b.e0);
+		if (b.e1) cudaEventDestroy(b.e1);
+		if (b.e2) cudaEventDestroy(b.e2);
+		if (b.stream) cudaStreamDestroy(b.stream);
+	}
+	if (c->main_stream) {
+		cudaStreamSynchronize(c->main_stream);
+		cudaStreamDestroy(c->main_stream);
+	}
+	for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
+	cudaFree(c->d_table);
+	cudaFree(c->d_stats);
+	cudaFree(c->d_hist);
+	delete c;
+}
+
+} // extern "C"

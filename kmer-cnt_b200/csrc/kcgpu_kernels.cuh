@@ -1,0 +1,81 @@
+/*
+ * kcgpu_kernels.cuh -- launch interface between the C ABI of include/kcgpu.h and the sm_100a
+ * kernels of the full k-mer counting mode, plus the table geometry both sides share.
+ *
+ * Table: n_slots 64-bit words, cut into 2^region_bits regions of 2^rslot_bits slots.  A k-mer
+ * with hash h = hash64(canonical k-mer) (kc-c4.c:40-50) belongs to owner h mod n_parts; with
+ * q = h div n_parts its region is the low region_bits of q (the reference's partition by hash
+ * suffix, kc-c4.c:66) and the slot holds (q >> region_bits) << 10 | count, the reference's
+ * "key << KC_BITS | count" word (kc-c4.c:11-15,124-125).  0 is a free slot (a used slot has a
+ * count of at least 1).  Linear probing inside the region from a multiplicative hash of the
+ * tag.  Nothing is lost: (owner, region, tag) give h back, and hash64 is invertible.
+ */
+#ifndef KCGPU_KERNELS_CUH
+#define KCGPU_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KC_HD __host__ __device__ __forceinline__
+#else
+#define KC_HD static inline
+#endif
+
+namespace kcgpu {
+
+enum { KC_COUNT_BITS = 10, KC_COUNT_MAX = 1023 }; /* kc-c4.c:11-12 */
+enum { KC_MAX_PARTS = 16 };
+enum { KC_MAX_PROBES = 8192 }; /* a region this crowded is reported as overflow, not walked for ever */
+enum { KC_TAG_BITS = 64 - KC_COUNT_BITS };
+
+/* per-context counters the kernels add to (unsigned long long each) */
+enum { KC_ST_KMERS = 0, KC_ST_NEW = 1, KC_ST_OVERFLOW = 2, KC_ST_DROPPED = 3, KC_ST_N = 4 };
+
+/* regions needed so that the tag of a 2k-bit hash fits beside the count */
+KC_HD uint32_t kc_region_bits(int k) { return 2 * k > KC_TAG_BITS ? (uint32_t)(2 * k - KC_TAG_BITS) : 0u; }
+
+KC_HD uint64_t kc_hash64(uint64_t key, uint64_t mask) /* kc-c4.c:40-50 */
+{
+	key = (~key + (key << 21)) & mask;
+	key ^= key >> 24;
+	key = (key * 265) & mask;
+	key ^= key >> 14;
+	key = (key * 21) & mask;
+	key ^= key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+
+struct CountArgs {
+	const uint8_t *bytes; /* stream: reads separated by '\n', 16-byte aligned */
+	uint64_t n_bytes;     /* multiple of 16                                    */
+	int k;
+	uint32_t n_parts;     /* owners of the hash space                          */
+	uint32_t region_bits, rslot_bits;
+	uint64_t *tables[KC_MAX_PARTS]; /* table of every owner (peer memory over NVLink for the others) */
+	unsigned long long *stats;
+	/* extract-only form */
+	uint64_t *out_keys;   /* [part * cap_per_part + i] */
+	uint64_t cap_per_part;
+	uint32_t *part_counts;
+};
+
+struct InsertArgs {
+	const uint64_t *hashed; /* hash64 values owned by this table */
+	uint64_t n;
+	uint32_t n_parts;
+	uint32_t region_bits, rslot_bits;
+	uint64_t *table;
+	unsigned long long *stats;
+};
+
+/* asynchronous launches on `stream` */
+cudaError_t launch_count(const CountArgs &a, cudaStream_t stream);   /* fused extract + insert */
+cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream); /* extract into per-owner lists */
+cudaError_t launch_insert(const InsertArgs &a, cudaStream_t stream);
+cudaError_t launch_histogram(const uint64_t *table, uint64_t n_slots, unsigned long long *hist256, int n_sm,
+                             cudaStream_t stream);
+
+} // namespace kcgpu
+#endif

@@ -1,0 +1,145 @@
+/*
+ * kc_count.c -- the kc-c4 command line on top of libvafgpu's counting mode (include/kcgpu.h).
+ *
+ * Same options, input and output as the reference tool (kc-c4.c:217-252):
+ *   kc-c4 [-k INT] [-p INT] [-b INT] [-t INT] <in.fa>
+ * prints the 255 lines "count<TAB>number of distinct canonical k-mers seen that often" (the
+ * last line collects 255 and more) on stdout.  The host keeps option parsing, FASTA/FASTQ
+ * parsing and the printing; count_seq_buf, the partitioned insert and the histogram scan
+ * (kc-c4.c:74-128,186-215) run on the GPUs.
+ *   -p  only checked (>= 10, kc-c4.c:243-246): the partition into 2^p tables is an internal of
+ *       the reference; here the hash space is split over the visible GPUs instead
+ *   -b  bases per turn when reads are dealt to several GPUs (the reference's block size)
+ *   -t  accepted; the insert it used to parallelise runs on the GPU
+ * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: all visible);
+ *              KCGPU_TABLE_SLOTS=n slots per GPU to start with (default: from the file size);
+ *              either way a table that fills up is doubled and the file counted again.
+ * Deviations: k outside 1..31 is rejected (the reference shifts by >= 64 bits there), and a
+ * file that cannot be opened is an error (the reference dereferences NULL, kc-c4.c:166,247-248).
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/kcgpu.h"
+#include "fastx.h"
+
+static uint64_t guess_slots(const char *fn, int n_dev)
+{
+	struct stat sb;
+	uint64_t est;
+	FILE *fp;
+	unsigned char magic[2] = {0, 0};
+	if (stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode)) return 0; /* a pipe: as large as fits */
+	est = (uint64_t)sb.st_size;
+	if ((fp = fopen(fn, "rb")) != NULL) {
+		if (fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) est *= 4; /* gzip */
+		fclose(fp);
+	}
+	est = est * 2 / (uint64_t)n_dev; /* at most one k-mer per byte; half-empty tables */
+	if (est < (1u << 20)) est = 1u << 20;
+	return est;
+}
+
+int main(int argc, char *argv[])
+{
+	int c, k = 31, p = 10, block_size = 10000000, n_thread = 4, n_dev = 0, i;
+	while ((c = getopt(argc, argv, "k:p:b:t:")) >= 0) {
+		if (c == 'k') k = atoi(optarg);
+		else if (c == 'p') p = atoi(optarg);
+		else if (c == 'b') block_size = atoi(optarg);
+		else if (c == 't') n_thread = atoi(optarg);
+	}
+	if (argc - optind < 1) { /* kc-c4.c:235-242 */
+		fprintf(stderr, "Usage: kc-c4 [options] <in.fa>\n");
+		fprintf(stderr, "Options:\n");
+		fprintf(stderr, "  -k INT     k-mer size [%d]\n", k);
+		fprintf(stderr, "  -p INT     prefix length [%d]\n", p);
+		fprintf(stderr, "  -b INT     block size [%d]\n", block_size);
+		fprintf(stderr, "  -t INT     number of worker threads [%d]\n", n_thread);
+		return 1;
+	}
+	if (p < 10) { /* kc-c4.c:243-246 */
+		fprintf(stderr, "ERROR: -p should be at least %d\n", 10);
+		return 1;
+	}
+	if (k < 1 || k > 31) {
+		fprintf(stderr, "ERROR: -k should be between 1 and 31\n");
+		return 1;
+	}
+	if (block_size < 1) block_size = 1;
+	const char *fn = argv[optind];
+
+	n_dev = kcgpu_device_count();
+	if (n_dev < 1) {
+		fprintf(stderr, "ERROR: no CUDA device (this build has no CPU path)\n");
+		return 1;
+	}
+	if (getenv("KCGPU_DEVICES") && atoi(getenv("KCGPU_DEVICES")) > 0 && atoi(getenv("KCGPU_DEVICES")) < n_dev)
+		n_dev = atoi(getenv("KCGPU_DEVICES"));
+	if (n_dev > KCGPU_MAX_OWNERS) n_dev = KCGPU_MAX_OWNERS;
+
+	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn, n_dev);
+	for (int attempt = 0;; ++attempt) {
+		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
+		uint64_t hist[256], part[256], overflow = 0;
+		kcgpu_stats st;
+		for (i = 0; i < n_dev; ++i)
+			if (kcgpu_create(&ctx[i], k, slots, 0, i) != VAFGPU_OK) {
+				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
+				return 1;
+			}
+		if (n_dev > 1 && kcgpu_link(ctx, n_dev) != VAFGPU_OK) {
+			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
+			return 1;
+		}
+		fastx_t *fx = fastx_open(fn);
+		if (!fx) {
+			fprintf(stderr, "ERROR: cannot open %s\n", fn);
+			return 1;
+		}
+		const char *seq;
+		long len;
+		int turn = 0;
+		uint64_t in_turn = 0;
+		while ((len = fastx_next(fx, &seq)) >= 0) { /* kc-c4.c:139-152 */
+			if (len < k) continue;
+			if (kcgpu_add_read(ctx[turn], seq, (size_t)len) != VAFGPU_OK) {
+				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[turn]));
+				return 1;
+			}
+			in_turn += (uint64_t)len;
+			if (in_turn >= (uint64_t)block_size) { /* kc-c4.c:150: the next block goes to the next GPU */
+				in_turn = 0;
+				turn = (turn + 1) % n_dev;
+			}
+		}
+		fastx_close(fx);
+		memset(hist, 0, sizeof hist);
+		for (i = 0; i < n_dev; ++i) {
+			if (kcgpu_histogram(ctx[i], part, &st) != VAFGPU_OK) {
+				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[i]));
+				return 1;
+			}
+			for (int j = 0; j < 256; ++j) hist[j] += part[j];
+			overflow += st.n_overflow;
+			slots = st.table_slots;
+		}
+		for (i = 0; i < n_dev; ++i) kcgpu_destroy(ctx[i]);
+		if (overflow) { /* never print a histogram with k-mers missing */
+			struct stat sb;
+			if (attempt >= 12 || stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode)) { /* a pipe cannot be read twice */
+				fprintf(stderr, "ERROR: the k-mer table (%llu slots per GPU) is full\n", (unsigned long long)slots);
+				return 1;
+			}
+			slots *= 2;
+			fprintf(stderr, "[kc-c4] table full, counting again with %llu slots per GPU\n", (unsigned long long)slots);
+			continue;
+		}
+		for (i = 1; i < 256; ++i) printf("%d\t%ld\n", i, (long)hist[i]); /* kc-c4.c:232-233 */
+		return 0;
+	}
+}

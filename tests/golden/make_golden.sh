@@ -4,6 +4,8 @@
 # reference tools or an input we generated ourselves; no reference source is copied.
 #   kat_vaf.tsv            known answers of the reference's own functions (oracle/ref_kat.c)
 #   e2e_*/                 small inputs + the .vaf the reference vaf-counter wrote for them
+#   kat_kc.tsv             known answers of kc-c4's hash64 / count_seq_buf (oracle/ref_kat_kc.c)
+#   kc/<reads>.k<K>.hist   what the reference kc-c4 -k K prints for e2e_<reads>/reads.fq.gz
 #   cfg2_patterns.txt.gz   snp-pattern-gen -k 21 over a synthetic hg38-length genome and the
 #                          NGSCheckMate GRCh38 panel (made separately, see tools/make_cfg2_patterns.sh)
 set -euo pipefail
@@ -29,4 +31,14 @@ mk k21 21 -L 60000 -n 300 -r 4000 -l 150 -s 11
 mk k15 15 -L 60000 -n 300 -r 4000 -l 150 -s 12 -N 0.02 -M 4
 mk k31 31 -L 60000 -n 300 -r 4000 -l 150 -s 13 -N 0.05 -M 5
 mk exotic 21 -L 60000 -n 300 -r 4000 -l 150 -j 40 -s 14 -x 0.01
-ls -la "$here" "$here"/e2e_*
+
+# counting mode: known answers of kc-c4's own functions, and the histogram the reference kc-c4
+# prints for the read sets above
+"$ref/ref_kat_kc" > "$here/kat_kc.tsv"
+rm -rf "$here/kc"; mkdir -p "$here/kc"
+for name in k21 k15 k31 exotic; do
+	for k in 5 15 21 28 31; do
+		"$ref/kc-c4" -k "$k" -t 2 "$here/e2e_$name/reads.fq.gz" > "$here/kc/$name.k$k.hist"
+	done
+done
+ls -la "$here" "$here"/e2e_* "$here"/kc

@@ -1,0 +1,140 @@
+"""The counting-mode oracle (oracle/kc_oracle.c) against the reference kc-c4: known answers of
+its own functions (tests/golden/kat_kc.tsv, dumped from the reference's object code), the
+histograms the reference binary printed for the committed read sets (tests/golden/kc/), and the
+live binary when oracle/_ref exists.  Plus the host side of the counting ABI.  No GPU."""
+import gzip
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from util import kcgpu
+
+KC_REF = os.path.join(util.REF_DIR, "kc-c4")
+GOLDEN_KC = os.path.join(util.GOLDEN, "kc")
+
+
+@pytest.fixture(scope="module")
+def kco():
+    return util.KcOracle()
+
+
+def kat_rows(kind):
+    with open(os.path.join(util.GOLDEN, "kat_kc.tsv")) as fh:
+        for line in fh:
+            f = line.rstrip("\n").split("\t")
+            if f[0] == kind:
+                yield f[1:]
+
+
+def test_base_table_matches_reference(kco):
+    rows = list(kat_rows("nt4"))
+    assert len(rows) == 256
+    for b, code in rows:
+        assert kco.lib.kco_nt4(int(b)) == int(code)
+
+
+def test_hash64_matches_reference(kco, lib):
+    kcgpu.load_library()
+    n = 0
+    for k, x, want in kat_rows("hash64"):
+        assert kco.lib.kco_hash64(int(x, 16), int(k)) == int(want, 16)
+        assert kcgpu.hash64(int(x, 16), int(k)) == int(want, 16)  # the library's host export
+        n += 1
+    assert n >= 400
+
+
+def test_hash64_is_a_bijection(kco):
+    for k in (1, 2, 5, 8):
+        seen = {kco.lib.kco_hash64(x, k) for x in range(1 << 2 * k)}
+        assert len(seen) == 1 << 2 * k and max(seen) < 1 << 2 * k
+
+
+def test_hashed_kmers_match_reference(kco):
+    n = 0
+    for k, hexseq, cnt, vals in kat_rows("kmers"):
+        seq = bytes.fromhex(hexseq)
+        got = kco.hashed_kmers(seq, int(k))
+        want = [int(v, 16) for v in vals.split(",")] if vals else []
+        assert len(want) == int(cnt)
+        assert got.tolist() == want, (k, seq)
+        n += 1
+    assert n >= 50
+
+
+@pytest.mark.parametrize("name", ["k21", "k15", "k31", "exotic"])
+@pytest.mark.parametrize("k", [5, 15, 21, 28, 31])
+def test_histogram_matches_reference_golden(kco, name, k):
+    hist, n_inst, n_dist = kco.count_file(os.path.join(util.GOLDEN, f"e2e_{name}", "reads.fq.gz"), k)
+    want = open(os.path.join(GOLDEN_KC, f"{name}.k{k}.hist")).read()
+    assert kcgpu.format_histogram(hist) == want
+    assert int(hist.sum()) == n_dist and hist[0] == 0
+
+
+@pytest.mark.skipif(not os.path.exists(KC_REF), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_histogram_matches_live_reference(kco, tmp_path):
+    rng = np.random.default_rng(5)
+    reads = util.make_genome_reads(rng, 30000, 3000, jitter=60, junk_rate=0.004, lower_rate=0.05, repeat=12)
+    reads += [b"", b"ACGT", b"N" * 40, b"ACGTTGCA" * 3]
+    for fasta, line in ((False, 0), (True, 60)):
+        fn = str(tmp_path / ("r.fa" if fasta else "r.fq"))
+        util.write_fastq(fn, reads, fasta=fasta, line=line)
+        for k in (3, 10, 17, 31):
+            for p in (10, 12):
+                ref = subprocess.run([KC_REF, "-k", str(k), "-p", str(p), "-t", "3", "-b", "100000", fn],
+                                     check=True, capture_output=True).stdout.decode()
+                hist, _, _ = kco.count_file(fn, k)
+                assert kcgpu.format_histogram(hist) == ref, (fasta, k, p)
+                hist2, _, _ = kco.count_reads(reads, k)
+                assert np.array_equal(hist, hist2)
+
+
+def test_saturation_and_top_bin(kco):
+    """a k-mer seen more than 1023 times stays at 1023 (kc-c4.c:125) and lands in bin 255"""
+    hist, n_inst, n_dist = kco.count_reads([b"A" * 2000], 11)
+    assert n_inst == 1990 and n_dist == 1 and hist[255] == 1 and int(hist.sum()) == 1
+    hist, _, _ = kco.count_reads([b"AC" * 150], 4)  # ACAC / GTGT canonical pair and CACA / TGTG
+    assert int(hist.sum()) == 2
+
+
+def test_abi_exports_match_header(lib):
+    hdr = open(os.path.join(util.ROOT, "include", "kcgpu.h")).read()
+    declared = re.findall(r"\b(kcgpu_[a-z0-9_]+)\s*\(", hdr)
+    declared = [d for d in dict.fromkeys(declared)]
+    assert set(declared) == set(kcgpu.EXPORTS), set(declared) ^ set(kcgpu.EXPORTS)
+    kl = kcgpu.load_library()
+    for name in kcgpu.EXPORTS:
+        getattr(kl, name)
+
+
+def test_no_gpu_fails_loudly(lib):
+    """without a B200 the product must refuse, not fall back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(util.vafgpu.VafGpuError) as e:
+        kcgpu.Counter(21, 1 << 16)
+    assert e.value.code == util.vafgpu.ENOGPU
+
+
+def test_owner_split_partitions_the_histogram(kco):
+    """several owners: a k-mer belongs to hash mod n; per-owner histograms add up to the whole
+    (what the several-GPU forms rely on)"""
+    rng = np.random.default_rng(9)
+    reads = util.make_genome_reads(rng, 20000, 1500, repeat=5)
+    for k in (15, 31):
+        hashed = np.concatenate([kco.hashed_kmers(r, k) for r in reads if len(r) >= k])
+        whole, n_inst, n_dist = kco.count_reads(reads, k)
+        assert n_inst == hashed.size
+        for n in (2, 3, 8):
+            own = kcgpu.owner_of(hashed, n)
+            total = np.zeros(256, dtype=np.uint64)
+            dist = 0
+            for part in range(n):
+                h, _, d = kco.count_hashed(hashed[own == part], k)
+                total += h
+                dist += d
+            assert np.array_equal(total, whole) and dist == n_dist

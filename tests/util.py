@@ -289,3 +289,102 @@ def write_fastq(path: str, reads: Sequence[bytes], *, fasta: bool = False, line:
                     fh.write(r + b"\n")
             else:
                 fh.write(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)))
+
+
+# ---------------------------------------------------------------------------------------------
+# counting mode (kc-c4 path)
+
+import kcgpu  # noqa: E402
+
+
+class KcOracle:
+    """liboracle.so's restatement of kc-c4 (oracle/kc_oracle.h)."""
+
+    def __init__(self):
+        build_oracle()
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "liboracle.so"))
+        lib.kco_nt4.argtypes = [C.c_uint8]
+        lib.kco_hash64.argtypes = [C.c_uint64, C.c_int]
+        lib.kco_hash64.restype = C.c_uint64
+        lib.kco_hashed_kmers.argtypes = [C.c_char_p, C.c_long, C.c_int, C.POINTER(C.c_uint64)]
+        lib.kco_hashed_kmers.restype = C.c_long
+        lib.kco_create.argtypes = [C.c_int]
+        lib.kco_create.restype = C.c_void_p
+        lib.kco_destroy.argtypes = [C.c_void_p]
+        lib.kco_add_read.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+        lib.kco_add_hashed.argtypes = [C.c_void_p, C.c_uint64]
+        lib.kco_add_file.argtypes = [C.c_void_p, C.c_char_p]
+        lib.kco_hist.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.kco_distinct.argtypes = [C.c_void_p]
+        lib.kco_distinct.restype = C.c_uint64
+        lib.kco_instances.argtypes = [C.c_void_p]
+        lib.kco_instances.restype = C.c_uint64
+        self.lib = lib
+
+    def hashed_kmers(self, seq: bytes, k: int) -> np.ndarray:
+        out = np.zeros(max(len(seq), 1), dtype=np.uint64)
+        n = self.lib.kco_hashed_kmers(seq, len(seq), k, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return out[:n]
+
+    def _finish(self, o) -> Tuple[np.ndarray, int, int]:
+        hist = np.zeros(256, dtype=np.uint64)
+        self.lib.kco_hist(o, hist.ctypes.data_as(C.POINTER(C.c_uint64)))
+        res = hist, int(self.lib.kco_instances(o)), int(self.lib.kco_distinct(o))
+        self.lib.kco_destroy(o)
+        return res
+
+    def count_reads(self, reads: Sequence[bytes], k: int) -> Tuple[np.ndarray, int, int]:
+        """(hist[256], k-mer instances, distinct k-mers) of kc-c4's recipe over `reads`."""
+        o = self.lib.kco_create(k)
+        for r in reads:
+            self.lib.kco_add_read(o, r, len(r))
+        return self._finish(o)
+
+    def count_file(self, fn: str, k: int) -> Tuple[np.ndarray, int, int]:
+        o = self.lib.kco_create(k)
+        assert self.lib.kco_add_file(o, fn.encode()) == 0, fn
+        return self._finish(o)
+
+    def count_hashed(self, hashed: np.ndarray, k: int) -> Tuple[np.ndarray, int, int]:
+        o = self.lib.kco_create(k)
+        for h in np.asarray(hashed, dtype=np.uint64).tolist():
+            self.lib.kco_add_hashed(o, h)
+        return self._finish(o)
+
+
+def pack_stream_strict(reads: Sequence[bytes], k: int) -> np.ndarray:
+    """What kcgpu_add_read builds in a staging block (strict base table everywhere)."""
+    return pack_stream(reads, k, simd_rule=False)
+
+
+def make_genome_reads(rng: np.random.Generator, genome_len: int, n_reads: int, *, mean_len: int = 150, jitter: int = 0,
+                      sub_rate: float = 0.01, n_rate: float = 0.003, junk_rate: float = 0.0, lower_rate: float = 0.0,
+                      repeat: int = 0) -> List[bytes]:
+    """Reads drawn from both strands of one random genome (so that k-mers repeat with the depth),
+    with substitutions, N, junk bytes and lower case; `repeat` low-complexity reads are appended
+    (poly-A, dinucleotide runs: the same k-mer hundreds of times, which exercises the saturating count)."""
+    g = ACGT[rng.integers(0, 4, genome_len)]
+    reads = []
+    for _ in range(n_reads):
+        ln = max(mean_len + (int(rng.integers(-jitter, jitter + 1)) if jitter else 0), 0)
+        ln = min(ln, genome_len)
+        at = int(rng.integers(0, genome_len - ln + 1))
+        s = g[at:at + ln].copy()
+        if sub_rate:
+            m = rng.random(ln) < sub_rate
+            s[m] = ACGT[rng.integers(0, 4, int(m.sum()))]
+        if rng.random() < 0.5:
+            s = COMP[s][::-1].copy()
+        if n_rate:
+            s[rng.random(ln) < n_rate] = ord("N")
+        if junk_rate:
+            m = rng.random(ln) < junk_rate
+            s[m] = JUNK[rng.integers(0, len(JUNK), int(m.sum()))]
+        if lower_rate:
+            m = rng.random(ln) < lower_rate
+            s[m] = s[m] | 0x20
+        reads.append(s.tobytes())
+    for i in range(repeat):
+        unit = [b"A", b"AC", b"T", b"ACG", b"GT"][i % 5]
+        reads.append((unit * 400)[: 300 + 7 * i])
+    return reads

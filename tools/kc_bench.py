@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""kc_bench.py -- Gbases/s of the full k-mer counting mode (the kc-c4 path, BASELINE config 5).
+
+    python tools/kc_bench.py [--reads N] [--k 31] [--steps K] [--warmup W] [--form fused|staged|both]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... tools/kc_bench.py --gpus N ...
+
+Workload: --reads x 150 bp synthetic reads IN TOTAL (strong scaling: every rank holds reads/N of
+them), drawn from both strands of one random genome of --genome bases with 1 % substitutions
+and 0.5 % N, generated on the GPU as the stream the engine consumes.  One step = empty tables,
+count every k-mer of the resident stream into the hash-partitioned tables, histogram.
+
+  fused    kcgpu_count_device after kcgpu_set_owners: the counting kernel adds every k-mer to
+           its owner's table itself, over NVLink peer memory (CUDA IPC between the ranks)
+  staged   kcgpu_extract_device -> torch.distributed.all_to_all_single (NCCL) -> kcgpu_insert_device,
+           in chunks of the stream: the NCCL baseline the fused form is compared with
+
+Prints one JSON line (rank 0).  The CPU baseline is the UNMODIFIED reference kc-c4 (oracle/_ref)
+on a bounded sample of the same reads; the same sample is also counted on the GPU through the
+CLI-facing entry point (kcgpu_add_read) and the two histograms must be identical.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "kmer-cnt_b200"))
+
+READ_LEN = 150
+
+
+def log(*a):
+    print("[kc_bench]", *a, file=sys.stderr, flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--reads", type=int, default=100_000_000, help="reads in total over all GPUs")
+    ap.add_argument("--genome", type=int, default=1_000_000_000)
+    ap.add_argument("--k", type=int, default=31)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--form", default="both", choices=["fused", "staged", "both"])
+    ap.add_argument("--table-slots", type=int, default=0, help="per GPU; 0 = from the expected number of distinct k-mers")
+    ap.add_argument("--sample", type=int, default=1_000_000, help="reads of the CPU baseline / parity sample")
+    ap.add_argument("--chunk-mb", type=int, default=1024, help="stream bytes per extract/exchange/insert round (staged)")
+    args = ap.parse_args()
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import bench as vb
+    import kcgpu
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    k = args.k
+    n_reads = args.reads // world
+
+    t0 = time.perf_counter()
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)  # the same genome on every rank
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    genome = torch.empty(args.genome, dtype=torch.uint8, device=dev)
+    for lo in range(0, args.genome, 1 << 28):
+        n = min(1 << 28, args.genome - lo)
+        genome[lo:lo + n] = acgt[torch.randint(0, 4, (n,), device=dev, generator=g)]
+    donor = torch.cat([genome, genome])
+    del genome
+    stream, n_bytes = vb.make_stream(torch, donor, args.genome, n_reads, 77 + rank, dev)
+    del donor
+    torch.cuda.synchronize()
+    n_bases = n_reads * READ_LEN
+    log(f"rank {rank}: {n_reads} reads ({stream.numel() / 1e9:.2f} GB) generated in {time.perf_counter() - t0:.1f} s")
+
+    exp_kmers = args.reads * (READ_LEN - k + 1)
+    slots = args.table_slots
+    if not slots:
+        # distinct k-mers: the genome's plus up to k new ones per substitution; tables at most ~0.7 full
+        est = args.genome + int(args.reads * READ_LEN * 0.01 * k)
+        slots = 1 << 20
+        while slots < 1.4 * min(est, exp_kmers) / world:
+            slots *= 2
+    ctr = kcgpu.Counter(k, slots, device=local)
+    my_table, slots = ctr.table()
+    log(f"rank {rank}: table of {slots} slots ({slots * 8 / 1e9:.1f} GB)")
+
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctr.ipc_export())
+        tables = [None if r == rank else ctr.ipc_open(handles[r]) for r in range(world)]
+        ctr.set_owners(rank, tables)
+        own_only = [my_table]  # staged form: a context that only knows its own table
+    ts = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def total_hist(h):
+        if world == 1:
+            return h
+        t = torch.from_numpy(h.astype(np.int64)).to(dev)
+        dist.all_reduce(t)
+        return t.cpu().numpy().astype(np.uint64)
+
+    chunk = args.chunk_mb << 20
+    rec = READ_LEN + 1
+    chunk -= chunk % (rec * 16)
+    kpc = chunk // rec * (READ_LEN - k + 1)  # k-mers per chunk at most
+    cap = int(kpc / world * 1.1) + 4096
+    if args.form in ("staged", "both"):
+        keys = torch.empty(world * cap, dtype=torch.int64, device=dev)
+        recv = torch.empty(int(world * cap), dtype=torch.int64, device=dev)
+        pcounts = torch.zeros(world, dtype=torch.int32, device=dev)
+
+    def step_fused():
+        ctr.count_device(stream.data_ptr(), stream.numel(), ts)
+
+    def step_staged():
+        for lo in range(0, stream.numel(), chunk):
+            n = min(chunk, stream.numel() - lo)
+            pcounts.zero_()
+            ctr.extract_device(stream.data_ptr() + lo, n, world, keys.data_ptr(), cap, pcounts.data_ptr(), ts)
+            if world == 1:
+                cnt = int(pcounts[0].item())
+                ctr.insert_device(keys.data_ptr(), cnt, 1, ts)
+                continue
+            send = pcounts.to(torch.int64)
+            got = torch.empty_like(send)
+            dist.all_to_all_single(got, send)
+            s_list, r_list = send.tolist(), got.tolist()
+            assert max(s_list) <= cap, "exchange lists too short"
+            packed = torch.cat([keys[p * cap:p * cap + s_list[p]] for p in range(world)])
+            out = recv[:sum(r_list)]
+            dist.all_to_all_single(out, packed, output_split_sizes=r_list, input_split_sizes=s_list)
+            ctr.insert_device(out.data_ptr(), out.numel(), world, ts)
+
+    results = {}
+    hists = {}
+    forms = ["fused", "staged"] if args.form == "both" else [args.form]
+    for form in forms:
+        fn = step_fused if form == "fused" else step_staged
+        if form == "staged" and world > 1:
+            ctr.set_owners(0, own_only)  # n_parts of the table's own kernels is irrelevant for extract/insert
+        times, count_ms = [], []
+        for it in range(args.warmup + args.steps):
+            ctr.reset()
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            fn()
+            e1.record()
+            ctr.sync()
+            barrier()
+            t1 = time.perf_counter()
+            h, st = ctr.histogram()
+            h = total_hist(h)
+            t_hist = time.perf_counter() - t1
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            if it >= args.warmup:
+                times.append(ms)
+                count_ms.append(t_hist * 1e3)
+        hists[form] = h
+        stt = torch.tensor([st["n_kmers"], st["n_distinct"], st["n_overflow"], st["n_dropped"]], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(stt)
+        tot = stt.tolist()
+        ms = sum(times) / len(times)
+        results[form] = {
+            "gbases_s": args.reads * READ_LEN / ms / 1e6, "gkmers_s": tot[0] / ms / 1e6, "ms_per_step": ms,
+            "hist_ms": sum(count_ms) / len(count_ms), "n_kmers": tot[0], "n_distinct_claims": tot[1],
+            "n_overflow": tot[2], "n_dropped": tot[3], "distinct": int(h.sum()),
+        }
+        log(f"{form}: {results[form]}")
+        if form == "staged" and world > 1:
+            ctr.set_owners(rank, tables)
+    if len(forms) == 2:
+        assert np.array_equal(hists["fused"], hists["staged"]), "fused and staged histograms differ"
+
+    out = None
+    if rank == 0:
+        best = max(results, key=lambda f: results[f]["gbases_s"])
+        r = results[best]
+        # algorithmic bytes: 1 byte per base read + one 8-byte slot read and written per k-mer
+        alg = n_bases * world + 16 * r["n_kmers"]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6544.3)) * world
+        out = {
+            "metric": "Gbases/s", "value": r["gbases_s"], "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8 in, u64 integer arithmetic and 64-bit atomics", "data": "synthetic",
+            "config": {"workload": f"config 5: kc-c4 k={k} full k-mer counting, {args.reads} x {READ_LEN} bp synthetic reads in total "
+                                   f"from a {args.genome}-base genome, hash-partitioned tables over {world} GPU(s)",
+                       "k": k, "reads_total": args.reads, "table_slots_per_gpu": slots, "form": best,
+                       "l2": "table and stream are far larger than L2"},
+            "forms": results,
+            "roofline": {"bound": "hbm", "achieved": alg / r["ms_per_step"] / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": alg / r["ms_per_step"] / 1e6 / peak, "traffic": None,
+                         "algorithmic_bytes": "1 B per base + 16 B (slot read + write) per k-mer instance",
+                         "kernel": "kc_scan_kernel"},
+            "table_load": r["distinct"] / (slots * world),
+        }
+
+    # parity + CPU baseline on a bounded sample (rank 0)
+    if rank == 0 and args.sample:
+        ns = min(args.sample, n_reads)
+        host = stream[:ns * rec].cpu().numpy().tobytes()
+        reads = vb.stream_to_reads(host)
+        tmp = tempfile.mkdtemp(dir=vb.shm_dir())
+        fa = os.path.join(tmp, "sample.fa")
+        with open(fa, "wb") as fh:
+            fh.write(b"".join(b">r%d\n%s\n" % (i, s) for i, s in enumerate(reads)))
+        ref = os.path.join(ROOT, "oracle", "_ref", "kc-c4")
+        kind = "reference"
+        if not os.path.exists(ref):
+            ref, kind = os.path.join(ROOT, "oracle", "kc_oracle"), "port"
+        cores = os.cpu_count() or 1
+        best_t, best_threads, ref_out = None, None, None
+        for th in sorted({1, 4, cores}) if kind == "reference" else [1]:
+            t1 = time.perf_counter()
+            ref_out = subprocess.run([ref, "-k", str(k), "-t", str(th), fa], check=True, capture_output=True).stdout.decode()
+            dt = time.perf_counter() - t1
+            log(f"{kind} kc-c4 -t {th}: {dt:.2f} s")
+            if best_t is None or dt < best_t:
+                best_t, best_threads = dt, th
+        with kcgpu.Counter(k, 1 << 28, device=local) as c2:
+            t1 = time.perf_counter()
+            for s in reads:
+                c2.add_read(s)
+            h2, st2 = c2.histogram()
+            t_api = time.perf_counter() - t1
+        cli = os.path.join(ROOT, "kmer-cnt_b200", "kc-c4")
+        t1 = time.perf_counter()
+        cli_out = subprocess.run([cli, "-k", str(k), fa], check=True, capture_output=True,
+                                 env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))).stdout.decode()
+        t_cli = time.perf_counter() - t1
+        out["cpu_baseline"] = {"value": ns * READ_LEN / best_t / 1e9, "unit": "Gbases/s", "cores": best_threads, "kind": kind,
+                               "sample": f"{ns} reads x {READ_LEN} bp of this workload as FASTA, whole process wall clock, best of -t 1/4/{cores}"}
+        out["parity"] = {"histogram_vs_reference_on_sample": "identical" if kcgpu.format_histogram(h2) == ref_out else "DIFFERENT",
+                         "cli_vs_reference_on_sample": "identical" if cli_out == ref_out else "DIFFERENT",
+                         "fused_equals_staged": (len(forms) == 2) or None}
+        out["this_repo_on_sample"] = {"add_read_python_loop_gbases_s": ns * READ_LEN / t_api / 1e9,
+                                      "cli_whole_process_gbases_s": ns * READ_LEN / t_cli / 1e9}
+        for f in os.listdir(tmp):
+            os.unlink(os.path.join(tmp, f))
+        os.rmdir(tmp)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    ctr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,11 +11,13 @@
  * hash64 is a bijection on 2k-bit words, so the reference's tables hold exactly one entry per
  * distinct canonical k-mer; the histogram is a function of the multiset of canonical k-mers and
  * of nothing else.  Here one open-addressing table per GPU holds the reference's own slot word
- * (hash bits << 10 | count).  With several GPUs a k-mer belongs to GPU hash64(k-mer) mod n (the
- * reference's partition by hash suffix, kc-c4.c:66, generalised from 2^p tables to n owners).
- * Two ways to get it there:
- *   fused    kcgpu_set_owners(): the counting kernel itself adds every k-mer to its owner's
- *            table, over NVLink peer memory for the other GPUs (no exchange buffers);
+ * (hash bits << 10 | count).  Like the reference, the scan does not touch the table: it files
+ * every hashed k-mer under its region (hash suffix) in a list, and the lists are emptied into
+ * the table region by region ("flush"), so that the slice of the table being filled stays in
+ * L2.  With several GPUs a k-mer belongs to GPU hash64(k-mer) mod n (the reference's partition
+ * by hash suffix, kc-c4.c:66, generalised from 2^p tables to n owners).  Two ways to get it there:
+ *   fused    kcgpu_set_owners(): the counting kernel itself files every k-mer in its owner's
+ *            lists, over NVLink peer memory for the other GPUs (no exchange buffers);
  *   staged   kcgpu_extract_device() files hashed k-mers per owner, the caller exchanges the
  *            lists (NCCL all-to-all), kcgpu_insert_device() adds what arrived.
  *
@@ -38,6 +40,7 @@ typedef struct kcgpu_ctx kcgpu_ctx;
 
 #define KCGPU_MAX_OWNERS 16
 #define KCGPU_IPC_HANDLE_BYTES 64
+#define KCGPU_NO_LISTS UINT64_MAX /* list_slots: no region lists, every k-mer goes straight to the table */
 
 typedef struct kcgpu_stats {
 	uint64_t n_reads;     /* reads accepted by kcgpu_add_read (len >= k)                      */
@@ -47,7 +50,11 @@ typedef struct kcgpu_stats {
 	uint64_t n_distinct;  /* slots this context's kernels claimed (in any owner's table)       */
 	uint64_t n_overflow;  /* k-mers lost because a table region was full: counts incomplete    */
 	uint64_t n_dropped;   /* k-mers that did not fit the lists of kcgpu_extract_device         */
+	uint64_t n_direct;    /* k-mers that found their region list full and went straight to the table */
+	uint64_t n_flushes;
 	uint64_t table_slots;
+	uint64_t list_slots;  /* capacity of the region lists, all regions together                */
+	uint64_t flush_bytes; /* stream bytes a context takes between two flushes                  */
 	double   kernel_ms;   /* kernels behind kcgpu_add_read (CUDA events on their streams)      */
 	double   h2d_ms;
 } kcgpu_stats;
@@ -56,12 +63,13 @@ typedef struct kcgpu_stats {
 int kcgpu_device_count(void);
 
 /*
- * One context = one table on one device.  table_slots is rounded up to a power of two
- * (at least 4096); 0 = the largest power of two that fits in 3/4 of the device's free memory
- * (8 bytes per slot).  block_bytes: size of each pinned staging block behind kcgpu_add_read
- * (0 = 16 MiB).
+ * One context = one table and its region lists on one device.  table_slots is rounded up to a
+ * power of two (at least 4096); 0 = the largest power of two that, with its lists, fits in 3/4
+ * of the device's free memory (8 bytes per slot).  list_slots: capacity of the region lists
+ * (8 bytes each; 0 = table_slots / 2; KCGPU_NO_LISTS = none).  block_bytes: size of each pinned
+ * staging block behind kcgpu_add_read (0 = 16 MiB).
  */
-int kcgpu_create(kcgpu_ctx **ctx, int k, uint64_t table_slots, size_t block_bytes, int device);
+int kcgpu_create(kcgpu_ctx **ctx, int k, uint64_t table_slots, uint64_t list_slots, size_t block_bytes, int device);
 
 /*
  * Hand one parsed read to the engine: replaces the per-read copy of step 0 and steps 1 and 2
@@ -74,8 +82,11 @@ int kcgpu_add_read(kcgpu_ctx *ctx, const char *seq, size_t len);
 /*
  * Count a stream that is already resident on the context's device: reads separated by '\n',
  * 16-byte aligned, n_bytes a multiple of 16; bytes other than A C G T U (either case) end a
- * k-mer.  Fused extract + insert, into the tables named by kcgpu_set_owners (default: this
- * context's own).  `stream` is a cudaStream_t (NULL = the context's own).  Asynchronous.
+ * k-mer; k-mers do not span calls.  Every k-mer is filed with its owner as named by
+ * kcgpu_set_owners (default: this context).  `stream` is a cudaStream_t (NULL = the context's
+ * own).  Asynchronous, except that the call flushes first (and waits for it) when the lists
+ * could not take n_bytes more k-mers; a context whose owners were set by kcgpu_set_owners never
+ * flushes by itself (see there).
  */
 int kcgpu_count_device(kcgpu_ctx *ctx, const void *d_bytes, size_t n_bytes, void *stream);
 
@@ -92,13 +103,19 @@ int kcgpu_extract_device(kcgpu_ctx *ctx, const void *d_bytes, size_t n_bytes, in
 int kcgpu_insert_device(kcgpu_ctx *ctx, const uint64_t *d_hashed_keys, size_t n, int n_parts, void *stream);
 
 /*
- * Several GPUs, fused form.  The table of this context as a device pointer and as a CUDA IPC
- * handle (KCGPU_IPC_HANDLE_BYTES bytes) for another process; kcgpu_ipc_open maps a peer's
- * table into this process.  kcgpu_set_owners names the table of every owner (all of the same
- * size as this context's; tables[my_part] may be NULL = this context's own); from then on this
- * context's kernels add a k-mer to tables[hash mod n_parts].  kcgpu_link does all of it for
- * contexts of one process (peer access enabled both ways) and makes kcgpu_sync /
- * kcgpu_histogram of any member wait for all of them.
+ * Several GPUs, fused form.  The allocation of this context (table, lists, cursors) as a device
+ * pointer and as a CUDA IPC handle (KCGPU_IPC_HANDLE_BYTES bytes) for another process;
+ * kcgpu_ipc_open maps a peer's allocation into this process.  kcgpu_set_owners names the
+ * allocation of every owner (all created with the same k, table_slots and list_slots as this
+ * context; tables[my_part] may be NULL = this context's own); from then on this context's
+ * kernels file a k-mer with owner hash mod n_parts.  The owners may live in other processes, so
+ * such a context never flushes by itself: the caller calls kcgpu_flush on every owner, between
+ * two barriers (nobody may be filing while lists are emptied), at the latest when the contexts
+ * together have taken n_parts * kcgpu_stats.flush_bytes of stream since the last flush.  Lists
+ * that fill up earlier cost speed, not k-mers: the excess goes straight to the table.
+ * kcgpu_link does all of it for contexts of one process (peer access enabled both ways),
+ * flushes the group when it is due, and makes kcgpu_sync / kcgpu_flush / kcgpu_histogram of any
+ * member act on all of them.
  */
 int kcgpu_table(kcgpu_ctx *ctx, void **d_table, uint64_t *table_slots);
 int kcgpu_ipc_export(kcgpu_ctx *ctx, void *handle);
@@ -110,8 +127,12 @@ int kcgpu_link(kcgpu_ctx *const *ctxs, int n);
  * contexts linked to it).  Across processes the caller adds its own barrier. */
 int kcgpu_sync(kcgpu_ctx *ctx);
 
+/* kcgpu_sync, then empty the region lists of this context (and of the contexts linked to it)
+ * into the table(s), and wait for that. */
+int kcgpu_flush(kcgpu_ctx *ctx);
+
 /*
- * kcgpu_sync, then the histogram of kc-c4.c:186-215 over this context's table: hist[c] = number
+ * kcgpu_flush, then the histogram of kc-c4.c:186-215 over this context's table: hist[c] = number
  * of distinct canonical k-mers seen min(c, 255) times, counts saturating at 1023 first as in
  * kc-c4.c:125 (hist[0] is 0).  With several owners the per-context histograms are summed by
  * the caller (they partition the k-mers).  Counting can go on afterwards.

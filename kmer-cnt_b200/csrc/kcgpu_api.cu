@@ -1,7 +1,8 @@
 /*
- * kcgpu_api.cu -- the C ABI of include/kcgpu.h: one table per context, pinned staging blocks
- * with a stream each (the copy of block i+1 overlaps the kernel of block i, which replaces
- * kt_pipeline's three steps, kc-c4.c:130-183), peer tables for the fused several-GPU form.
+ * kcgpu_api.cu -- the C ABI of include/kcgpu.h: one table with its region lists per context,
+ * pinned staging blocks with a stream each (the copy of block i+1 overlaps the kernel of block
+ * i, which replaces kt_pipeline's three steps, kc-c4.c:130-183), the flush of the lists into
+ * the table when they are due, peer allocations for the fused several-GPU form.
  * Host logic only; the kernels are in kcgpu_kernels.cu.
  */
 #include "../../include/kcgpu.h"
@@ -37,9 +38,14 @@ struct KcBlock {
 
 struct kcgpu_ctx {
 	int k = 0, device = 0, n_sm = 0;
-	uint64_t n_slots = 0;
+	uint64_t n_slots = 0, list_cap = 0; /* list_cap: entries per region; 0 = no lists */
 	uint32_t region_bits = 0, rslot_bits = 0;
-	uint64_t *d_table = nullptr;
+	uint64_t *d_table = nullptr;        /* the whole allocation: table, lists, cursors */
+	uint64_t pending_bytes = 0;         /* stream bytes filed since the last flush */
+	uint64_t flush_bytes = 0;           /* flush before pending_bytes exceeds this */
+	bool external_owners = false;       /* owners set by kcgpu_set_owners: the caller flushes */
+	std::vector<std::pair<cudaStream_t, cudaEvent_t>> user_streams; /* last launch on each caller stream */
+	cudaEvent_t f0 = nullptr, f1 = nullptr;
 	unsigned long long *d_stats = nullptr, *d_hist = nullptr;
 	cudaStream_t main_stream = nullptr;
 	size_t block_bytes = 0;
@@ -94,13 +100,55 @@ CountArgs count_args(const kcgpu_ctx *c, const void *bytes, size_t n)
 	CountArgs a{};
 	a.bytes = static_cast<const uint8_t *>(bytes);
 	a.n_bytes = n;
+	a.first_chunk = 0;
+	a.end_chunk = n >> 4;
+	a.n_slots = c->n_slots;
+	a.list_cap = c->list_cap;
 	a.k = c->k;
+	a.exp = getenv("KCGPU_EXP") ? atoi(getenv("KCGPU_EXP")) : 0;
 	a.n_parts = c->n_parts;
 	a.region_bits = c->region_bits;
 	a.rslot_bits = c->rslot_bits;
 	for (uint32_t i = 0; i < c->n_parts; ++i) a.tables[i] = c->tables[i];
 	a.stats = c->d_stats;
 	return a;
+}
+
+int kc_flush_group(kcgpu_ctx *c);
+
+cudaError_t kc_launch_scan(const kcgpu_ctx *c, const CountArgs &a, cudaStream_t s)
+{
+	if (!c->list_cap) return launch_count(a, s);
+	return c->n_parts > 1 ? launch_push(a, s) : launch_partition(a, s);
+}
+
+/* what the lists (one owner) or the inbox (several owners) of m hold, into its table */
+cudaError_t kc_launch_flush(const kcgpu_ctx *m, cudaStream_t s)
+{
+	if (m->n_parts == 1)
+		return launch_flush(m->d_table, m->n_slots, m->list_cap, m->region_bits, m->rslot_bits, m->d_stats, s);
+	InsertArgs a{};
+	a.hashed = kc_lists_of(m->d_table, m->n_slots);
+	a.n = m->list_cap << m->region_bits;
+	a.n_ptr = kc_cursors_of(m->d_table, m->n_slots, m->list_cap, m->region_bits);
+	a.split = 1;
+	a.n_parts = m->n_parts;
+	a.region_bits = m->region_bits;
+	a.rslot_bits = m->rslot_bits;
+	a.table = m->d_table;
+	a.stats = m->d_stats;
+	return launch_insert(a, s);
+}
+
+/* the lists must be able to take n more k-mers: flush first if they might not (a context whose
+ * owners the caller named flushes only when told to) */
+int kc_make_room(kcgpu_ctx *c, uint64_t n_bytes)
+{
+	if (!c->list_cap || c->external_owners) return VAFGPU_OK;
+	uint64_t pending = 0;
+	for (const kcgpu_ctx *m : c->group) pending += m->pending_bytes;
+	if (pending && pending + n_bytes > c->flush_bytes * c->group.size()) return kc_flush_group(c);
+	return VAFGPU_OK;
 }
 
 int kc_submit_current(kcgpu_ctx *c)
@@ -111,13 +159,16 @@ int kc_submit_current(kcgpu_ctx *c)
 	if (!b->used) return VAFGPU_OK;
 	const size_t n = (b->used + 15) & ~(size_t)15;
 	memset(b->h + b->used, '\n', n - b->used);
+	int rc = kc_make_room(c, n);
+	if (rc) return rc;
 	KCU(c, cudaSetDevice(c->device));
 	KCU(c, cudaEventRecord(b->e0, b->stream));
 	KCU(c, cudaMemcpyAsync(b->d, b->h, n, cudaMemcpyHostToDevice, b->stream));
 	KCU(c, cudaEventRecord(b->e1, b->stream));
-	KCU(c, launch_count(count_args(c, b->d, n), b->stream));
+	KCU(c, kc_launch_scan(c, count_args(c, b->d, n), b->stream));
 	KCU(c, cudaEventRecord(b->e2, b->stream));
 	b->in_flight = true;
+	c->pending_bytes += n;
 	c->st.n_blocks++;
 	return VAFGPU_OK;
 }
@@ -149,6 +200,55 @@ int kc_sync_one(kcgpu_ctx *c)
 		if (rc) return rc;
 	}
 	KCU(c, cudaStreamSynchronize(c->main_stream));
+	for (auto &us : c->user_streams) KCU(c, cudaEventSynchronize(us.second));
+	return VAFGPU_OK;
+}
+
+/* every member: wait for what was filed, empty the lists into the table, wait for that */
+int kc_flush_group(kcgpu_ctx *c)
+{
+	for (kcgpu_ctx *m : c->group) {
+		int rc = kc_sync_one(m);
+		if (rc) {
+			if (m != c) c->err = m->err;
+			return rc;
+		}
+	}
+	for (kcgpu_ctx *m : c->group) {
+		if (!m->list_cap) continue;
+		KCU(m, cudaSetDevice(m->device));
+		KCU(m, cudaEventRecord(m->f0, m->main_stream));
+		KCU(m, kc_launch_flush(m, m->main_stream));
+		KCU(m, cudaMemsetAsync(kc_cursors_of(m->d_table, m->n_slots, m->list_cap, m->region_bits), 0,
+		                       (size_t)KC_CURSOR_STRIDE * 8 << m->region_bits, m->main_stream));
+		KCU(m, cudaEventRecord(m->f1, m->main_stream));
+	}
+	for (kcgpu_ctx *m : c->group) {
+		if (!m->list_cap) continue;
+		KCU(m, cudaSetDevice(m->device));
+		KCU(m, cudaStreamSynchronize(m->main_stream));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, m->f0, m->f1);
+		m->st.kernel_ms += ms;
+		m->st.n_flushes++;
+		m->pending_bytes = 0;
+	}
+	return VAFGPU_OK;
+}
+
+/* a launch went to a stream of the caller's: remember where it ends */
+int kc_note_user_stream(kcgpu_ctx *c, cudaStream_t s)
+{
+	if (s == c->main_stream) return VAFGPU_OK;
+	for (auto &us : c->user_streams)
+		if (us.first == s) {
+			KCU(c, cudaEventRecord(us.second, s));
+			return VAFGPU_OK;
+		}
+	cudaEvent_t e;
+	KCU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	c->user_streams.emplace_back(s, e);
+	KCU(c, cudaEventRecord(e, s));
 	return VAFGPU_OK;
 }
 
@@ -161,6 +261,7 @@ int kc_read_stats(kcgpu_ctx *c)
 	c->st.n_distinct = s[KC_ST_NEW];
 	c->st.n_overflow = s[KC_ST_OVERFLOW];
 	c->st.n_dropped = s[KC_ST_DROPPED];
+	c->st.n_direct = s[KC_ST_DIRECT];
 	return VAFGPU_OK;
 }
 
@@ -186,7 +287,7 @@ int kcgpu_device_count(void)
 
 const char *kcgpu_strerror(const kcgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_kc_create_error.c_str(); }
 
-int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, size_t block_bytes, int device)
+int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slots, size_t block_bytes, int device)
 {
 	if (!out) return kfail(nullptr, VAFGPU_EINVAL, "ctx is NULL");
 	*out = nullptr;
@@ -213,12 +314,16 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, size_t block_byte
 			return kfail(c, VAFGPU_ENOGPU, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", device, prop.name,
 			             prop.major, prop.minor);
 		c->n_sm = prop.multiProcessorCount;
-		c->region_bits = kc_region_bits(k);
-		const uint64_t min_slots = (uint64_t)4096 > ((uint64_t)16 << c->region_bits) ? (uint64_t)4096 : ((uint64_t)16 << c->region_bits);
+		if (const char *env = getenv("KCGPU_L2_FETCH")) /* tuning knob: 32, 64 or 128 */
+			KCU(c, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env)));
+		const uint32_t need_bits = kc_region_bits(k); /* regions the slot word needs (tag beside the count) */
+		const uint64_t min_slots = (uint64_t)4096 > ((uint64_t)16 << need_bits) ? (uint64_t)4096 : ((uint64_t)16 << need_bits);
+		const bool lists = list_slots != KCGPU_NO_LISTS;
 		if (table_slots == 0) {
 			size_t free_b = 0, total_b = 0;
 			KCU(c, cudaMemGetInfo(&free_b, &total_b));
-			const uint64_t budget = (uint64_t)free_b / 4 * 3 / 8;
+			uint64_t budget = (uint64_t)free_b / 4 * 3 / 8; /* 8-byte words */
+			if (lists) budget = list_slots ? (budget > list_slots ? budget - list_slots : 0) : budget / 3 * 2;
 			table_slots = min_slots;
 			while (table_slots * 2 <= budget) table_slots *= 2;
 		}
@@ -230,13 +335,41 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, size_t block_byte
 		c->n_slots = n;
 		uint32_t bits = 0;
 		while ((1ull << bits) < n) ++bits;
+		/* regions: what the slot word needs, and small enough (16 MiB) to stay in L2 while the
+		 * lists of one region are emptied into it */
+		uint32_t slice_bits = KC_REGION_SLOT_BITS;
+		if (const char *env = getenv("KCGPU_REGION_SLOT_BITS")) /* tuning knob */
+			if (atoi(env) >= 8 && atoi(env) <= 30) slice_bits = (uint32_t)atoi(env);
+		c->region_bits = need_bits;
+		if (lists && bits > slice_bits && bits - slice_bits > c->region_bits) c->region_bits = bits - slice_bits;
+		if (c->region_bits > 20) c->region_bits = 20;
 		c->rslot_bits = bits - c->region_bits;
-		KCU(c, cudaMalloc(&c->d_table, n * 8));
+		if (lists) {
+			if (list_slots == 0) list_slots = n / 2;
+			uint64_t cap = (list_slots >> c->region_bits) + 31 & ~(uint64_t)31;
+			if (cap < 64) cap = 64;
+			if (cap >> 40) return kfail(c, VAFGPU_EINVAL, "list_slots too large");
+			c->list_cap = cap;
+			c->flush_bytes = (cap << c->region_bits) / 20 * 19; /* a byte is at most one k-mer; what a list cannot take goes to the table */
+			if (c->flush_bytes > ((uint64_t)1 << 40)) c->flush_bytes = (uint64_t)1 << 40;
+		}
+		const uint64_t alloc = kc_alloc_bytes(n, c->list_cap, c->region_bits);
+		cudaError_t me = cudaMalloc(&c->d_table, alloc);
+		if (me != cudaSuccess) {
+			cudaGetLastError();
+			return kfail(c, VAFGPU_ENOMEM, "cannot allocate %llu MiB on device %d for %llu slots and lists of %llu: %s",
+			             (unsigned long long)(alloc >> 20), device, (unsigned long long)n,
+			             (unsigned long long)(c->list_cap << c->region_bits), cudaGetErrorString(me));
+		}
 		KCU(c, cudaMalloc(&c->d_stats, KC_ST_N * sizeof(unsigned long long)));
 		KCU(c, cudaMalloc(&c->d_hist, 256 * sizeof(unsigned long long)));
 		KCU(c, cudaMemset(c->d_table, 0, n * 8));
+		if (c->list_cap)
+			KCU(c, cudaMemset(kc_cursors_of(c->d_table, n, c->list_cap, c->region_bits), 0, (size_t)KC_CURSOR_STRIDE * 8 << c->region_bits));
 		KCU(c, cudaMemset(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long)));
 		KCU(c, cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking));
+		KCU(c, cudaEventCreate(&c->f0));
+		KCU(c, cudaEventCreate(&c->f1));
 		c->blocks.resize(3);
 		for (KcBlock &b : c->blocks) {
 			KCU(c, cudaHostAlloc(&b.h, block_bytes + 64, cudaHostAllocPortable));
@@ -257,6 +390,8 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, size_t block_byte
 	c->tables[0] = c->d_table;
 	c->group.push_back(c);
 	c->st.table_slots = c->n_slots;
+	c->st.list_slots = c->list_cap << c->region_bits;
+	c->st.flush_bytes = c->flush_bytes;
 	*out = c;
 	return VAFGPU_OK;
 }
@@ -299,9 +434,35 @@ int kcgpu_count_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, void *
 	if (!c) return VAFGPU_EINVAL;
 	if (((uintptr_t)d_bytes & 15) || (n_bytes & 15))
 		return kfail(c, VAFGPU_EINVAL, "device stream must be 16-byte aligned and a multiple of 16 bytes");
-	KCU(c, cudaSetDevice(c->device));
-	KCU(c, launch_count(count_args(c, d_bytes, n_bytes), stream ? (cudaStream_t)stream : c->main_stream));
-	c->st.n_blocks++;
+	cudaStream_t s = stream ? (cudaStream_t)stream : c->main_stream;
+	/* as much at a time as the lists are sure to take, a flush in between */
+	const uint64_t n_chunks = n_bytes >> 4;
+	uint64_t step = n_chunks;
+	if (c->list_cap && !c->external_owners) {
+		step = c->flush_bytes * c->group.size() >> 4;
+		if (step < 4096) step = 4096;
+	}
+	for (uint64_t lo = 0; lo < n_chunks;) {
+		uint64_t pending = 0;
+		for (const kcgpu_ctx *m : c->group) pending += m->pending_bytes;
+		uint64_t room = step > (pending >> 4) ? step - (pending >> 4) : 0;
+		if (c->list_cap && !c->external_owners && room < 4096 && pending) {
+			int rc = kc_flush_group(c);
+			if (rc) return rc;
+			continue;
+		}
+		const uint64_t hi = lo + room < n_chunks && room ? lo + room : n_chunks;
+		CountArgs a = count_args(c, d_bytes, n_bytes);
+		a.first_chunk = lo;
+		a.end_chunk = hi;
+		KCU(c, cudaSetDevice(c->device));
+		KCU(c, kc_launch_scan(c, a, s));
+		int rc = kc_note_user_stream(c, s);
+		if (rc) return rc;
+		c->pending_bytes += (hi - lo) << 4;
+		c->st.n_blocks++;
+		lo = hi;
+	}
 	return VAFGPU_OK;
 }
 
@@ -320,9 +481,10 @@ int kcgpu_extract_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, int 
 	a.cap_per_part = cap_per_part;
 	a.part_counts = d_part_counts;
 	KCU(c, cudaSetDevice(c->device));
-	KCU(c, launch_extract(a, stream ? (cudaStream_t)stream : c->main_stream));
+	cudaStream_t s = stream ? (cudaStream_t)stream : c->main_stream;
+	KCU(c, launch_extract(a, s));
 	c->st.n_blocks++;
-	return VAFGPU_OK;
+	return kc_note_user_stream(c, s);
 }
 
 int kcgpu_insert_device(kcgpu_ctx *c, const uint64_t *d_hashed_keys, size_t n, int n_parts, void *stream)
@@ -339,8 +501,9 @@ int kcgpu_insert_device(kcgpu_ctx *c, const uint64_t *d_hashed_keys, size_t n, i
 	a.table = c->d_table;
 	a.stats = c->d_stats;
 	KCU(c, cudaSetDevice(c->device));
-	KCU(c, launch_insert(a, stream ? (cudaStream_t)stream : c->main_stream));
-	return VAFGPU_OK;
+	cudaStream_t s = stream ? (cudaStream_t)stream : c->main_stream;
+	KCU(c, launch_insert(a, s));
+	return kc_note_user_stream(c, s);
 }
 
 int kcgpu_table(kcgpu_ctx *c, void **d_table, uint64_t *table_slots)
@@ -380,8 +543,9 @@ int kcgpu_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *tables
 	if (!c) return VAFGPU_EINVAL;
 	if (n_parts < 1 || n_parts > KC_MAX_PARTS || my_part < 0 || my_part >= n_parts || !tables)
 		return kfail(c, VAFGPU_EINVAL, "owner %d of %d", my_part, n_parts);
-	int rc = kc_sync_one(c); /* nothing of this context may still be running with the old owners */
+	int rc = kc_flush_group(c); /* nothing of this context may still be running, or waiting in a list, under the old owners */
 	if (rc) return rc;
+	c->external_owners = true;
 	for (int i = 0; i < n_parts; ++i) {
 		if (!tables[i] && i != my_part) return kfail(c, VAFGPU_EINVAL, "table of owner %d is NULL", i);
 		c->tables[i] = tables[i] ? static_cast<uint64_t *>(tables[i]) : c->d_table;
@@ -396,8 +560,8 @@ int kcgpu_link(kcgpu_ctx *const *ctxs, int n)
 	if (!ctxs || n < 1 || n > KC_MAX_PARTS) return VAFGPU_EINVAL;
 	for (int i = 0; i < n; ++i) {
 		if (!ctxs[i]) return VAFGPU_EINVAL;
-		if (ctxs[i]->n_slots != ctxs[0]->n_slots || ctxs[i]->k != ctxs[0]->k)
-			return kfail(ctxs[i], VAFGPU_EINVAL, "linked contexts must share k and the table size");
+		if (ctxs[i]->n_slots != ctxs[0]->n_slots || ctxs[i]->k != ctxs[0]->k || ctxs[i]->list_cap != ctxs[0]->list_cap)
+			return kfail(ctxs[i], VAFGPU_EINVAL, "linked contexts must share k, the table size and the list size");
 	}
 	for (int i = 0; i < n; ++i) {
 		kcgpu_ctx *c = ctxs[i];
@@ -417,7 +581,10 @@ int kcgpu_link(kcgpu_ctx *const *ctxs, int n)
 	for (int i = 0; i < n; ++i) {
 		int rc = kcgpu_set_owners(ctxs[i], n, i, tables.data());
 		if (rc) return rc;
+	}
+	for (int i = 0; i < n; ++i) {
 		ctxs[i]->group.assign(ctxs, ctxs + n);
+		ctxs[i]->external_owners = false; /* the group is in this process: it flushes itself */
 	}
 	return VAFGPU_OK;
 }
@@ -435,10 +602,16 @@ int kcgpu_sync(kcgpu_ctx *c)
 	return VAFGPU_OK;
 }
 
+int kcgpu_flush(kcgpu_ctx *c)
+{
+	if (!c) return VAFGPU_EINVAL;
+	return kc_flush_group(c);
+}
+
 int kcgpu_histogram(kcgpu_ctx *c, uint64_t hist[256], kcgpu_stats *stats)
 {
 	if (!c) return VAFGPU_EINVAL;
-	int rc = kcgpu_sync(c);
+	int rc = kc_flush_group(c);
 	if (rc) return rc;
 	KCU(c, cudaSetDevice(c->device));
 	if (hist) {
@@ -465,10 +638,17 @@ int kcgpu_reset(kcgpu_ctx *c)
 	if (rc) return rc;
 	KCU(c, cudaSetDevice(c->device));
 	KCU(c, cudaMemsetAsync(c->d_table, 0, c->n_slots * 8, c->main_stream));
+	if (c->list_cap)
+		KCU(c, cudaMemsetAsync(kc_cursors_of(c->d_table, c->n_slots, c->list_cap, c->region_bits), 0,
+		                       (size_t)KC_CURSOR_STRIDE * 8 << c->region_bits, c->main_stream));
 	KCU(c, cudaMemsetAsync(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long), c->main_stream));
-	const uint64_t slots = c->st.table_slots;
+	KCU(c, cudaStreamSynchronize(c->main_stream));
+	const kcgpu_stats keep = c->st;
 	c->st = kcgpu_stats{};
-	c->st.table_slots = slots;
+	c->st.table_slots = keep.table_slots;
+	c->st.list_slots = keep.list_slots;
+	c->st.flush_bytes = keep.flush_bytes;
+	c->pending_bytes = 0;
 	return VAFGPU_OK;
 }
 
@@ -497,6 +677,9 @@ void kcgpu_destroy(kcgpu_ctx *c)
 		cudaStreamSynchronize(c->main_stream);
 		cudaStreamDestroy(c->main_stream);
 	}
+	for (auto &us : c->user_streams) cudaEventDestroy(us.second);
+	if (c->f0) cudaEventDestroy(c->f0);
+	if (c->f1) cudaEventDestroy(c->f1);
 	for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
 	cudaFree(c->d_table);
 	cudaFree(c->d_stats);

@@ -1,25 +1,36 @@
 /*
  * kcgpu_kernels.cu -- sm_100a kernels of the full k-mer counting mode (the kc-c4 path).
  *
- *  kc_scan_kernel<false>   fused extract + insert: every thread owns the 16 stream positions
- *                          of one 128-bit chunk, warms its two rolling words up on the 32
- *                          bytes before them (k - 1 <= 30), and for each position where a
- *                          k-mer ends (kc-c4.c:80-87) hashes the canonical word (kc-c4.c:40-50)
- *                          and adds it to its owner's table with 64-bit compare-and-swap.
- *                          The owner's table may be peer memory: the same instruction then
- *                          travels over NVLink, which is the all-to-all of kc-c4's partition
- *                          step (kc-c4.c:64-72) fused into the producer.
- *  kc_scan_kernel<true>    extract only: hashed k-mers are appended to one list per owner
- *                          (warp-aggregated), for an exchange by NCCL all-to-all.
- *  kc_insert_kernel        the insert step for lists that came from an exchange (kc-c4.c:116-128)
+ *  kc_scan_kernel<MODE>    every thread owns the 16 stream positions of one 128-bit chunk, warms
+ *                          its two rolling words up on the 32 bytes before them (k - 1 <= 30),
+ *                          and for each position where a k-mer ends (kc-c4.c:80-87) hashes the
+ *                          canonical word (kc-c4.c:40-50).  Then
+ *    KC_PARTITION          appends it to the list of its region in its owner's allocation
+ *                          (count_seq_buf / c4x_insert_buf, kc-c4.c:64-90); a list that is full
+ *                          sends the k-mer straight to the table instead;
+ *    KC_PUSH               several owners: appends it to its owner's inbox (the owner's list area
+ *                          used as one list).  The CTA counts its k-mers per owner in shared
+ *                          memory and reserves one range per owner with one atomic on the
+ *                          owner's cursor, so a warp's k-mers for one owner are neighbours and
+ *                          leave as whole sectors -- over NVLink when the owner is a peer;
+ *    KC_DIRECT             adds it to its owner's table with 64-bit compare-and-swap;
+ *    KC_EXTRACT            appends it to one list per owner (warp-aggregated), for an exchange
+ *                          by NCCL all-to-all.
+ *                          In the first two the owner's memory may be a peer's: the same
+ *                          instructions then travel over NVLink, which is the all-to-all of
+ *                          the partition step fused into the producer.
+ *  kc_flush_kernel         worker_for (kc-c4.c:116-128): the region lists into the table, region
+ *                          by region so that the slice being filled stays in L2
+ *  kc_insert_kernel        the same for lists that came from an exchange
  *  kc_hist_kernel          worker_hist (kc-c4.c:186-197) over the slots
  *
- * No tensor cores: shifts, multiplies and atomics.  The bound is random 32-byte sector
- * traffic of the table.
+ * No tensor cores: shifts, multiplies and atomics.
  */
 #include "kcgpu_kernels.cuh"
 
 #include <cooperative_groups.h>
+
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -50,18 +61,20 @@ __device__ __forceinline__ uint64_t cas_slot(uint64_t *p, uint64_t expect, uint6
 	return atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)expect, (unsigned long long)want);
 }
 
-/* kc-c4.c:116-128 on one table: find or claim the slot of q, count up to 1023 */
-__device__ __forceinline__ void kc_insert(uint64_t *table, uint32_t region_bits, uint32_t rslot_bits, uint64_t q,
-                                          uint32_t &n_new, uint32_t &n_overflow)
+enum { KC_PARTITION = 0, KC_DIRECT = 1, KC_EXTRACT = 2, KC_PUSH = 3 };
+
+__device__ __forceinline__ uint64_t kc_home(uint64_t tag, uint32_t rslot_bits) { return (tag * 0x9E3779B97F4A7C15ull) >> (64 - rslot_bits); }
+
+/* kc-c4.c:116-128 on one region of one table: find or claim the slot of `tag`, count up to 1023.
+ * `v` is what the home slot `pos` held when the caller looked (callers look at several home
+ * slots before they resolve the first, so that the loads overlap). */
+__device__ __forceinline__ void kc_insert_from(uint64_t *base, uint32_t rslot_bits, uint64_t tag, uint64_t pos, uint64_t v,
+                                               uint32_t &n_new, uint32_t &n_overflow)
 {
-	const uint64_t region = q & ((1ull << region_bits) - 1ull);
-	const uint64_t tag = q >> region_bits;
 	const uint64_t rmask = (1ull << rslot_bits) - 1ull;
-	uint64_t *base = table + (region << rslot_bits);
-	uint64_t pos = (tag * 0x9E3779B97F4A7C15ull) >> (64 - rslot_bits);
 	for (int tries = 0; tries < KC_MAX_PROBES; ++tries) {
 		uint64_t *p = base + pos;
-		uint64_t v = ld_slot(p);
+		if (tries) v = ld_slot(p);
 		if (v == 0) {
 			v = cas_slot(p, 0, (tag << KC_COUNT_BITS) | 1ull);
 			if (v == 0) {
@@ -80,6 +93,20 @@ __device__ __forceinline__ void kc_insert(uint64_t *table, uint32_t region_bits,
 	++n_overflow;
 }
 
+__device__ __forceinline__ void kc_insert_region(uint64_t *base, uint32_t rslot_bits, uint64_t tag, uint32_t &n_new,
+                                                 uint32_t &n_overflow)
+{
+	const uint64_t pos = kc_home(tag, rslot_bits);
+	kc_insert_from(base, rslot_bits, tag, pos, ld_slot(base + pos), n_new, n_overflow);
+}
+
+__device__ __forceinline__ void kc_insert(uint64_t *table, uint32_t region_bits, uint32_t rslot_bits, uint64_t q,
+                                          uint32_t &n_new, uint32_t &n_overflow)
+{
+	const uint64_t region = q & ((1ull << region_bits) - 1ull);
+	kc_insert_region(table + (region << rslot_bits), rslot_bits, q >> region_bits, n_new, n_overflow);
+}
+
 __device__ __forceinline__ void kc_owner(uint64_t h, uint32_t n_parts, int part_shift, uint32_t &owner, uint64_t &q)
 {
 	if (part_shift >= 0) {
@@ -91,18 +118,29 @@ __device__ __forceinline__ void kc_owner(uint64_t h, uint32_t n_parts, int part_
 	}
 }
 
-template <bool EXTRACT>
+__device__ __forceinline__ uint64_t kc_unsplit(uint64_t q, uint32_t owner, uint32_t n_parts, int part_shift)
+{
+	return part_shift >= 0 ? (q << part_shift) | owner : q * n_parts + owner;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, const int part_shift)
 {
-	const uint64_t n_chunks = a.n_bytes >> 4;
-	const uint64_t c = (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x;
-	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_dropped = 0;
-	if (c < n_chunks) {
+	const uint64_t c = a.first_chunk + (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x;
+	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_dropped = 0, n_direct = 0;
+	const bool live = c < a.end_chunk;
+	__shared__ uint32_t s_cnt[2][KC_MAX_PARTS];
+	__shared__ unsigned long long s_base[2][KC_MAX_PARTS];
+	if (MODE == KC_PUSH) {
+		if (threadIdx.x < KC_MAX_PARTS) s_cnt[0][threadIdx.x] = 0;
+		__syncthreads();
+	}
+	if (live || MODE == KC_PUSH) { /* KC_PUSH: the whole CTA walks in step (barriers below) */
 		const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
 		const uint4 sep = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
-		const uint4 w0 = c >= 2 ? __ldg(chunks + c - 2) : sep;
-		const uint4 w1 = c >= 1 ? __ldg(chunks + c - 1) : sep;
-		uint4 own = __ldg(chunks + c);
+		const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
+		const uint4 w1 = live && c >= 1 ? __ldg(chunks + c - 1) : sep;
+		uint4 own = live ? __ldg(chunks + c) : sep;
 		const int k = a.k;
 		const uint64_t mask = (1ull << 2 * k) - 1ull;
 		const int top = 2 * (k - 1);
@@ -121,36 +159,97 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 			rv = rv >> 2 | (3ull - code) << top;
 			run = kc_is_base(b) ? run + 1 : 0;
 		}
+		/* four positions at a time: their memory operations are independent, so a thread has
+		 * four round trips to L2 in flight instead of one (the kernel waits for memory, not for
+		 * issue slots: profiles/r1_kc_part_v1) */
 #pragma unroll 1
-		for (int i = 0; i < 16; ++i) {
-			const uint32_t b = own.x & 0xFFu;
-			own.x = __funnelshift_r(own.x, own.y, 8);
-			own.y = __funnelshift_r(own.y, own.z, 8);
-			own.z = __funnelshift_r(own.z, own.w, 8);
-			own.w >>= 8;
-			uint64_t code = (b >> 1) & 3u;
-			code ^= code >> 1;
-			fw = (fw << 2 | code) & mask;
-			rv = rv >> 2 | (3ull - code) << top;
-			run = kc_is_base(b) ? run + 1 : 0;
-			if (run < k) continue;
-			++n_kmers;
-			const uint64_t h = kc_hash64(fw < rv ? fw : rv, mask);
-			uint32_t owner;
-			uint64_t q;
-			kc_owner(h, a.n_parts, part_shift, owner, q);
-			if (!EXTRACT) {
-				kc_insert(a.tables[owner], a.region_bits, a.rslot_bits, q, n_new, n_overflow);
+		for (int g = 0; g < 4; ++g) {
+			uint32_t word = own.x;
+			own.x = own.y, own.y = own.z, own.z = own.w;
+			uint64_t q[4];
+			uint32_t owner[4];
+			bool ok[4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint32_t b = word & 0xFFu;
+				word >>= 8;
+				uint64_t code = (b >> 1) & 3u;
+				code ^= code >> 1;
+				fw = (fw << 2 | code) & mask;
+				rv = rv >> 2 | (3ull - code) << top;
+				run = kc_is_base(b) ? run + 1 : 0;
+				ok[j] = run >= k;
+				kc_owner(kc_hash64(fw < rv ? fw : rv, mask), a.n_parts, part_shift, owner[j], q[j]);
+				n_kmers += ok[j];
+			}
+			if (MODE == KC_PARTITION) {
+				/* file q under its region in the owner's allocation; the cursor runs on past the
+				 * capacity so that the flush knows the list was full, the excess goes to the table */
+				uint64_t at[4];
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const uint64_t region = q[j] & ((1ull << a.region_bits) - 1ull);
+					unsigned long long *cursor =
+					    kc_cursors_of(a.tables[owner[j]], a.n_slots, a.list_cap, a.region_bits) + region * KC_CURSOR_STRIDE;
+					if (a.exp & 1) at[j] = (c * 16 + g * 4 + j) % a.list_cap;
+					else at[j] = ok[j] ? atomicAdd(cursor, 1ull) : 0ull;
+				}
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					if (!ok[j]) continue;
+					uint64_t *base = a.tables[owner[j]];
+					const uint64_t region = q[j] & ((1ull << a.region_bits) - 1ull);
+					if (at[j] < a.list_cap) {
+						if (!(a.exp & 2)) kc_lists_of(base, a.n_slots)[region * a.list_cap + at[j]] = q[j];
+					} else {
+						++n_direct;
+						kc_insert(base, a.region_bits, a.rslot_bits, q[j], n_new, n_overflow);
+					}
+				}
+			} else if (MODE == KC_PUSH) {
+				const int buf = g & 1;
+				uint32_t idx[4];
+#pragma unroll
+				for (int j = 0; j < 4; ++j) idx[j] = ok[j] ? atomicAdd(&s_cnt[buf][owner[j]], 1u) : 0u;
+				__syncthreads();
+				if (threadIdx.x < a.n_parts) {
+					const uint32_t n = s_cnt[buf][threadIdx.x];
+					if (n) s_base[buf][threadIdx.x] =
+						atomicAdd(kc_cursors_of(a.tables[threadIdx.x], a.n_slots, a.list_cap, a.region_bits), (unsigned long long)n);
+					s_cnt[buf ^ 1][threadIdx.x] = 0;
+				}
+				__syncthreads();
+				const uint64_t cap = a.list_cap << a.region_bits;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					if (!ok[j]) continue;
+					uint64_t *base = a.tables[owner[j]];
+					const uint64_t pos = s_base[buf][owner[j]] + idx[j];
+					if (pos < cap) {
+						kc_lists_of(base, a.n_slots)[pos] = q[j];
+					} else { /* inbox full: straight to the owner's table */
+						++n_direct;
+						kc_insert(base, a.region_bits, a.rslot_bits, q[j], n_new, n_overflow);
+					}
+				}
+			} else if (MODE == KC_DIRECT) {
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					if (ok[j]) kc_insert(a.tables[owner[j]], a.region_bits, a.rslot_bits, q[j], n_new, n_overflow);
 			} else {
-				/* one atomic per owner and warp: the lanes that have a k-mer for the same owner
-				 * reserve consecutive entries of its list */
-				cg::coalesced_group active = cg::coalesced_threads();
-				cg::coalesced_group same = cg::labeled_partition(active, owner);
-				uint32_t at = 0;
-				if (same.thread_rank() == 0) at = atomicAdd(a.part_counts + owner, same.size());
-				at = same.shfl(at, 0) + same.thread_rank();
-				if (at < a.cap_per_part) a.out_keys[(uint64_t)owner * a.cap_per_part + at] = h;
-				else ++n_dropped;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					if (!ok[j]) continue;
+					/* one atomic per owner and warp: the lanes that have a k-mer for the same owner
+					 * reserve consecutive entries of its list */
+					cg::coalesced_group active = cg::coalesced_threads();
+					cg::coalesced_group same = cg::labeled_partition(active, owner[j]);
+					uint32_t at = 0;
+					if (same.thread_rank() == 0) at = atomicAdd(a.part_counts + owner[j], same.size());
+					at = same.shfl(at, 0) + same.thread_rank();
+					if (at < a.cap_per_part) a.out_keys[(uint64_t)owner[j] * a.cap_per_part + at] = kc_unsplit(q[j], owner[j], a.n_parts, part_shift);
+					else ++n_dropped;
+				}
 			}
 		}
 	}
@@ -159,12 +258,48 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
 		n_overflow += __shfl_xor_sync(KC_FULL, n_overflow, o);
 		n_dropped += __shfl_xor_sync(KC_FULL, n_dropped, o);
+		n_direct += __shfl_xor_sync(KC_FULL, n_direct, o);
 	}
 	if ((threadIdx.x & 31) == 0) {
 		if (n_kmers) atomicAdd(a.stats + KC_ST_KMERS, (unsigned long long)n_kmers);
 		if (n_new) atomicAdd(a.stats + KC_ST_NEW, (unsigned long long)n_new);
 		if (n_overflow) atomicAdd(a.stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
 		if (n_dropped) atomicAdd(a.stats + KC_ST_DROPPED, (unsigned long long)n_dropped);
+		if (n_direct) atomicAdd(a.stats + KC_ST_DIRECT, (unsigned long long)n_direct);
+	}
+}
+
+/* The region lists into the table.  CTA b takes tile b % tiles_per_region of region
+ * b / tiles_per_region: CTAs are dispatched in order, so the resident ones work on two or
+ * three neighbouring regions and their slices (<= 16 MiB each) stay in L2 while they fill. */
+__global__ void __launch_bounds__(KC_THREADS) kc_flush_kernel(uint64_t *base, const uint64_t n_slots, const uint64_t list_cap,
+                                                               const uint32_t region_bits, const uint32_t rslot_bits,
+                                                               const uint32_t tiles_per_region, const uint32_t tile_entries,
+                                                               unsigned long long *stats)
+{
+	const uint32_t region = blockIdx.x / tiles_per_region, tile = blockIdx.x % tiles_per_region;
+	const uint64_t filled = kc_cursors_of(base, n_slots, list_cap, region_bits)[(uint64_t)region * KC_CURSOR_STRIDE];
+	const uint64_t n = filled < list_cap ? filled : list_cap;
+	const uint64_t lo = (uint64_t)tile * tile_entries;
+	if (lo >= n) return;
+	const uint64_t hi = lo + tile_entries < n ? lo + tile_entries : n;
+	const uint64_t *list = kc_lists_of(base, n_slots) + (uint64_t)region * list_cap;
+	uint64_t *slice = base + ((uint64_t)region << rslot_bits);
+	uint32_t n_new = 0, n_overflow = 0;
+	/* one entry per thread and step: more entries in flight per thread (four home slots
+	 * requested at once) measured slower -- the compare-and-swap chain, not the first load, is
+	 * what a thread waits for, and the registers halve the resident threads */
+	for (uint64_t i = lo + threadIdx.x; i < hi; i += KC_THREADS) {
+		const uint64_t q = __ldcs(reinterpret_cast<const unsigned long long *>(list + i));
+		kc_insert_region(slice, rslot_bits, q >> region_bits, n_new, n_overflow);
+	}
+	for (int o = 16; o; o >>= 1) {
+		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
+		n_overflow += __shfl_xor_sync(KC_FULL, n_overflow, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (n_new) atomicAdd(stats + KC_ST_NEW, (unsigned long long)n_new);
+		if (n_overflow) atomicAdd(stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
 	}
 }
 
@@ -172,12 +307,18 @@ __global__ void __launch_bounds__(KC_THREADS) kc_insert_kernel(const InsertArgs 
 {
 	uint32_t n_new = 0, n_overflow = 0, n_kmers = 0;
 	const uint64_t stride = (uint64_t)gridDim.x * KC_THREADS;
-	for (uint64_t i = (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x; i < a.n; i += stride) {
-		const uint64_t h = __ldg(a.hashed + i);
-		uint32_t owner;
-		uint64_t q;
-		kc_owner(h, a.n_parts, part_shift, owner, q);
-		++n_kmers;
+	uint64_t n = a.n;
+	if (a.n_ptr) { /* an inbox: as many as its cursor says, at most its capacity */
+		const uint64_t filled = *a.n_ptr;
+		n = filled < n ? filled : n;
+	}
+	for (uint64_t i = (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x; i < n; i += stride) {
+		uint64_t q = __ldcs(reinterpret_cast<const unsigned long long *>(a.hashed + i));
+		if (!a.split) {
+			uint32_t owner;
+			kc_owner(q, a.n_parts, part_shift, owner, q);
+			++n_kmers;
+		}
 		kc_insert(a.table, a.region_bits, a.rslot_bits, q, n_new, n_overflow);
 	}
 	for (int o = 16; o; o >>= 1) {
@@ -246,23 +387,30 @@ int shift_of(uint32_t n_parts)
 
 } // namespace
 
-cudaError_t launch_count(const CountArgs &a, cudaStream_t stream)
+template <int MODE>
+static cudaError_t launch_scan(const CountArgs &a, cudaStream_t stream)
 {
-	if (a.n_bytes == 0) return cudaSuccess;
-	const uint64_t chunks = a.n_bytes >> 4;
-	const uint64_t blocks = (chunks + KC_THREADS - 1) / KC_THREADS;
+	if (a.end_chunk <= a.first_chunk) return cudaSuccess;
+	const uint64_t blocks = (a.end_chunk - a.first_chunk + KC_THREADS - 1) / KC_THREADS;
 	if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-	kc_scan_kernel<false><<<(unsigned)blocks, KC_THREADS, 0, stream>>>(a, shift_of(a.n_parts));
+	kc_scan_kernel<MODE><<<(unsigned)blocks, KC_THREADS, 0, stream>>>(a, shift_of(a.n_parts));
 	return cudaGetLastError();
 }
 
-cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream)
+cudaError_t launch_count(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_DIRECT>(a, stream); }
+cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_PARTITION>(a, stream); }
+cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_EXTRACT>(a, stream); }
+cudaError_t launch_push(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_PUSH>(a, stream); }
+
+cudaError_t launch_flush(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits, uint32_t rslot_bits,
+                         unsigned long long *stats, cudaStream_t stream)
 {
-	if (a.n_bytes == 0) return cudaSuccess;
-	const uint64_t chunks = a.n_bytes >> 4;
-	const uint64_t blocks = (chunks + KC_THREADS - 1) / KC_THREADS;
+	if (!list_cap) return cudaSuccess;
+	static const uint32_t tile = getenv("KCGPU_FLUSH_TILE") ? (uint32_t)atoi(getenv("KCGPU_FLUSH_TILE")) : (uint32_t)KC_FLUSH_TILE; /* tuning knob */
+	const uint64_t tiles = (list_cap + tile - 1) / tile;
+	const uint64_t blocks = tiles << region_bits;
 	if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-	kc_scan_kernel<true><<<(unsigned)blocks, KC_THREADS, 0, stream>>>(a, shift_of(a.n_parts));
+	kc_flush_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(base, n_slots, list_cap, region_bits, rslot_bits, (uint32_t)tiles, tile, stats);
 	return cudaGetLastError();
 }
 

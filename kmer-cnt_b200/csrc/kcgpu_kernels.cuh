@@ -9,6 +9,19 @@
  * "key << KC_BITS | count" word (kc-c4.c:11-15,124-125).  0 is a free slot (a used slot has a
  * count of at least 1).  Linear probing inside the region from a multiplicative hash of the
  * tag.  Nothing is lost: (owner, region, tag) give h back, and hash64 is invertible.
+ *
+ * Region lists: like the reference (count_seq_buf files k-mers per partition, worker_for then
+ * fills one partition's table at a time, kc-c4.c:64-72,116-128), the scan does not touch the
+ * table: it appends q to the list of its region, and a second kernel walks the lists region by
+ * region, so that the slice of the table it fills (at most 16 MiB) stays in L2 while it is
+ * filled.  Random 8-byte updates of a table far larger than L2 cost ~130 bytes of DRAM traffic
+ * each (profiles/r1_kc_scan_v0); through the lists a k-mer costs 16 bytes of streaming plus its
+ * share of one pass over the table.
+ *
+ * One allocation per owner, so that one pointer (one CUDA IPC handle) names it all:
+ *   [ table: n_slots x 8 B ][ lists: n_regions x list_cap x 8 B ][ cursors: n_regions x 256 B, one 64-bit count each ]
+ * With several owners the list area is one list, the owner's inbox (cursor 0): whoever finds a
+ * k-mer appends it there in sector-sized runs, and the owner inserts what arrived.
  */
 #ifndef KCGPU_KERNELS_CUH
 #define KCGPU_KERNELS_CUH
@@ -27,10 +40,13 @@ namespace kcgpu {
 enum { KC_COUNT_BITS = 10, KC_COUNT_MAX = 1023 }; /* kc-c4.c:11-12 */
 enum { KC_MAX_PARTS = 16 };
 enum { KC_MAX_PROBES = 8192 }; /* a region this crowded is reported as overflow, not walked for ever */
+enum { KC_REGION_SLOT_BITS = 21 }; /* slots per region at most: 16 MiB of table, a few of them fit L2 */
+enum { KC_CURSOR_STRIDE = 32 };    /* 64-bit words between two regions' cursors: one 256-byte line each */
+enum { KC_FLUSH_TILE = 2048 };     /* list entries per CTA of the list-insert kernel */
 enum { KC_TAG_BITS = 64 - KC_COUNT_BITS };
 
 /* per-context counters the kernels add to (unsigned long long each) */
-enum { KC_ST_KMERS = 0, KC_ST_NEW = 1, KC_ST_OVERFLOW = 2, KC_ST_DROPPED = 3, KC_ST_N = 4 };
+enum { KC_ST_KMERS = 0, KC_ST_NEW = 1, KC_ST_OVERFLOW = 2, KC_ST_DROPPED = 3, KC_ST_DIRECT = 4, KC_ST_N = 8 };
 
 /* regions needed so that the tag of a 2k-bit hash fits beside the count */
 KC_HD uint32_t kc_region_bits(int k) { return 2 * k > KC_TAG_BITS ? (uint32_t)(2 * k - KC_TAG_BITS) : 0u; }
@@ -50,7 +66,10 @@ KC_HD uint64_t kc_hash64(uint64_t key, uint64_t mask) /* kc-c4.c:40-50 */
 struct CountArgs {
 	const uint8_t *bytes; /* stream: reads separated by '\n', 16-byte aligned */
 	uint64_t n_bytes;     /* multiple of 16                                    */
+	uint64_t first_chunk, end_chunk; /* the 16-byte chunks this launch owns (it reads up to two before them) */
+	uint64_t n_slots, list_cap;      /* geometry of every owner's allocation; list_cap 0 = no lists */
 	int k;
+	int exp;              /* development: 1 = no cursor atomics, 2 = no list stores, 3 = neither */
 	uint32_t n_parts;     /* owners of the hash space                          */
 	uint32_t region_bits, rslot_bits;
 	uint64_t *tables[KC_MAX_PARTS]; /* table of every owner (peer memory over NVLink for the others) */
@@ -64,6 +83,8 @@ struct CountArgs {
 struct InsertArgs {
 	const uint64_t *hashed; /* hash64 values owned by this table */
 	uint64_t n;
+	const unsigned long long *n_ptr; /* if set: the count is min(*n_ptr, n), read on the device */
+	int split;              /* the values are already hash div n_parts (an inbox), not hashes */
 	uint32_t n_parts;
 	uint32_t region_bits, rslot_bits;
 	uint64_t *table;
@@ -71,11 +92,26 @@ struct InsertArgs {
 };
 
 /* asynchronous launches on `stream` */
-cudaError_t launch_count(const CountArgs &a, cudaStream_t stream);   /* fused extract + insert */
+cudaError_t launch_count(const CountArgs &a, cudaStream_t stream);   /* extract + insert straight into the tables */
+cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream); /* extract + append to the region lists (one owner) */
+cudaError_t launch_push(const CountArgs &a, cudaStream_t stream);      /* extract + append to the owners' inboxes (several owners) */
+/* insert what the region lists of this allocation hold into its table; the cursors are left as they are */
+cudaError_t launch_flush(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits, uint32_t rslot_bits,
+                         unsigned long long *stats, cudaStream_t stream);
 cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream); /* extract into per-owner lists */
 cudaError_t launch_insert(const InsertArgs &a, cudaStream_t stream);
 cudaError_t launch_histogram(const uint64_t *table, uint64_t n_slots, unsigned long long *hist256, int n_sm,
                              cudaStream_t stream);
+
+KC_HD uint64_t *kc_lists_of(uint64_t *base, uint64_t n_slots) { return base + n_slots; }
+KC_HD unsigned long long *kc_cursors_of(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits)
+{
+	return reinterpret_cast<unsigned long long *>(base + n_slots + (list_cap << region_bits));
+}
+KC_HD uint64_t kc_alloc_bytes(uint64_t n_slots, uint64_t list_cap, uint32_t region_bits)
+{
+	return (n_slots + (list_cap << region_bits)) * 8 + ((uint64_t)KC_CURSOR_STRIDE * 8 << region_bits);
+}
 
 } // namespace kcgpu
 #endif

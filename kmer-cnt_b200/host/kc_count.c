@@ -82,13 +82,14 @@ int main(int argc, char *argv[])
 		n_dev = atoi(getenv("KCGPU_DEVICES"));
 	if (n_dev > KCGPU_MAX_OWNERS) n_dev = KCGPU_MAX_OWNERS;
 
+	const int direct = getenv("KCGPU_DIRECT") && atoi(getenv("KCGPU_DIRECT")); /* no region lists (development) */
 	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn, n_dev);
 	for (int attempt = 0;; ++attempt) {
 		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
 		uint64_t hist[256], part[256], overflow = 0;
 		kcgpu_stats st;
 		for (i = 0; i < n_dev; ++i)
-			if (kcgpu_create(&ctx[i], k, slots, 0, i) != VAFGPU_OK) {
+			if (kcgpu_create(&ctx[i], k, slots, direct ? KCGPU_NO_LISTS : 0, 0, i) != VAFGPU_OK) {
 				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
 				return 1;
 			}

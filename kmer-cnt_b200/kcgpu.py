@@ -22,11 +22,12 @@ from vafgpu import VafGpuError
 
 MAX_OWNERS = 16
 IPC_HANDLE_BYTES = 64
+NO_LISTS = (1 << 64) - 1  # list_slots: every k-mer straight to the table
 
 EXPORTS = (
     "kcgpu_device_count", "kcgpu_create", "kcgpu_add_read", "kcgpu_count_device", "kcgpu_extract_device",
     "kcgpu_insert_device", "kcgpu_table", "kcgpu_ipc_export", "kcgpu_ipc_open", "kcgpu_set_owners",
-    "kcgpu_link", "kcgpu_sync", "kcgpu_histogram", "kcgpu_reset", "kcgpu_destroy", "kcgpu_strerror",
+    "kcgpu_link", "kcgpu_sync", "kcgpu_flush", "kcgpu_histogram", "kcgpu_reset", "kcgpu_destroy", "kcgpu_strerror",
     "kcgpu_hash64",
 )
 
@@ -34,8 +35,9 @@ EXPORTS = (
 class Stats(C.Structure):
     _fields_ = [
         ("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("n_blocks", C.c_uint64), ("n_kmers", C.c_uint64),
-        ("n_distinct", C.c_uint64), ("n_overflow", C.c_uint64), ("n_dropped", C.c_uint64),
-        ("table_slots", C.c_uint64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
+        ("n_distinct", C.c_uint64), ("n_overflow", C.c_uint64), ("n_dropped", C.c_uint64), ("n_direct", C.c_uint64),
+        ("n_flushes", C.c_uint64), ("table_slots", C.c_uint64), ("list_slots", C.c_uint64), ("flush_bytes", C.c_uint64),
+        ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -53,7 +55,7 @@ def load_library() -> C.CDLL:
         return lib
     vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
     lib.kcgpu_device_count.restype = C.c_int
-    lib.kcgpu_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint64, C.c_size_t, C.c_int]
+    lib.kcgpu_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int]
     lib.kcgpu_add_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.kcgpu_count_device.argtypes = [vp, vp, C.c_size_t, vp]
     lib.kcgpu_extract_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, vp, vp]
@@ -64,6 +66,7 @@ def load_library() -> C.CDLL:
     lib.kcgpu_set_owners.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
     lib.kcgpu_link.argtypes = [C.POINTER(vp), C.c_int]
     lib.kcgpu_sync.argtypes = [vp]
+    lib.kcgpu_flush.argtypes = [vp]
     lib.kcgpu_histogram.argtypes = [vp, u64p, C.POINTER(Stats)]
     lib.kcgpu_reset.argtypes = [vp]
     for name in EXPORTS:
@@ -94,12 +97,12 @@ def format_histogram(hist: Sequence[int]) -> str:
 
 
 class Counter:
-    """One k-mer table on one device."""
+    """One k-mer table with its region lists on one device."""
 
-    def __init__(self, k: int, table_slots: int = 0, block_bytes: int = 0, device: int = 0):
+    def __init__(self, k: int, table_slots: int = 0, block_bytes: int = 0, device: int = 0, list_slots: int = 0):
         self._lib = load_library()
         self._ctx = C.c_void_p()
-        rc = self._lib.kcgpu_create(C.byref(self._ctx), k, table_slots, block_bytes, device)
+        rc = self._lib.kcgpu_create(C.byref(self._ctx), k, table_slots, list_slots, block_bytes, device)
         if rc:
             raise VafGpuError(rc, self._lib.kcgpu_strerror(None).decode())
         self.k = k
@@ -144,6 +147,9 @@ class Counter:
 
     def sync(self) -> None:
         self._check(self._lib.kcgpu_sync(self._ctx))
+
+    def flush(self) -> None:
+        self._check(self._lib.kcgpu_flush(self._ctx))
 
     def histogram(self) -> Tuple[np.ndarray, dict]:
         hist = np.zeros(256, dtype=np.uint64)

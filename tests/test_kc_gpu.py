@@ -52,6 +52,40 @@ def test_add_read_matches_oracle_over_k(kco, lib, k):
     assert st["n_blocks"] > 3
 
 
+@pytest.mark.parametrize("list_slots", [kcgpu.NO_LISTS, 1 << 10, 1 << 16])
+def test_list_sizes_do_not_change_the_result(kco, lib, list_slots):
+    """no lists at all, lists that flush every few kilobytes, lists that flush a few times"""
+    for k in (9, 31):
+        reads = reads_case(300 + k, jitter=50, repeat=8)
+        want, n_inst, n_dist = kco.count_reads(reads, k)
+        with kcgpu.Counter(k, 1 << 21, block_bytes=1 << 17, list_slots=list_slots) as c:
+            for r in reads:
+                c.add_read(r)
+            got, st = c.histogram()
+        assert np.array_equal(got, want) and st["n_kmers"] == n_inst and st["n_distinct"] == n_dist
+        if list_slots == kcgpu.NO_LISTS:
+            assert st["n_flushes"] == 0 and st["list_slots"] == 0
+        else:
+            assert st["n_flushes"] >= (2 if list_slots == 1 << 16 else 5)
+
+
+def test_full_lists_fall_back_to_the_table(kco, torch_cuda):
+    """a context whose owners the caller named never flushes by itself: what does not fit its
+    lists goes straight to the table, nothing is lost"""
+    torch = torch_cuda
+    k = 31
+    reads = reads_case(17, repeat=4)
+    d = torch.from_numpy(util.pack_stream_strict(reads, k)).cuda()
+    want, n_inst, n_dist = kco.count_reads(reads, k)
+    with kcgpu.Counter(k, 1 << 21, list_slots=1 << 15) as c:
+        c.set_owners(0, [None])
+        c.count_device(d.data_ptr(), d.numel())
+        got, st = c.histogram()
+    assert np.array_equal(got, want) and st["n_kmers"] == n_inst and st["n_distinct"] == n_dist
+    assert st["n_direct"] > n_inst // 2
+    assert st["n_flushes"] <= 2  # the one set_owners does, the one histogram does: none in between
+
+
 def test_saturating_count(kco, lib):
     """one k-mer thousands of times, from every lane at once: 1023 is the ceiling (kc-c4.c:125)"""
     reads = [b"A" * 5000, b"T" * 3000, b"ACGT" * 600]
@@ -278,7 +312,7 @@ def test_cli_prints_the_reference_histogram(lib, name):
         out = subprocess.run([KC_CLI, "-k", str(k), "-t", "2", fq], check=True, capture_output=True).stdout.decode()
         assert out == open(os.path.join(GOLDEN_KC, f"{name}.k{k}.hist")).read(), (name, k)
     # a table that starts too small is grown and the file counted again, never printed short
-    env = dict(os.environ, KCGPU_TABLE_SLOTS="65536")
+    env = dict(os.environ, KCGPU_TABLE_SLOTS="4096")
     r = subprocess.run([KC_CLI, "-k", "31", fq], check=True, capture_output=True, env=env)
     assert r.stdout.decode() == open(os.path.join(GOLDEN_KC, f"{name}.k31.hist")).read()
     assert b"counting again" in r.stderr

@@ -9,10 +9,15 @@ them), drawn from both strands of one random genome of --genome bases with 1 % s
 and 0.5 % N, generated on the GPU as the stream the engine consumes.  One step = empty tables,
 count every k-mer of the resident stream into the hash-partitioned tables, histogram.
 
-  fused    kcgpu_count_device after kcgpu_set_owners: the counting kernel adds every k-mer to
-           its owner's table itself, over NVLink peer memory (CUDA IPC between the ranks)
+  fused    kcgpu_count_device after kcgpu_set_owners: the counting kernel files every k-mer in
+           its owner's region lists itself, over NVLink peer memory (CUDA IPC between the ranks);
+           kcgpu_flush empties the lists into the tables, between barriers
+  direct   the same without region lists (KCGPU_NO_LISTS): every k-mer is a compare-and-swap on
+           its owner's table, wherever that is
   staged   kcgpu_extract_device -> torch.distributed.all_to_all_single (NCCL) -> kcgpu_insert_device,
            in chunks of the stream: the NCCL baseline the fused form is compared with
+Timing: host clock around barrier + device synchronize on both sides (a step takes 0.1 s and
+more; the flushes inside it run on the library's own stream).
 
 Prints one JSON line (rank 0).  The CPU baseline is the UNMODIFIED reference kc-c4 (oracle/_ref)
 on a bounded sample of the same reads; the same sample is also counted on the GPU through the
@@ -45,7 +50,8 @@ def main():
     ap.add_argument("--k", type=int, default=31)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--form", default="both", choices=["fused", "staged", "both"])
+    ap.add_argument("--form", default="fused", help="comma-separated: fused, direct, staged")
+    ap.add_argument("--list-slots", type=int, default=0, help="per GPU; 0 = table_slots / 2")
     ap.add_argument("--table-slots", type=int, default=0, help="per GPU; 0 = from the expected number of distinct k-mers")
     ap.add_argument("--sample", type=int, default=1_000_000, help="reads of the CPU baseline / parity sample")
     ap.add_argument("--chunk-mb", type=int, default=1024, help="stream bytes per extract/exchange/insert round (staged)")
@@ -92,22 +98,37 @@ def main():
         slots = 1 << 20
         while slots < 1.4 * min(est, exp_kmers) / world:
             slots *= 2
-    ctr = kcgpu.Counter(k, slots, device=local)
-    my_table, slots = ctr.table()
-    log(f"rank {rank}: table of {slots} slots ({slots * 8 / 1e9:.1f} GB)")
-
-    if world > 1:
-        handles = [None] * world
-        dist.all_gather_object(handles, ctr.ipc_export())
-        tables = [None if r == rank else ctr.ipc_open(handles[r]) for r in range(world)]
-        ctr.set_owners(rank, tables)
-        own_only = [my_table]  # staged form: a context that only knows its own table
-    ts = torch.cuda.current_stream().cuda_stream
+    forms = args.form.split(",")
+    state = {}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+
+    def open_counter(form):
+        """a fresh context per form: with region lists (fused), without (direct, staged)"""
+        if "ctr" in state:
+            barrier()  # nobody is still filing with a peer that is about to go away
+            state["ctr"].close()
+            barrier()
+        ctr = kcgpu.Counter(k, slots, device=local, list_slots=args.list_slots if form == "fused" else kcgpu.NO_LISTS)
+        state["ctr"] = ctr
+        _, got_slots = ctr.table()
+        _, st = ctr.histogram()
+        log(f"rank {rank} [{form}]: table of {got_slots} slots ({got_slots * 8 / 1e9:.1f} GB), lists of {st['list_slots']} "
+            f"({st['list_slots'] * 8 / 1e9:.1f} GB), a flush every {st['flush_bytes'] / 1e9:.2f} GB of stream")
+        if world > 1 and form != "staged":
+            handles = [None] * world
+            dist.all_gather_object(handles, ctr.ipc_export())
+            ctr.set_owners(rank, [None if r == rank else ctr.ipc_open(handles[r]) for r in range(world)])
+        return ctr, got_slots, st["flush_bytes"]
+    # a stream of our own: the legacy default stream has handle 0, which the C ABI reads as "the context's stream"
+    work = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work)
+    ts = work.cuda_stream
+    assert ts != 0
 
     def total_hist(h):
         if world == 1:
@@ -121,15 +142,27 @@ def main():
     chunk -= chunk % (rec * 16)
     kpc = chunk // rec * (READ_LEN - k + 1)  # k-mers per chunk at most
     cap = int(kpc / world * 1.1) + 4096
-    if args.form in ("staged", "both"):
+    if "staged" in forms:
         keys = torch.empty(world * cap, dtype=torch.int64, device=dev)
         recv = torch.empty(int(world * cap), dtype=torch.int64, device=dev)
         pcounts = torch.zeros(world, dtype=torch.int32, device=dev)
 
     def step_fused():
-        ctr.count_device(stream.data_ptr(), stream.numel(), ts)
+        ctr, flush_bytes = state["ctr"], state["flush_bytes"]
+        if world == 1 or not flush_bytes:  # one process: the library flushes when it is due
+            ctr.count_device(stream.data_ptr(), stream.numel(), ts)
+            ctr.flush()
+            return
+        batch = flush_bytes - flush_bytes % (rec * 16)  # whole reads, 16-byte aligned
+        for lo in range(0, stream.numel(), batch):
+            ctr.count_device(stream.data_ptr() + lo, min(batch, stream.numel() - lo), ts)
+            ctr.sync()
+            dist.barrier()  # everybody has filed its k-mers
+            ctr.flush()
+            dist.barrier()  # every list is empty before anybody files again
 
     def step_staged():
+        ctr = state["ctr"]
         for lo in range(0, stream.numel(), chunk):
             n = min(chunk, stream.numel() - lo)
             pcounts.zero_()
@@ -150,49 +183,48 @@ def main():
 
     results = {}
     hists = {}
-    forms = ["fused", "staged"] if args.form == "both" else [args.form]
     for form in forms:
-        fn = step_fused if form == "fused" else step_staged
-        if form == "staged" and world > 1:
-            ctr.set_owners(0, own_only)  # n_parts of the table's own kernels is irrelevant for extract/insert
-        times, count_ms = [], []
+        ctr, slots, state["flush_bytes"] = open_counter(form)
+        fn = step_staged if form == "staged" else step_fused
+        times, hist_ms = [], []
         for it in range(args.warmup + args.steps):
             ctr.reset()
             barrier()
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
+            t1 = time.perf_counter()
             fn()
-            e1.record()
             ctr.sync()
             barrier()
+            ms = (time.perf_counter() - t1) * 1e3
             t1 = time.perf_counter()
             h, st = ctr.histogram()
             h = total_hist(h)
             t_hist = time.perf_counter() - t1
-            ms = e0.elapsed_time(e1)
             if world > 1:
                 t = torch.tensor([ms], device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
             if it >= args.warmup:
                 times.append(ms)
-                count_ms.append(t_hist * 1e3)
+                hist_ms.append(t_hist * 1e3)
         hists[form] = h
-        stt = torch.tensor([st["n_kmers"], st["n_distinct"], st["n_overflow"], st["n_dropped"]], device=dev, dtype=torch.int64)
+        stt = torch.tensor([st["n_kmers"], st["n_distinct"], st["n_overflow"], st["n_dropped"], st["n_direct"]], device=dev, dtype=torch.int64)
         if world > 1:
             dist.all_reduce(stt)
         tot = stt.tolist()
+        if form == "staged":
+            tot[0] //= 2  # the extract and the insert kernel both count what they handle
         ms = sum(times) / len(times)
         results[form] = {
             "gbases_s": args.reads * READ_LEN / ms / 1e6, "gkmers_s": tot[0] / ms / 1e6, "ms_per_step": ms,
-            "hist_ms": sum(count_ms) / len(count_ms), "n_kmers": tot[0], "n_distinct_claims": tot[1],
-            "n_overflow": tot[2], "n_dropped": tot[3], "distinct": int(h.sum()),
+            "hist_ms": sum(hist_ms) / len(hist_ms), "n_kmers": tot[0], "n_distinct_claims": tot[1],
+            "n_overflow": tot[2], "n_dropped": tot[3], "n_direct": tot[4], "n_flushes": st["n_flushes"], "distinct": int(h.sum()),
+            "lib_kernel_ms": st["kernel_ms"],
         }
         log(f"{form}: {results[form]}")
-        if form == "staged" and world > 1:
-            ctr.set_owners(rank, tables)
-    if len(forms) == 2:
-        assert np.array_equal(hists["fused"], hists["staged"]), "fused and staged histograms differ"
+    for form in forms[1:]:
+        assert np.array_equal(hists[forms[0]], hists[form]), f"{forms[0]} and {form} histograms differ"
+    state["ctr"].close()
+    del state["ctr"]
 
     out = None
     if rank == 0:
@@ -213,7 +245,8 @@ def main():
             "config": {"workload": f"config 5: kc-c4 k={k} full k-mer counting, {args.reads} x {READ_LEN} bp synthetic reads in total "
                                    f"from a {args.genome}-base genome, hash-partitioned tables over {world} GPU(s)",
                        "k": k, "reads_total": args.reads, "table_slots_per_gpu": slots, "form": best,
-                       "l2": "table and stream are far larger than L2"},
+                       "l2": "table and stream are far larger than L2",
+                       "timing": "host clock around barrier + device synchronize"},
             "forms": results,
             "roofline": {"bound": "hbm", "achieved": alg / r["ms_per_step"] / 1e6, "peak": peak, "unit": "GB/s",
                          "frac": alg / r["ms_per_step"] / 1e6 / peak, "traffic": None,
@@ -259,7 +292,7 @@ def main():
                                "sample": f"{ns} reads x {READ_LEN} bp of this workload as FASTA, whole process wall clock, best of -t 1/4/{cores}"}
         out["parity"] = {"histogram_vs_reference_on_sample": "identical" if kcgpu.format_histogram(h2) == ref_out else "DIFFERENT",
                          "cli_vs_reference_on_sample": "identical" if cli_out == ref_out else "DIFFERENT",
-                         "fused_equals_staged": (len(forms) == 2) or None}
+                         "forms_agree": (len(forms) > 1) or None}
         out["this_repo_on_sample"] = {"add_read_python_loop_gbases_s": ns * READ_LEN / t_api / 1e9,
                                       "cli_whole_process_gbases_s": ns * READ_LEN / t_cli / 1e9}
         for f in os.listdir(tmp):
@@ -267,7 +300,6 @@ def main():
         os.rmdir(tmp)
     if rank == 0:
         print(json.dumps(out), flush=True)
-    ctr.close()
     if world > 1:
         dist.destroy_process_group()
 

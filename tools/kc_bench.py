@@ -51,7 +51,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--form", default="fused", help="comma-separated: fused, direct, staged")
-    ap.add_argument("--list-slots", type=int, default=0, help="per GPU; 0 = table_slots / 2")
+    ap.add_argument("--list-slots", type=int, default=0, help="per GPU; 0 = as large as the memory beside stream and table allows, up to one flush for the whole stream")
     ap.add_argument("--table-slots", type=int, default=0, help="per GPU; 0 = from the expected number of distinct k-mers")
     ap.add_argument("--sample", type=int, default=1_000_000, help="reads of the CPU baseline / parity sample")
     ap.add_argument("--chunk-mb", type=int, default=1024, help="stream bytes per extract/exchange/insert round (staged)")
@@ -86,6 +86,7 @@ def main():
     del genome
     stream, n_bytes = vb.make_stream(torch, donor, args.genome, n_reads, 77 + rank, dev)
     del donor
+    torch.cuda.empty_cache()  # the lists are sized from what is free
     torch.cuda.synchronize()
     n_bases = n_reads * READ_LEN
     log(f"rank {rank}: {n_reads} reads ({stream.numel() / 1e9:.2f} GB) generated in {time.perf_counter() - t0:.1f} s")
@@ -113,7 +114,19 @@ def main():
             barrier()  # nobody is still filing with a peer that is about to go away
             state["ctr"].close()
             barrier()
-        ctr = kcgpu.Counter(k, slots, device=local, list_slots=args.list_slots if form == "fused" else kcgpu.NO_LISTS)
+        list_slots = kcgpu.NO_LISTS
+        if form == "fused":
+            list_slots = args.list_slots
+            if not list_slots:
+                # as few flushes as the memory left beside stream and table allows: every flush
+                # streams the whole table once, whatever the lists hold
+                free_b, _ = torch.cuda.mem_get_info()
+                room = int((free_b - slots * 8) * 0.85) // 8
+                for n_int in range(1, 65):
+                    list_slots = int(stream.numel() / n_int / 0.94) + (1 << 20)
+                    if list_slots <= room:
+                        break
+        ctr = kcgpu.Counter(k, slots, device=local, list_slots=list_slots)
         state["ctr"] = ctr
         _, got_slots = ctr.table()
         _, st = ctr.histogram()

@@ -80,6 +80,15 @@ int kcgpu_create(kcgpu_ctx **ctx, int k, uint64_t table_slots, uint64_t list_slo
 int kcgpu_add_read(kcgpu_ctx *ctx, const char *seq, size_t len);
 
 /*
+ * Count a stream the caller has already packed in HOST memory: reads separated by '\n', bytes
+ * other than A C G T U (either case) end a k-mer (no byte translation is done: hand parsed reads
+ * to kcgpu_add_read if they may hold the bytes 0..3).  Page-locked memory is copied to the
+ * device as it is, block by block, each copy overlapping the previous block's kernel; pageable
+ * memory goes through the pinned staging blocks.  Returns when everything is submitted.
+ */
+int kcgpu_submit_stream(kcgpu_ctx *ctx, const char *bytes, size_t n_bytes);
+
+/*
  * Count a stream that is already resident on the context's device: reads separated by '\n',
  * 16-byte aligned, n_bytes a multiple of 16; bytes other than A C G T U (either case) end a
  * k-mer; k-mers do not span calls.  Every k-mer is filed with its owner as named by

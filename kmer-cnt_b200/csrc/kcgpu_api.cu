@@ -429,6 +429,65 @@ int kcgpu_add_read(kcgpu_ctx *c, const char *seq, size_t len)
 	return VAFGPU_OK;
 }
 
+int kcgpu_submit_stream(kcgpu_ctx *c, const char *bytes, size_t n_bytes)
+{
+	if (!c || (!bytes && n_bytes)) return VAFGPU_EINVAL;
+	cudaPointerAttributes attr;
+	const bool pinned = cudaPointerGetAttributes(&attr, bytes) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError(); /* a plain malloc pointer is reported as an error by older drivers */
+	size_t at = 0;
+	while (at < n_bytes) {
+		int rc = kc_submit_current(c); /* close what kcgpu_add_read left open */
+		if (rc) return rc;
+		rc = kc_ensure_room(c, 1);
+		if (rc) return rc;
+		KcBlock *b = c->cur;
+		size_t n = n_bytes - at, advance;
+		bool add_nl = false;
+		if (n > c->block_bytes) {
+			/* cut after the last separator that fits; a read longer than a block is cut with a
+			 * k-1 overlap, as in kcgpu_add_read */
+			n = c->block_bytes;
+			const char *nl = (const char *)memrchr(bytes + at, '\n', n);
+			if (nl) {
+				n = (size_t)(nl - (bytes + at)) + 1;
+				advance = n;
+			} else {
+				n -= 1;
+				add_nl = true;
+				advance = n - (size_t)(c->k - 1);
+			}
+		} else {
+			advance = n;
+			add_nl = bytes[at + n - 1] != '\n';
+		}
+		if (!pinned) {
+			memcpy(b->h, bytes + at, n);
+			if (add_nl) b->h[n++] = '\n';
+			b->used = n;
+			at += advance;
+			continue; /* submitted at the top of the loop or after it */
+		}
+		/* zero-copy: H2D straight from the caller's buffer, separator and padding written on the device */
+		c->cur = nullptr;
+		const size_t n16 = (n + (add_nl ? 1 : 0) + 15) & ~(size_t)15;
+		rc = kc_make_room(c, n16);
+		if (rc) return rc;
+		KCU(c, cudaSetDevice(c->device));
+		KCU(c, cudaEventRecord(b->e0, b->stream));
+		KCU(c, cudaMemcpyAsync(b->d, bytes + at, n, cudaMemcpyHostToDevice, b->stream));
+		if (n16 > n) KCU(c, cudaMemsetAsync(b->d + n, '\n', n16 - n, b->stream));
+		KCU(c, cudaEventRecord(b->e1, b->stream));
+		KCU(c, kc_launch_scan(c, count_args(c, b->d, n16), b->stream));
+		KCU(c, cudaEventRecord(b->e2, b->stream));
+		b->in_flight = true;
+		c->pending_bytes += n16;
+		c->st.n_blocks++;
+		at += advance;
+	}
+	return kc_submit_current(c);
+}
+
 int kcgpu_count_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, void *stream)
 {
 	if (!c) return VAFGPU_EINVAL;

@@ -141,6 +141,27 @@ def test_device_stream_and_reset(kco, torch_cuda):
             c.count_device(d.data_ptr() + 1, d.numel() - 16)
 
 
+def test_host_stream_pinned_and_pageable(kco, torch_cuda):
+    """kcgpu_submit_stream: the caller's packed stream from page-locked memory (copied as it is)
+    and from pageable memory (through the staging blocks), cut into blocks at read boundaries"""
+    torch = torch_cuda
+    rng = np.random.default_rng(21)
+    reads = util.make_genome_reads(rng, 60000, 4000, jitter=70, lower_rate=0.05, n_rate=0.01)
+    reads += util.make_genome_reads(rng, 300000, 2, mean_len=200000)  # longer than a block: cut with overlap
+    for k in (17, 31):
+        want, n_inst, n_dist = kco.count_reads(reads, k)
+        buf = b"".join(r + b"\n" for r in reads if len(r) >= k)[:-1]  # no trailing separator: the engine adds it
+        for pinned in (True, False):
+            t = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+            if pinned:
+                t = t.pin_memory()
+            with kcgpu.Counter(k, 1 << 21, block_bytes=1 << 16) as c:
+                c.submit_stream(t.data_ptr(), t.numel())
+                got, st = c.histogram()
+            assert np.array_equal(got, want) and st["n_kmers"] == n_inst and st["n_distinct"] == n_dist, (k, pinned)
+            assert st["n_blocks"] > 10
+
+
 def test_full_table_is_reported_not_walked_forever(torch_cuda):
     torch = torch_cuda
     reads = reads_case(12, genome=200000, n=3000)

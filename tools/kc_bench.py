@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--form", default="fused", help="comma-separated: fused, direct, staged")
     ap.add_argument("--list-slots", type=int, default=0, help="per GPU; 0 = as large as the memory beside stream and table allows, up to one flush for the whole stream")
     ap.add_argument("--table-slots", type=int, default=0, help="per GPU; 0 = from the expected number of distinct k-mers")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sample", type=int, default=1_000_000, help="reads of the CPU baseline / parity sample")
     ap.add_argument("--chunk-mb", type=int, default=1024, help="stream bytes per extract/exchange/insert round (staged)")
     args = ap.parse_args()
@@ -126,7 +127,7 @@ def main():
                     list_slots = int(stream.numel() / n_int / 0.94) + (1 << 20)
                     if list_slots <= room:
                         break
-        ctr = kcgpu.Counter(k, slots, device=local, list_slots=list_slots)
+        ctr = kcgpu.Counter(k, slots, device=local, list_slots=list_slots, block_bytes=256 << 20)
         state["ctr"] = ctr
         _, got_slots = ctr.table()
         _, st = ctr.histogram()
@@ -174,6 +175,21 @@ def main():
             ctr.flush()
             dist.barrier()  # every list is empty before anybody files again
 
+    def step_e2e():
+        """the same from page-locked HOST memory: H2D copies inside the timed region"""
+        ctr, flush_bytes = state["ctr"], state["flush_bytes"]
+        if world == 1 or not flush_bytes:
+            ctr.submit_stream(host.data_ptr(), host.numel())
+            ctr.flush()
+            return
+        batch = flush_bytes - flush_bytes % (rec * 16)
+        for lo in range(0, host.numel(), batch):
+            ctr.submit_stream(host.data_ptr() + lo, min(batch, host.numel() - lo))
+            ctr.sync()
+            dist.barrier()
+            ctr.flush()
+            dist.barrier()
+
     def step_staged():
         ctr = state["ctr"]
         for lo in range(0, stream.numel(), chunk):
@@ -219,6 +235,32 @@ def main():
             if it >= args.warmup:
                 times.append(ms)
                 hist_ms.append(t_hist * 1e3)
+        e2e = None
+        if form == forms[0] and not args.no_e2e:
+            host = torch.empty(stream.numel(), dtype=torch.uint8, pin_memory=True)
+            host.copy_(stream)
+            torch.cuda.synchronize()
+            e2e_ms = []
+            for it in range(1 + args.steps):
+                ctr.reset()
+                barrier()
+                t1 = time.perf_counter()
+                step_e2e()
+                h_e, _ = ctr.histogram()  # the result comes back to the host inside the timed region
+                barrier()
+                ms_e = (time.perf_counter() - t1) * 1e3
+                if world > 1:
+                    t = torch.tensor([ms_e], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms_e = float(t.item())
+                if it:
+                    e2e_ms.append(ms_e)
+            assert np.array_equal(total_hist(h_e), h), "end-to-end histogram differs from the resident one"
+            ms_e = sum(e2e_ms) / len(e2e_ms)
+            e2e = {"value": args.reads * READ_LEN / ms_e / 1e6, "unit": "Gbases/s", "ms_per_step": ms_e,
+                   "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": 256 * 8,
+                   "sample": f"all {n_reads} reads per GPU from page-locked host memory through kcgpu_submit_stream + kcgpu_histogram"}
+            del host
         hists[form] = h
         stt = torch.tensor([st["n_kmers"], st["n_distinct"], st["n_overflow"], st["n_dropped"], st["n_direct"]], device=dev, dtype=torch.int64)
         if world > 1:
@@ -231,7 +273,7 @@ def main():
             "gbases_s": args.reads * READ_LEN / ms / 1e6, "gkmers_s": tot[0] / ms / 1e6, "ms_per_step": ms,
             "hist_ms": sum(hist_ms) / len(hist_ms), "n_kmers": tot[0], "n_distinct_claims": tot[1],
             "n_overflow": tot[2], "n_dropped": tot[3], "n_direct": tot[4], "n_flushes": st["n_flushes"], "distinct": int(h.sum()),
-            "lib_kernel_ms": st["kernel_ms"],
+            "lib_kernel_ms": st["kernel_ms"], "e2e": e2e,
         }
         log(f"{form}: {results[form]}")
     for form in forms[1:]:
@@ -260,7 +302,7 @@ def main():
                        "k": k, "reads_total": args.reads, "table_slots_per_gpu": slots, "form": best,
                        "l2": "table and stream are far larger than L2",
                        "timing": "host clock around barrier + device synchronize"},
-            "forms": results,
+            "e2e": results[forms[0]]["e2e"], "forms": results,
             "roofline": {"bound": "hbm", "achieved": alg / r["ms_per_step"] / 1e6, "peak": peak, "unit": "GB/s",
                          "frac": alg / r["ms_per_step"] / 1e6 / peak, "traffic": None,
                          "algorithmic_bytes": "1 B per base + 16 B (slot read + write) per k-mer instance",

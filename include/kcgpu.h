@@ -37,6 +37,7 @@ extern "C" {
 #endif
 
 typedef struct kcgpu_ctx kcgpu_ctx;
+typedef struct kcgpu_producer kcgpu_producer;
 
 #define KCGPU_MAX_OWNERS 16
 #define KCGPU_IPC_HANDLE_BYTES 64
@@ -75,9 +76,20 @@ int kcgpu_create(kcgpu_ctx **ctx, int k, uint64_t table_slots, uint64_t list_slo
  * Hand one parsed read to the engine: replaces the per-read copy of step 0 and steps 1 and 2
  * (kc-c4.c:133-180).  Reads shorter than k are dropped (kc-c4.c:141).  Bytes are classified by
  * the reference's strict table (kc-c4.c:21-38): A C G T U in either case and the bytes 0..3
- * are bases, everything else ends a k-mer.  One producer thread per context.
+ * are bases, everything else ends a k-mer.  One thread at a time (more: kcgpu_producer_*).
  */
 int kcgpu_add_read(kcgpu_ctx *ctx, const char *seq, size_t len);
+
+/*
+ * Several reader threads: one producer each.  A producer packs its reads into a staging block
+ * of its own (creating it adds one to the context) and submits the block when it is full, when
+ * it is flushed and when it is destroyed; kcgpu_add_read is the context's built-in producer.
+ * Everything else of a context may be called from any one thread at a time.
+ */
+int kcgpu_producer_create(kcgpu_ctx *ctx, kcgpu_producer **producer);
+int kcgpu_producer_add_read(kcgpu_producer *producer, const char *seq, size_t len);
+int kcgpu_producer_flush(kcgpu_producer *producer);
+int kcgpu_producer_destroy(kcgpu_producer *producer);
 
 /*
  * Count a stream the caller has already packed in HOST memory: reads separated by '\n', bytes

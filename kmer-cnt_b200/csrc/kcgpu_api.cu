@@ -13,8 +13,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kcgpu_kernels.cuh"
@@ -25,12 +27,18 @@ namespace {
 
 thread_local std::string g_kc_create_error;
 
+/* One lock for every launch, flush and statistic of every context of the process: reader
+ * threads (producers) fill their staging blocks outside it and take it only to fetch a block
+ * and to submit one.  Contexts linked into a group flush together, hence not one lock each. */
+std::mutex g_kc_mu;
+
 struct KcBlock {
 	char *h = nullptr;
 	uint8_t *d = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; /* copy start, copy end, kernel end */
 	bool in_flight = false;
+	bool owned = false; /* a producer is filling it */
 	size_t used = 0;
 };
 
@@ -49,16 +57,23 @@ struct kcgpu_ctx {
 	unsigned long long *d_stats = nullptr, *d_hist = nullptr;
 	cudaStream_t main_stream = nullptr;
 	size_t block_bytes = 0;
-	std::vector<KcBlock> blocks;
+	std::vector<KcBlock *> blocks;
 	size_t next_block = 0;
-	KcBlock *cur = nullptr;
-	std::vector<char> scratch;
+	kcgpu_producer *def = nullptr; /* the producer behind kcgpu_add_read / kcgpu_submit_stream */
 	uint32_t n_parts = 1, my_part = 0;
 	uint64_t *tables[KC_MAX_PARTS] = {};
 	std::vector<void *> ipc_mapped;
 	std::vector<kcgpu_ctx *> group; /* contexts linked in this process, this one included */
 	kcgpu_stats st{};
 	std::string err;
+};
+
+/* One stream of reads being packed into staging blocks; one per reader thread. */
+struct kcgpu_producer {
+	kcgpu_ctx *c = nullptr;
+	KcBlock *cur = nullptr;
+	uint64_t n_reads = 0, n_bases = 0; /* added to the context's statistics when a block is submitted */
+	std::vector<char> scratch;
 };
 
 namespace {
@@ -151,11 +166,33 @@ int kc_make_room(kcgpu_ctx *c, uint64_t n_bytes)
 	return VAFGPU_OK;
 }
 
-int kc_submit_current(kcgpu_ctx *c)
+/* lock held.  One more staging block for the context. */
+int kc_add_block(kcgpu_ctx *c)
 {
-	KcBlock *b = c->cur;
+	KcBlock *b = new (std::nothrow) KcBlock;
+	if (!b) return kfail(c, VAFGPU_ENOMEM, "out of memory");
+	c->blocks.push_back(b);
+	KCU(c, cudaSetDevice(c->device));
+	KCU(c, cudaHostAlloc(&b->h, c->block_bytes + 64, cudaHostAllocPortable));
+	KCU(c, cudaMalloc(&b->d, c->block_bytes + 64));
+	KCU(c, cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	KCU(c, cudaEventCreate(&b->e0));
+	KCU(c, cudaEventCreate(&b->e1));
+	KCU(c, cudaEventCreate(&b->e2));
+	return VAFGPU_OK;
+}
+
+/* lock held.  Copy the producer's block to the device and scan it there, on the block's stream. */
+int kc_submit_current(kcgpu_producer *p)
+{
+	kcgpu_ctx *c = p->c;
+	KcBlock *b = p->cur;
+	c->st.n_reads += p->n_reads;
+	c->st.n_bases += p->n_bases;
+	p->n_reads = p->n_bases = 0;
 	if (!b) return VAFGPU_OK;
-	c->cur = nullptr;
+	p->cur = nullptr;
+	b->owned = false;
 	if (!b->used) return VAFGPU_OK;
 	const size_t n = (b->used + 15) & ~(size_t)15;
 	memset(b->h + b->used, '\n', n - b->used);
@@ -173,30 +210,45 @@ int kc_submit_current(kcgpu_ctx *c)
 	return VAFGPU_OK;
 }
 
-int kc_ensure_room(kcgpu_ctx *c, size_t need)
+/* Takes the lock.  Room for `need` more bytes in the producer's block: submit it if it is
+ * full, fetch a free one if there is none (waiting for a block in flight is the back-pressure
+ * that replaces kt_pipeline's "at most three blocks"). */
+int kc_ensure_room(kcgpu_producer *p, size_t need)
 {
-	if (c->cur && c->cur->used + need > c->block_bytes) {
-		int rc = kc_submit_current(c);
-		if (rc) return rc;
+	kcgpu_ctx *c = p->c;
+	if (p->cur && p->cur->used + need <= c->block_bytes) return VAFGPU_OK;
+	for (;;) {
+		{
+			std::lock_guard<std::mutex> lk(g_kc_mu);
+			if (p->cur) {
+				int rc = kc_submit_current(p);
+				if (rc) return rc;
+			}
+			for (size_t tries = 0; tries < c->blocks.size(); ++tries) {
+				KcBlock *b = c->blocks[c->next_block];
+				c->next_block = (c->next_block + 1) % c->blocks.size();
+				if (b->owned) continue;
+				int rc = kc_wait_block(c, *b);
+				if (rc) return rc;
+				b->owned = true;
+				b->used = 0;
+				p->cur = b;
+				return VAFGPU_OK;
+			}
+		}
+		std::this_thread::yield(); /* more producers than blocks: wait for one to be submitted */
 	}
-	if (!c->cur) {
-		KcBlock &b = c->blocks[c->next_block];
-		c->next_block = (c->next_block + 1) % c->blocks.size();
-		int rc = kc_wait_block(c, b); /* back-pressure: at most blocks.size() blocks in flight */
-		if (rc) return rc;
-		b.used = 0;
-		c->cur = &b;
-	}
-	return VAFGPU_OK;
 }
 
+/* lock held.  Submit what the context's own producer has staged (other producers submit
+ * their own when they are flushed or destroyed) and wait for everything in flight. */
 int kc_sync_one(kcgpu_ctx *c)
 {
-	int rc = kc_submit_current(c);
+	int rc = c->def ? kc_submit_current(c->def) : VAFGPU_OK;
 	if (rc) return rc;
 	KCU(c, cudaSetDevice(c->device));
-	for (KcBlock &b : c->blocks) {
-		rc = kc_wait_block(c, b);
+	for (KcBlock *b : c->blocks) {
+		rc = kc_wait_block(c, *b);
 		if (rc) return rc;
 	}
 	KCU(c, cudaStreamSynchronize(c->main_stream));
@@ -370,15 +422,13 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 		KCU(c, cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking));
 		KCU(c, cudaEventCreate(&c->f0));
 		KCU(c, cudaEventCreate(&c->f1));
-		c->blocks.resize(3);
-		for (KcBlock &b : c->blocks) {
-			KCU(c, cudaHostAlloc(&b.h, block_bytes + 64, cudaHostAllocPortable));
-			KCU(c, cudaMalloc(&b.d, block_bytes + 64));
-			KCU(c, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
-			KCU(c, cudaEventCreate(&b.e0));
-			KCU(c, cudaEventCreate(&b.e1));
-			KCU(c, cudaEventCreate(&b.e2));
+		for (int i = 0; i < 3; ++i) {
+			int brc = kc_add_block(c);
+			if (brc) return brc;
 		}
+		c->def = new (std::nothrow) kcgpu_producer;
+		if (!c->def) return kfail(c, VAFGPU_ENOMEM, "out of memory");
+		c->def->c = c;
 		KCU(c, cudaDeviceSynchronize());
 		return VAFGPU_OK;
 	}();
@@ -396,16 +446,33 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 	return VAFGPU_OK;
 }
 
-int kcgpu_add_read(kcgpu_ctx *c, const char *seq, size_t len)
+int kcgpu_producer_create(kcgpu_ctx *c, kcgpu_producer **out)
 {
-	if (!c || (!seq && len)) return VAFGPU_EINVAL;
+	if (!c || !out) return VAFGPU_EINVAL;
+	kcgpu_producer *p = new (std::nothrow) kcgpu_producer;
+	if (!p) return kfail(c, VAFGPU_ENOMEM, "out of memory");
+	p->c = c;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	int rc = kc_add_block(c); /* one block per reader to fill, on top of those in flight */
+	if (rc) {
+		delete p;
+		return rc;
+	}
+	*out = p;
+	return VAFGPU_OK;
+}
+
+int kcgpu_producer_add_read(kcgpu_producer *p, const char *seq, size_t len)
+{
+	if (!p || (!seq && len)) return VAFGPU_EINVAL;
+	kcgpu_ctx *c = p->c;
 	if (len < (size_t)c->k) return VAFGPU_OK; /* kc-c4.c:141 */
-	c->st.n_reads++;
-	c->st.n_bases += len;
+	p->n_reads++;
+	p->n_bases += len;
 	if (len + 1 <= c->block_bytes) {
-		int rc = kc_ensure_room(c, len + 1);
+		int rc = kc_ensure_room(p, len + 1);
 		if (rc) return rc;
-		KcBlock *b = c->cur;
+		KcBlock *b = p->cur;
 		vafgpu_canonicalise_read(seq, len, b->h + b->used, 0); /* strict table: kc-c4.c:21-38 */
 		b->h[b->used + len] = '\n';
 		b->used += len + 1;
@@ -413,15 +480,15 @@ int kcgpu_add_read(kcgpu_ctx *c, const char *seq, size_t len)
 	}
 	/* a read longer than a block (a chromosome): pieces that overlap by k-1 bases, so that
 	 * every k-mer lies in exactly one piece */
-	if (c->scratch.size() < len) c->scratch.resize(len);
-	vafgpu_canonicalise_read(seq, len, c->scratch.data(), 0);
+	if (p->scratch.size() < len) p->scratch.resize(len);
+	vafgpu_canonicalise_read(seq, len, p->scratch.data(), 0);
 	const size_t piece = c->block_bytes - 1, step = piece - (size_t)(c->k - 1);
 	for (size_t at = 0;; at += step) {
 		const size_t n = len - at < piece ? len - at : piece;
-		int rc = kc_ensure_room(c, n + 1);
+		int rc = kc_ensure_room(p, n + 1);
 		if (rc) return rc;
-		KcBlock *b = c->cur;
-		memcpy(b->h + b->used, c->scratch.data() + at, n);
+		KcBlock *b = p->cur;
+		memcpy(b->h + b->used, p->scratch.data() + at, n);
 		b->h[b->used + n] = '\n';
 		b->used += n + 1;
 		if (at + n >= len) break;
@@ -429,19 +496,40 @@ int kcgpu_add_read(kcgpu_ctx *c, const char *seq, size_t len)
 	return VAFGPU_OK;
 }
 
+int kcgpu_producer_flush(kcgpu_producer *p)
+{
+	if (!p) return VAFGPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	return kc_submit_current(p);
+}
+
+int kcgpu_producer_destroy(kcgpu_producer *p)
+{
+	if (!p) return VAFGPU_OK;
+	int rc = kcgpu_producer_flush(p);
+	delete p;
+	return rc;
+}
+
+int kcgpu_add_read(kcgpu_ctx *c, const char *seq, size_t len)
+{
+	if (!c) return VAFGPU_EINVAL;
+	return kcgpu_producer_add_read(c->def, seq, len);
+}
+
 int kcgpu_submit_stream(kcgpu_ctx *c, const char *bytes, size_t n_bytes)
 {
 	if (!c || (!bytes && n_bytes)) return VAFGPU_EINVAL;
+	kcgpu_producer *p = c->def;
 	cudaPointerAttributes attr;
 	const bool pinned = cudaPointerGetAttributes(&attr, bytes) == cudaSuccess && attr.type == cudaMemoryTypeHost;
 	cudaGetLastError(); /* a plain malloc pointer is reported as an error by older drivers */
 	size_t at = 0;
 	while (at < n_bytes) {
-		int rc = kc_submit_current(c); /* close what kcgpu_add_read left open */
+		/* a fresh block: what kcgpu_add_read or the last round left open is submitted first */
+		int rc = kc_ensure_room(p, c->block_bytes + 1);
 		if (rc) return rc;
-		rc = kc_ensure_room(c, 1);
-		if (rc) return rc;
-		KcBlock *b = c->cur;
+		KcBlock *b = p->cur;
 		size_t n = n_bytes - at, advance;
 		bool add_nl = false;
 		if (n > c->block_bytes) {
@@ -461,21 +549,23 @@ int kcgpu_submit_stream(kcgpu_ctx *c, const char *bytes, size_t n_bytes)
 			advance = n;
 			add_nl = bytes[at + n - 1] != '\n';
 		}
+		at += advance;
 		if (!pinned) {
-			memcpy(b->h, bytes + at, n);
+			memcpy(b->h, bytes + at - advance, n);
 			if (add_nl) b->h[n++] = '\n';
 			b->used = n;
-			at += advance;
-			continue; /* submitted at the top of the loop or after it */
+			continue; /* submitted by the next kc_ensure_room or after the loop */
 		}
 		/* zero-copy: H2D straight from the caller's buffer, separator and padding written on the device */
-		c->cur = nullptr;
+		std::lock_guard<std::mutex> lk(g_kc_mu);
+		p->cur = nullptr;
+		b->owned = false;
 		const size_t n16 = (n + (add_nl ? 1 : 0) + 15) & ~(size_t)15;
 		rc = kc_make_room(c, n16);
 		if (rc) return rc;
 		KCU(c, cudaSetDevice(c->device));
 		KCU(c, cudaEventRecord(b->e0, b->stream));
-		KCU(c, cudaMemcpyAsync(b->d, bytes + at, n, cudaMemcpyHostToDevice, b->stream));
+		KCU(c, cudaMemcpyAsync(b->d, bytes + at - advance, n, cudaMemcpyHostToDevice, b->stream));
 		if (n16 > n) KCU(c, cudaMemsetAsync(b->d + n, '\n', n16 - n, b->stream));
 		KCU(c, cudaEventRecord(b->e1, b->stream));
 		KCU(c, kc_launch_scan(c, count_args(c, b->d, n16), b->stream));
@@ -483,9 +573,9 @@ int kcgpu_submit_stream(kcgpu_ctx *c, const char *bytes, size_t n_bytes)
 		b->in_flight = true;
 		c->pending_bytes += n16;
 		c->st.n_blocks++;
-		at += advance;
 	}
-	return kc_submit_current(c);
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	return kc_submit_current(p);
 }
 
 int kcgpu_count_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, void *stream)
@@ -493,6 +583,7 @@ int kcgpu_count_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, void *
 	if (!c) return VAFGPU_EINVAL;
 	if (((uintptr_t)d_bytes & 15) || (n_bytes & 15))
 		return kfail(c, VAFGPU_EINVAL, "device stream must be 16-byte aligned and a multiple of 16 bytes");
+	std::lock_guard<std::mutex> lk(g_kc_mu);
 	cudaStream_t s = stream ? (cudaStream_t)stream : c->main_stream;
 	/* as much at a time as the lists are sure to take, a flush in between */
 	const uint64_t n_chunks = n_bytes >> 4;
@@ -539,6 +630,7 @@ int kcgpu_extract_device(kcgpu_ctx *c, const void *d_bytes, size_t n_bytes, int 
 	a.out_keys = d_keys;
 	a.cap_per_part = cap_per_part;
 	a.part_counts = d_part_counts;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
 	KCU(c, cudaSetDevice(c->device));
 	cudaStream_t s = stream ? (cudaStream_t)stream : c->main_stream;
 	KCU(c, launch_extract(a, s));
@@ -559,6 +651,7 @@ int kcgpu_insert_device(kcgpu_ctx *c, const uint64_t *d_hashed_keys, size_t n, i
 	a.rslot_bits = c->rslot_bits;
 	a.table = c->d_table;
 	a.stats = c->d_stats;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
 	KCU(c, cudaSetDevice(c->device));
 	cudaStream_t s = stream ? (cudaStream_t)stream : c->main_stream;
 	KCU(c, launch_insert(a, s));
@@ -597,9 +690,18 @@ int kcgpu_ipc_open(kcgpu_ctx *c, const void *handle, void **d_peer_table)
 	return VAFGPU_OK;
 }
 
+static int kc_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *tables);
+
 int kcgpu_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *tables)
 {
 	if (!c) return VAFGPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	return kc_set_owners(c, n_parts, my_part, tables);
+}
+
+/* lock held */
+static int kc_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *tables)
+{
 	if (n_parts < 1 || n_parts > KC_MAX_PARTS || my_part < 0 || my_part >= n_parts || !tables)
 		return kfail(c, VAFGPU_EINVAL, "owner %d of %d", my_part, n_parts);
 	int rc = kc_flush_group(c); /* nothing of this context may still be running, or waiting in a list, under the old owners */
@@ -617,6 +719,7 @@ int kcgpu_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *tables
 int kcgpu_link(kcgpu_ctx *const *ctxs, int n)
 {
 	if (!ctxs || n < 1 || n > KC_MAX_PARTS) return VAFGPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
 	for (int i = 0; i < n; ++i) {
 		if (!ctxs[i]) return VAFGPU_EINVAL;
 		if (ctxs[i]->n_slots != ctxs[0]->n_slots || ctxs[i]->k != ctxs[0]->k || ctxs[i]->list_cap != ctxs[0]->list_cap)
@@ -638,7 +741,7 @@ int kcgpu_link(kcgpu_ctx *const *ctxs, int n)
 	std::vector<void *> tables(n);
 	for (int i = 0; i < n; ++i) tables[i] = ctxs[i]->d_table;
 	for (int i = 0; i < n; ++i) {
-		int rc = kcgpu_set_owners(ctxs[i], n, i, tables.data());
+		int rc = kc_set_owners(ctxs[i], n, i, tables.data());
 		if (rc) return rc;
 	}
 	for (int i = 0; i < n; ++i) {
@@ -648,9 +751,18 @@ int kcgpu_link(kcgpu_ctx *const *ctxs, int n)
 	return VAFGPU_OK;
 }
 
+static int kc_sync_group(kcgpu_ctx *c);
+
 int kcgpu_sync(kcgpu_ctx *c)
 {
 	if (!c) return VAFGPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	return kc_sync_group(c);
+}
+
+/* lock held */
+static int kc_sync_group(kcgpu_ctx *c)
+{
 	for (kcgpu_ctx *m : c->group) {
 		int rc = kc_sync_one(m);
 		if (rc) {
@@ -664,12 +776,14 @@ int kcgpu_sync(kcgpu_ctx *c)
 int kcgpu_flush(kcgpu_ctx *c)
 {
 	if (!c) return VAFGPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
 	return kc_flush_group(c);
 }
 
 int kcgpu_histogram(kcgpu_ctx *c, uint64_t hist[256], kcgpu_stats *stats)
 {
 	if (!c) return VAFGPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
 	int rc = kc_flush_group(c);
 	if (rc) return rc;
 	KCU(c, cudaSetDevice(c->device));
@@ -693,7 +807,8 @@ int kcgpu_histogram(kcgpu_ctx *c, uint64_t hist[256], kcgpu_stats *stats)
 int kcgpu_reset(kcgpu_ctx *c)
 {
 	if (!c) return VAFGPU_EINVAL;
-	int rc = kcgpu_sync(c);
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	int rc = kc_sync_group(c);
 	if (rc) return rc;
 	KCU(c, cudaSetDevice(c->device));
 	KCU(c, cudaMemsetAsync(c->d_table, 0, c->n_slots * 8, c->main_stream));
@@ -714,6 +829,7 @@ int kcgpu_reset(kcgpu_ctx *c)
 void kcgpu_destroy(kcgpu_ctx *c)
 {
 	if (!c) return;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
 	cudaSetDevice(c->device);
 	for (kcgpu_ctx *m : c->group) /* the others must not wait for a context that is gone */
 		if (m != c) {
@@ -723,15 +839,17 @@ void kcgpu_destroy(kcgpu_ctx *c)
 					break;
 				}
 		}
-	for (KcBlock &b : c->blocks) {
-		if (b.stream) cudaStreamSynchronize(b.stream);
-		if (b.h) cudaFreeHost(b.h);
-		if (b.d) cudaFree(b.d);
-		if (b.e0) cudaEventDestroy(b.e0);
-		if (b.e1) cudaEventDestroy(b.e1);
-		if (b.e2) cudaEventDestroy(b.e2);
-		if (b.stream) cudaStreamDestroy(b.stream);
+	for (KcBlock *b : c->blocks) {
+		if (b->stream) cudaStreamSynchronize(b->stream);
+		if (b->h) cudaFreeHost(b->h);
+		if (b->d) cudaFree(b->d);
+		if (b->e0) cudaEventDestroy(b->e0);
+		if (b->e1) cudaEventDestroy(b->e1);
+		if (b->e2) cudaEventDestroy(b->e2);
+		if (b->stream) cudaStreamDestroy(b->stream);
+		delete b;
 	}
+	delete c->def;
 	if (c->main_stream) {
 		cudaStreamSynchronize(c->main_stream);
 		cudaStreamDestroy(c->main_stream);

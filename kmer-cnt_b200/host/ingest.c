@@ -103,7 +103,7 @@ typedef struct {
 } unit_t;
 
 typedef struct {
-	vafgpu_ctx *ctx;
+	const ingest_sink_t *sink;
 	int k, block_len, pass;
 	file_t *files;
 	unit_t *units;
@@ -126,7 +126,7 @@ static void add_totals(pool_t *pl, file_t *f, uint64_t seqs, uint64_t bases, dou
 static int engine_failed(pool_t *pl)
 {
 	pthread_mutex_lock(&pl->mu);
-	if (!pl->failed) fprintf(stderr, "Error: %s\n", vafgpu_strerror(pl->ctx));
+	if (!pl->failed) fprintf(stderr, "Error: %s\n", pl->sink->error(pl->sink->engine));
 	pl->failed = 1;
 	pthread_mutex_unlock(&pl->mu);
 	return -1;
@@ -136,7 +136,7 @@ static int engine_failed(pool_t *pl)
  * closes a block when it holds >= block_len bases or the reader returns < 0, and stops the file
  * when a block comes out empty; reproduced so that a malformed FASTQ record ends (or does not
  * end) the file at the same place. */
-static int run_sequential(pool_t *pl, file_t *f, vafgpu_producer *prod)
+static int run_sequential(pool_t *pl, file_t *f, void *prod)
 {
 	fastx_t *fx = fastx_open(f->fn);
 	uint64_t seqs = 0, bases = 0;
@@ -148,7 +148,7 @@ static int run_sequential(pool_t *pl, file_t *f, vafgpu_producer *prod)
 		const char *s;
 		while ((l = fastx_next(fx, &s)) >= 0) {
 			if (l < pl->k) continue;
-			if (vafgpu_producer_add_read(prod, s, (size_t)l) != VAFGPU_OK) {
+			if (pl->sink->producer_add_read(prod, s, (size_t)l) != 0) {
 				fastx_close(fx);
 				return engine_failed(pl);
 			}
@@ -165,7 +165,7 @@ static int run_sequential(pool_t *pl, file_t *f, vafgpu_producer *prod)
 }
 
 /* one slice: pass 1 walks and validates, pass 2 walks again and feeds the engine */
-static int run_slice(pool_t *pl, file_t *f, int i, vafgpu_producer *prod)
+static int run_slice(pool_t *pl, file_t *f, int i, void *prod)
 {
 	const size_t hi = (size_t)(i + 1) * f->slice < f->size ? (size_t)(i + 1) * f->slice : f->size;
 	size_t o, seq, len, next;
@@ -176,7 +176,7 @@ static int run_slice(pool_t *pl, file_t *f, int i, vafgpu_producer *prod)
 	o = f->guess[i];
 	while (o < hi && (rc = strict_record(f->map, f->size, o, &seq, &len, &next)) == 1) {
 		if (pl->pass == 2 && len >= (size_t)pl->k) {
-			if (vafgpu_producer_add_read(prod, (const char *)f->map + seq, len) != VAFGPU_OK) return engine_failed(pl);
+			if (pl->sink->producer_add_read(prod, (const char *)f->map + seq, len) != 0) return engine_failed(pl);
 			++seqs;
 			bases += len;
 		}
@@ -192,8 +192,8 @@ static int run_slice(pool_t *pl, file_t *f, int i, vafgpu_producer *prod)
 static void *worker(void *arg)
 {
 	pool_t *pl = (pool_t *)arg;
-	vafgpu_producer *prod = NULL;
-	if (pl->pass == 2 && vafgpu_producer_create(pl->ctx, &prod) != VAFGPU_OK) {
+	void *prod = NULL;
+	if (pl->pass == 2 && pl->sink->producer_create(pl->sink->engine, &prod) != 0) {
 		engine_failed(pl);
 		return NULL;
 	}
@@ -207,7 +207,7 @@ static void *worker(void *arg)
 		if (pl->units[u].slice < 0) run_sequential(pl, f, prod);
 		else run_slice(pl, f, pl->units[u].slice, prod);
 	}
-	if (prod && vafgpu_producer_destroy(prod) != VAFGPU_OK) engine_failed(pl);
+	if (prod && pl->sink->producer_destroy(prod) != 0) engine_failed(pl);
 	return NULL;
 }
 
@@ -262,7 +262,8 @@ static void unmap(file_t *f)
 	f->n_slices = 0;
 }
 
-int ingest_files(vafgpu_ctx *ctx, int n_files, char **files, int k, int block_len, int n_threads, ingest_file_t *out)
+int ingest_files_to(const ingest_sink_t *sink, int n_files, char **files, int k, int block_len, int n_threads,
+                    ingest_file_t *out)
 {
 	pool_t pl;
 	file_t *fs = (file_t *)calloc((size_t)(n_files > 0 ? n_files : 1), sizeof *fs);
@@ -272,7 +273,7 @@ int ingest_files(vafgpu_ctx *ctx, int n_files, char **files, int k, int block_le
 	if (n_threads < 1) n_threads = 1;
 	memset(&pl, 0, sizeof pl);
 	pthread_mutex_init(&pl.mu, NULL);
-	pl.ctx = ctx, pl.k = k, pl.block_len = block_len, pl.files = fs;
+	pl.sink = sink, pl.k = k, pl.block_len = block_len, pl.files = fs;
 	for (i = 0; i < n_files; ++i) {
 		memset(&out[i], 0, sizeof out[i]);
 		fs[i].fn = files[i];
@@ -315,4 +316,16 @@ int ingest_files(vafgpu_ctx *ctx, int n_files, char **files, int k, int block_le
 	free(fs);
 	pthread_mutex_destroy(&pl.mu);
 	return pl.failed ? -1 : 0;
+}
+
+/* the vaf-counter engine as a sink */
+static int vaf_producer_create(void *engine, void **producer) { return vafgpu_producer_create((vafgpu_ctx *)engine, (vafgpu_producer **)producer); }
+static int vaf_producer_add_read(void *producer, const char *seq, size_t len) { return vafgpu_producer_add_read((vafgpu_producer *)producer, seq, len); }
+static int vaf_producer_destroy(void *producer) { return vafgpu_producer_destroy((vafgpu_producer *)producer); }
+static const char *vaf_error(void *engine) { return vafgpu_strerror((const vafgpu_ctx *)engine); }
+
+int ingest_files(vafgpu_ctx *ctx, int n_files, char **files, int k, int block_len, int n_threads, ingest_file_t *out)
+{
+	ingest_sink_t sink = {ctx, vaf_producer_create, vaf_producer_add_read, vaf_producer_destroy, vaf_error};
+	return ingest_files_to(&sink, n_files, files, k, block_len, n_threads, out);
 }

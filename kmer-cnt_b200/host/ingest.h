@@ -22,6 +22,7 @@
 #ifndef KMERCNT_INGEST_H
 #define KMERCNT_INGEST_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/vafgpu.h"
@@ -36,6 +37,19 @@ typedef struct {
 	int opened;           /* 0: could not be opened (silently skipped, vaf-counter.c:557) */
 	int sliced;           /* number of slices it was cut into (0 = read sequentially) */
 } ingest_file_t;
+
+/* Where the readers hand their reads: one producer per reader thread (vafgpu_producer_* for
+ * vaf-counter, kcgpu_producer_* for kc-c4). */
+typedef struct ingest_sink {
+	void *engine;
+	int (*producer_create)(void *engine, void **producer);
+	int (*producer_add_read)(void *producer, const char *seq, size_t len);
+	int (*producer_destroy)(void *producer);
+	const char *(*error)(void *engine);
+} ingest_sink_t;
+
+int ingest_files_to(const ingest_sink_t *sink, int n_files, char **files, int k, int block_len, int n_threads,
+                    ingest_file_t *out);
 
 /* Count every file with n_threads reader threads.  block_len is -b (the sequential reader
  * closes a block when it holds that many bases, vaf-counter.c:509).  Returns 0, or -1 after

@@ -10,7 +10,9 @@
  *   -p  only checked (>= 10, kc-c4.c:243-246): the partition into 2^p tables is an internal of
  *       the reference; here the hash space is split over the visible GPUs instead
  *   -b  bases per turn when reads are dealt to several GPUs (the reference's block size)
- *   -t  accepted; the insert it used to parallelise runs on the GPU
+ *   -t  number of host reader threads (the insert it used to parallelise runs on the GPU): a
+ *       plain four-line FASTQ is cut into slices read in parallel (ingest.h), anything else
+ *       goes through the one sequential reader
  * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: all visible);
  *              KCGPU_TABLE_SLOTS=n slots per GPU to start with (default: from the file size);
  *              either way a table that fills up is doubled and the file counted again.
@@ -26,6 +28,7 @@
 
 #include "../../include/kcgpu.h"
 #include "fastx.h"
+#include "ingest.h"
 
 static uint64_t guess_slots(const char *fn, int n_dev)
 {
@@ -42,6 +45,67 @@ static uint64_t guess_slots(const char *fn, int n_dev)
 	est = est * 2 / (uint64_t)n_dev; /* at most one k-mer per byte; half-empty tables */
 	if (est < (1u << 20)) est = 1u << 20;
 	return est;
+}
+
+/* the counting engine as a sink of the readers: every reader thread deals its reads to the
+ * GPUs in turns of -b bases (kc-c4.c:150: a block is closed when it holds that many) */
+typedef struct {
+	kcgpu_ctx **ctx;
+	int n_dev, block_size;
+} engine_t;
+
+typedef struct {
+	engine_t *e;
+	kcgpu_producer *prod[KCGPU_MAX_OWNERS];
+	int turn;
+	uint64_t in_turn;
+} reader_t;
+
+static int reader_destroy(void *producer)
+{
+	reader_t *r = (reader_t *)producer;
+	int rc = 0;
+	for (int i = 0; i < r->e->n_dev; ++i)
+		if (r->prod[i] && kcgpu_producer_destroy(r->prod[i]) != VAFGPU_OK) rc = -1;
+	free(r);
+	return rc;
+}
+
+static int reader_create(void *engine, void **producer)
+{
+	static int next_turn = 0;
+	engine_t *e = (engine_t *)engine;
+	reader_t *r = (reader_t *)calloc(1, sizeof *r);
+	if (!r) return -1;
+	r->e = e;
+	r->turn = __atomic_fetch_add(&next_turn, 1, __ATOMIC_RELAXED) % e->n_dev; /* readers start on different GPUs */
+	for (int i = 0; i < e->n_dev; ++i)
+		if (kcgpu_producer_create(e->ctx[i], &r->prod[i]) != VAFGPU_OK) {
+			reader_destroy(r);
+			return -1;
+		}
+	*producer = r;
+	return 0;
+}
+
+static int reader_add_read(void *producer, const char *seq, size_t len)
+{
+	reader_t *r = (reader_t *)producer;
+	if (kcgpu_producer_add_read(r->prod[r->turn], seq, len) != VAFGPU_OK) return -1;
+	r->in_turn += len;
+	if (r->in_turn >= (uint64_t)r->e->block_size) {
+		r->in_turn = 0;
+		r->turn = (r->turn + 1) % r->e->n_dev;
+	}
+	return 0;
+}
+
+static const char *engine_error(void *engine)
+{
+	engine_t *e = (engine_t *)engine;
+	for (int i = 0; i < e->n_dev; ++i)
+		if (kcgpu_strerror(e->ctx[i])[0]) return kcgpu_strerror(e->ctx[i]);
+	return "unknown error";
 }
 
 int main(int argc, char *argv[])
@@ -97,28 +161,15 @@ int main(int argc, char *argv[])
 			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
 			return 1;
 		}
-		fastx_t *fx = fastx_open(fn);
-		if (!fx) {
+		engine_t eng = {ctx, n_dev, block_size};
+		ingest_sink_t sink = {&eng, reader_create, reader_add_read, reader_destroy, engine_error};
+		ingest_file_t info;
+		char *files[1] = {(char *)fn};
+		if (ingest_files_to(&sink, 1, files, k, block_size, n_thread, &info) != 0) return 1;
+		if (!info.opened) {
 			fprintf(stderr, "ERROR: cannot open %s\n", fn);
 			return 1;
 		}
-		const char *seq;
-		long len;
-		int turn = 0;
-		uint64_t in_turn = 0;
-		while ((len = fastx_next(fx, &seq)) >= 0) { /* kc-c4.c:139-152 */
-			if (len < k) continue;
-			if (kcgpu_add_read(ctx[turn], seq, (size_t)len) != VAFGPU_OK) {
-				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[turn]));
-				return 1;
-			}
-			in_turn += (uint64_t)len;
-			if (in_turn >= (uint64_t)block_size) { /* kc-c4.c:150: the next block goes to the next GPU */
-				in_turn = 0;
-				turn = (turn + 1) % n_dev;
-			}
-		}
-		fastx_close(fx);
 		memset(hist, 0, sizeof hist);
 		for (i = 0; i < n_dev; ++i) {
 			if (kcgpu_histogram(ctx[i], part, &st) != VAFGPU_OK) {

@@ -25,7 +25,8 @@ IPC_HANDLE_BYTES = 64
 NO_LISTS = (1 << 64) - 1  # list_slots: every k-mer straight to the table
 
 EXPORTS = (
-    "kcgpu_device_count", "kcgpu_create", "kcgpu_add_read", "kcgpu_submit_stream", "kcgpu_count_device", "kcgpu_extract_device",
+    "kcgpu_device_count", "kcgpu_create", "kcgpu_add_read", "kcgpu_producer_create", "kcgpu_producer_add_read",
+    "kcgpu_producer_flush", "kcgpu_producer_destroy", "kcgpu_submit_stream", "kcgpu_count_device", "kcgpu_extract_device",
     "kcgpu_insert_device", "kcgpu_table", "kcgpu_ipc_export", "kcgpu_ipc_open", "kcgpu_set_owners",
     "kcgpu_link", "kcgpu_sync", "kcgpu_flush", "kcgpu_histogram", "kcgpu_reset", "kcgpu_destroy", "kcgpu_strerror",
     "kcgpu_hash64",
@@ -58,6 +59,10 @@ def load_library() -> C.CDLL:
     lib.kcgpu_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int]
     lib.kcgpu_add_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.kcgpu_submit_stream.argtypes = [vp, vp, C.c_size_t]
+    lib.kcgpu_producer_create.argtypes = [vp, C.POINTER(vp)]
+    lib.kcgpu_producer_add_read.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.kcgpu_producer_flush.argtypes = [vp]
+    lib.kcgpu_producer_destroy.argtypes = [vp]
     lib.kcgpu_count_device.argtypes = [vp, vp, C.c_size_t, vp]
     lib.kcgpu_extract_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, vp, vp]
     lib.kcgpu_insert_device.argtypes = [vp, vp, C.c_size_t, C.c_int, vp]

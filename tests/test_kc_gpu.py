@@ -339,6 +339,21 @@ def test_cli_prints_the_reference_histogram(lib, name):
     assert b"counting again" in r.stderr
 
 
+def test_cli_parallel_readers(kco, lib, tmp_path):
+    """-t N: a plain FASTQ cut into slices, one producer per reader thread (and per GPU)"""
+    rng = np.random.default_rng(23)
+    reads = util.make_genome_reads(rng, 200000, 30000, jitter=60, junk_rate=0.002, lower_rate=0.02, repeat=6)
+    fq = str(tmp_path / "r.fq")
+    util.write_fastq(fq, reads)
+    env = dict(os.environ, VAFGPU_SLICE_BYTES="300000")
+    for k in (21, 31):
+        want, _, _ = kco.count_reads(reads, k)
+        for t in (1, 4, 9):
+            out = subprocess.run([KC_CLI, "-k", str(k), "-t", str(t), "-b", "500000", fq], check=True, capture_output=True,
+                                 env=env).stdout.decode()
+            assert out == kcgpu.format_histogram(want), (k, t)
+
+
 def test_cli_usage_and_errors(lib, tmp_path):
     r = subprocess.run([KC_CLI], capture_output=True)
     assert r.returncode == 1 and r.stderr.startswith(b"Usage: kc-c4 [options] <in.fa>\n")

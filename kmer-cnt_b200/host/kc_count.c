@@ -24,11 +24,19 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include "../../include/kcgpu.h"
 #include "fastx.h"
 #include "ingest.h"
+
+static double now(void)
+{
+	struct timeval tv;
+	gettimeofday(&tv, NULL);
+	return tv.tv_sec + tv.tv_usec * 1e-6;
+}
 
 static uint64_t guess_slots(const char *fn, int n_dev)
 {
@@ -42,7 +50,9 @@ static uint64_t guess_slots(const char *fn, int n_dev)
 		if (fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) est *= 4; /* gzip */
 		fclose(fp);
 	}
-	est = est * 2 / (uint64_t)n_dev; /* at most one k-mer per byte; half-empty tables */
+	est = est / (uint64_t)n_dev; /* at most one k-mer per byte, and in a FASTQ half the bytes are qualities:
+	                              * the table is at most half full; a FASTA of all-distinct k-mers fills
+	                              * it, and the file is then counted again with twice the slots */
 	if (est < (1u << 20)) est = 1u << 20;
 	return est;
 }
@@ -148,7 +158,9 @@ int main(int argc, char *argv[])
 
 	const int direct = getenv("KCGPU_DIRECT") && atoi(getenv("KCGPU_DIRECT")); /* no region lists (development) */
 	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn, n_dev);
+	const int timing = getenv("KCGPU_TIMING") != NULL; /* phase times on stderr */
 	for (int attempt = 0;; ++attempt) {
+		double t0 = now(), t1;
 		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
 		uint64_t hist[256], part[256], overflow = 0;
 		kcgpu_stats st;
@@ -161,6 +173,9 @@ int main(int argc, char *argv[])
 			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
 			return 1;
 		}
+		t1 = now();
+		if (timing) fprintf(stderr, "[kc-c4] contexts (%llu slots per GPU)  %8.1f ms\n", (unsigned long long)slots, (t1 - t0) * 1e3);
+		t0 = t1;
 		engine_t eng = {ctx, n_dev, block_size};
 		ingest_sink_t sink = {&eng, reader_create, reader_add_read, reader_destroy, engine_error};
 		ingest_file_t info;
@@ -170,6 +185,11 @@ int main(int argc, char *argv[])
 			fprintf(stderr, "ERROR: cannot open %s\n", fn);
 			return 1;
 		}
+		t1 = now();
+		if (timing)
+			fprintf(stderr, "[kc-c4] reading + counting (%d slices) %8.1f ms, %.1f Mbases/s\n", info.sliced, (t1 - t0) * 1e3,
+			        info.bases / (t1 - t0) / 1e6);
+		t0 = t1;
 		memset(hist, 0, sizeof hist);
 		for (i = 0; i < n_dev; ++i) {
 			if (kcgpu_histogram(ctx[i], part, &st) != VAFGPU_OK) {
@@ -180,7 +200,11 @@ int main(int argc, char *argv[])
 			overflow += st.n_overflow;
 			slots = st.table_slots;
 		}
+		t1 = now();
+		if (timing) fprintf(stderr, "[kc-c4] flush + histogram               %8.1f ms (kernels %.1f ms, copies %.1f ms)\n", (t1 - t0) * 1e3, st.kernel_ms, st.h2d_ms);
+		t0 = t1;
 		for (i = 0; i < n_dev; ++i) kcgpu_destroy(ctx[i]);
+		if (timing) fprintf(stderr, "[kc-c4] destroy                         %8.1f ms\n", (now() - t0) * 1e3);
 		if (overflow) { /* never print a histogram with k-mers missing */
 			struct stat sb;
 			if (attempt >= 12 || stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode)) { /* a pipe cannot be read twice */

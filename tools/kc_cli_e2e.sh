@@ -16,14 +16,15 @@ for reads in ${@:-1000000 10000000}; do
 		s=$(date +%s%N)
 		"$ref/kc-c4" -k 31 -t $t "$work/c.fq" > "$work/ref$t.hist"
 		e=$(date +%s%N)
-		echo "reference -t $t: wall $(( (e - s) / 1000000 )) ms = $(( reads * 150 * 1000 / ((e - s) / 1000) )) Mbases/s"
+		echo "reference -t $t: wall $(( (e - s) / 1000000 )) ms = $(( reads * 150 * 1000 / ((e - s) / 1000) / 1000 )) Mbases/s"
 	done
 	for t in 1 4 $ncpu; do
 		s=$(date +%s%N)
-		"$root/kmer-cnt_b200/kc-c4" -k 31 -t $t "$work/c.fq" > "$work/gpu$t.hist"
+		KCGPU_TIMING=1 "$root/kmer-cnt_b200/kc-c4" -k 31 -t $t "$work/c.fq" > "$work/gpu$t.hist" 2> "$work/gpu$t.err"
 		e=$(date +%s%N)
 		cmp -s "$work/gpu$t.hist" "$work/ref1.hist" && same=identical || same=DIFFERENT
-		echo "this repo -t $t: wall $(( (e - s) / 1000000 )) ms = $(( reads * 150 * 1000 / ((e - s) / 1000) )) Mbases/s; histogram $same"
+		echo "this repo -t $t: wall $(( (e - s) / 1000000 )) ms = $(( reads * 150 * 1000 / ((e - s) / 1000) / 1000 )) Mbases/s; histogram $same"
+		sed 's/^/    /' "$work/gpu$t.err"
 	done
 	head -3 "$work/ref1.hist" | tr '\n' ' '; echo
 done

@@ -140,19 +140,25 @@ cudaError_t kc_launch_scan(const kcgpu_ctx *c, const CountArgs &a, cudaStream_t 
 /* what the lists (one owner) or the inbox (several owners) of m hold, into its table */
 cudaError_t kc_launch_flush(const kcgpu_ctx *m, cudaStream_t s)
 {
+	uint64_t *lists = kc_lists_of(m->d_table, m->n_slots);
+	unsigned long long *cursors = kc_cursors_of(m->d_table, m->n_slots, m->list_cap, m->region_bits);
 	if (m->n_parts == 1)
-		return launch_flush(m->d_table, m->n_slots, m->list_cap, m->region_bits, m->rslot_bits, m->d_stats, s);
-	InsertArgs a{};
-	a.hashed = kc_lists_of(m->d_table, m->n_slots);
-	a.n = m->list_cap << m->region_bits;
-	a.n_ptr = kc_cursors_of(m->d_table, m->n_slots, m->list_cap, m->region_bits);
-	a.split = 1;
-	a.n_parts = m->n_parts;
+		return launch_flush(m->d_table, lists, cursors, m->list_cap, m->region_bits, m->rslot_bits, m->d_stats, s);
+	/* the inbox (first half of the list area) into the region lists (second half), then those */
+	RouteArgs a{};
+	a.inbox = lists;
+	a.n_ptr = kc_inbox_cursor(m->d_table, m->n_slots, m->list_cap, m->region_bits);
+	a.inbox_cap = kc_inbox_cap(m->list_cap, m->region_bits);
+	a.lists = lists + a.inbox_cap;
+	a.cursors = cursors;
+	a.cap = m->list_cap / 2;
+	a.table = m->d_table;
 	a.region_bits = m->region_bits;
 	a.rslot_bits = m->rslot_bits;
-	a.table = m->d_table;
 	a.stats = m->d_stats;
-	return launch_insert(a, s);
+	cudaError_t e = launch_route(a, s);
+	if (e != cudaSuccess) return e;
+	return launch_flush(m->d_table, a.lists, cursors, a.cap, m->region_bits, m->rslot_bits, m->d_stats, s);
 }
 
 /* the lists must be able to take n more k-mers: flush first if they might not (a context whose
@@ -272,7 +278,7 @@ int kc_flush_group(kcgpu_ctx *c)
 		KCU(m, cudaEventRecord(m->f0, m->main_stream));
 		KCU(m, kc_launch_flush(m, m->main_stream));
 		KCU(m, cudaMemsetAsync(kc_cursors_of(m->d_table, m->n_slots, m->list_cap, m->region_bits), 0,
-		                       (size_t)KC_CURSOR_STRIDE * 8 << m->region_bits, m->main_stream));
+		                       (size_t)kc_cursor_bytes(m->region_bits), m->main_stream));
 		KCU(m, cudaEventRecord(m->f1, m->main_stream));
 	}
 	for (kcgpu_ctx *m : c->group) {
@@ -417,7 +423,7 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 		KCU(c, cudaMalloc(&c->d_hist, 256 * sizeof(unsigned long long)));
 		KCU(c, cudaMemset(c->d_table, 0, n * 8));
 		if (c->list_cap)
-			KCU(c, cudaMemset(kc_cursors_of(c->d_table, n, c->list_cap, c->region_bits), 0, (size_t)KC_CURSOR_STRIDE * 8 << c->region_bits));
+			KCU(c, cudaMemset(kc_cursors_of(c->d_table, n, c->list_cap, c->region_bits), 0, (size_t)kc_cursor_bytes(c->region_bits)));
 		KCU(c, cudaMemset(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long)));
 		KCU(c, cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking));
 		KCU(c, cudaEventCreate(&c->f0));
@@ -713,6 +719,9 @@ static int kc_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *ta
 	}
 	c->n_parts = (uint32_t)n_parts;
 	c->my_part = (uint32_t)my_part;
+	/* several owners: half of the list area is the inbox, the other half the region lists */
+	c->flush_bytes = (c->list_cap << c->region_bits) / 20 * 19 / (n_parts > 1 ? 2 : 1);
+	c->st.flush_bytes = c->flush_bytes;
 	return VAFGPU_OK;
 }
 
@@ -814,7 +823,7 @@ int kcgpu_reset(kcgpu_ctx *c)
 	KCU(c, cudaMemsetAsync(c->d_table, 0, c->n_slots * 8, c->main_stream));
 	if (c->list_cap)
 		KCU(c, cudaMemsetAsync(kc_cursors_of(c->d_table, c->n_slots, c->list_cap, c->region_bits), 0,
-		                       (size_t)KC_CURSOR_STRIDE * 8 << c->region_bits, c->main_stream));
+		                       (size_t)kc_cursor_bytes(c->region_bits), c->main_stream));
 	KCU(c, cudaMemsetAsync(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long), c->main_stream));
 	KCU(c, cudaStreamSynchronize(c->main_stream));
 	const kcgpu_stats keep = c->st;

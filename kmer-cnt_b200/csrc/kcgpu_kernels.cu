@@ -19,6 +19,7 @@
  *                          In the first two the owner's memory may be a peer's: the same
  *                          instructions then travel over NVLink, which is the all-to-all of
  *                          the partition step fused into the producer.
+ *  kc_route_kernel         several owners: what arrived in the inbox, filed under its region
  *  kc_flush_kernel         worker_for (kc-c4.c:116-128): the region lists into the table, region
  *                          by region so that the slice being filled stays in L2
  *  kc_insert_kernel        the same for lists that came from an exchange
@@ -215,11 +216,11 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 				if (threadIdx.x < a.n_parts) {
 					const uint32_t n = s_cnt[buf][threadIdx.x];
 					if (n) s_base[buf][threadIdx.x] =
-						atomicAdd(kc_cursors_of(a.tables[threadIdx.x], a.n_slots, a.list_cap, a.region_bits), (unsigned long long)n);
+						atomicAdd(kc_inbox_cursor(a.tables[threadIdx.x], a.n_slots, a.list_cap, a.region_bits), (unsigned long long)n);
 					s_cnt[buf ^ 1][threadIdx.x] = 0;
 				}
 				__syncthreads();
-				const uint64_t cap = a.list_cap << a.region_bits;
+				const uint64_t cap = kc_inbox_cap(a.list_cap, a.region_bits);
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
 					if (!ok[j]) continue;
@@ -272,18 +273,18 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 /* The region lists into the table.  CTA b takes tile b % tiles_per_region of region
  * b / tiles_per_region: CTAs are dispatched in order, so the resident ones work on two or
  * three neighbouring regions and their slices (<= 16 MiB each) stay in L2 while they fill. */
-__global__ void __launch_bounds__(KC_THREADS) kc_flush_kernel(uint64_t *base, const uint64_t n_slots, const uint64_t list_cap,
-                                                               const uint32_t region_bits, const uint32_t rslot_bits,
-                                                               const uint32_t tiles_per_region, const uint32_t tile_entries,
-                                                               unsigned long long *stats)
+__global__ void __launch_bounds__(KC_THREADS) kc_flush_kernel(uint64_t *base, const uint64_t *lists, const unsigned long long *cursors,
+                                                               const uint64_t list_cap, const uint32_t region_bits,
+                                                               const uint32_t rslot_bits, const uint32_t tiles_per_region,
+                                                               const uint32_t tile_entries, unsigned long long *stats)
 {
 	const uint32_t region = blockIdx.x / tiles_per_region, tile = blockIdx.x % tiles_per_region;
-	const uint64_t filled = kc_cursors_of(base, n_slots, list_cap, region_bits)[(uint64_t)region * KC_CURSOR_STRIDE];
+	const uint64_t filled = cursors[(uint64_t)region * KC_CURSOR_STRIDE];
 	const uint64_t n = filled < list_cap ? filled : list_cap;
 	const uint64_t lo = (uint64_t)tile * tile_entries;
 	if (lo >= n) return;
 	const uint64_t hi = lo + tile_entries < n ? lo + tile_entries : n;
-	const uint64_t *list = kc_lists_of(base, n_slots) + (uint64_t)region * list_cap;
+	const uint64_t *list = lists + (uint64_t)region * list_cap;
 	uint64_t *slice = base + ((uint64_t)region << rslot_bits);
 	uint32_t n_new = 0, n_overflow = 0;
 	/* one entry per thread and step: more entries in flight per thread (four home slots
@@ -330,6 +331,36 @@ __global__ void __launch_bounds__(KC_THREADS) kc_insert_kernel(const InsertArgs 
 		if (n_kmers) atomicAdd(a.stats + KC_ST_KMERS, (unsigned long long)n_kmers);
 		if (n_new) atomicAdd(a.stats + KC_ST_NEW, (unsigned long long)n_new);
 		if (n_overflow) atomicAdd(a.stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
+	}
+}
+
+/* several owners: the inbox into the region lists (c4x_insert_buf, kc-c4.c:64-72, on the owner's side) */
+__global__ void __launch_bounds__(KC_THREADS) kc_route_kernel(const RouteArgs a)
+{
+	uint32_t n_new = 0, n_overflow = 0, n_direct = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * KC_THREADS;
+	const uint64_t filled = *a.n_ptr;
+	const uint64_t n = filled < a.inbox_cap ? filled : a.inbox_cap;
+	for (uint64_t i = (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x; i < n; i += stride) {
+		const uint64_t q = __ldcs(reinterpret_cast<const unsigned long long *>(a.inbox + i));
+		const uint64_t region = q & ((1ull << a.region_bits) - 1ull);
+		const uint64_t at = atomicAdd(a.cursors + region * KC_CURSOR_STRIDE, 1ull);
+		if (at < a.cap) {
+			a.lists[region * a.cap + at] = q;
+		} else {
+			++n_direct;
+			kc_insert(a.table, a.region_bits, a.rslot_bits, q, n_new, n_overflow);
+		}
+	}
+	for (int o = 16; o; o >>= 1) {
+		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
+		n_overflow += __shfl_xor_sync(KC_FULL, n_overflow, o);
+		n_direct += __shfl_xor_sync(KC_FULL, n_direct, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (n_new) atomicAdd(a.stats + KC_ST_NEW, (unsigned long long)n_new);
+		if (n_overflow) atomicAdd(a.stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
+		if (n_direct) atomicAdd(a.stats + KC_ST_DIRECT, (unsigned long long)n_direct);
 	}
 }
 
@@ -402,15 +433,22 @@ cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream) { return l
 cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_EXTRACT>(a, stream); }
 cudaError_t launch_push(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_PUSH>(a, stream); }
 
-cudaError_t launch_flush(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits, uint32_t rslot_bits,
-                         unsigned long long *stats, cudaStream_t stream)
+cudaError_t launch_flush(uint64_t *base, const uint64_t *lists, const unsigned long long *cursors, uint64_t list_cap,
+                         uint32_t region_bits, uint32_t rslot_bits, unsigned long long *stats, cudaStream_t stream)
 {
 	if (!list_cap) return cudaSuccess;
 	static const uint32_t tile = getenv("KCGPU_FLUSH_TILE") ? (uint32_t)atoi(getenv("KCGPU_FLUSH_TILE")) : (uint32_t)KC_FLUSH_TILE; /* tuning knob */
 	const uint64_t tiles = (list_cap + tile - 1) / tile;
 	const uint64_t blocks = tiles << region_bits;
 	if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-	kc_flush_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(base, n_slots, list_cap, region_bits, rslot_bits, (uint32_t)tiles, tile, stats);
+	kc_flush_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(base, lists, cursors, list_cap, region_bits, rslot_bits, (uint32_t)tiles, tile, stats);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_route(const RouteArgs &a, cudaStream_t stream)
+{
+	if (!a.inbox_cap) return cudaSuccess;
+	kc_route_kernel<<<148 * 8, KC_THREADS, 0, stream>>>(a);
 	return cudaGetLastError();
 }
 

@@ -20,8 +20,9 @@
  *
  * One allocation per owner, so that one pointer (one CUDA IPC handle) names it all:
  *   [ table: n_slots x 8 B ][ lists: n_regions x list_cap x 8 B ][ cursors: n_regions x 256 B, one 64-bit count each ]
- * With several owners the list area is one list, the owner's inbox (cursor 0): whoever finds a
- * k-mer appends it there in sector-sized runs, and the owner inserts what arrived.
+ * With several owners the first half of the list area is the owner's inbox (its cursor follows
+ * the regions'): whoever finds a k-mer appends it there in sector-sized runs; at a flush the
+ * owner files what arrived under its region in the second half and empties that region by region.
  */
 #ifndef KCGPU_KERNELS_CUH
 #define KCGPU_KERNELS_CUH
@@ -95,9 +96,25 @@ struct InsertArgs {
 cudaError_t launch_count(const CountArgs &a, cudaStream_t stream);   /* extract + insert straight into the tables */
 cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream); /* extract + append to the region lists (one owner) */
 cudaError_t launch_push(const CountArgs &a, cudaStream_t stream);      /* extract + append to the owners' inboxes (several owners) */
-/* insert what the region lists of this allocation hold into its table; the cursors are left as they are */
-cudaError_t launch_flush(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits, uint32_t rslot_bits,
-                         unsigned long long *stats, cudaStream_t stream);
+/* insert what the region lists hold (`cap` entries per region at most, one cursor per region)
+ * into the table; the cursors are left as they are */
+cudaError_t launch_flush(uint64_t *table, const uint64_t *lists, const unsigned long long *cursors, uint64_t cap,
+                         uint32_t region_bits, uint32_t rslot_bits, unsigned long long *stats, cudaStream_t stream);
+
+/* several owners: what arrived in the inbox, filed under its region (straight to the table
+ * where a region list is full) */
+struct RouteArgs {
+	const uint64_t *inbox;
+	const unsigned long long *n_ptr; /* the inbox's cursor */
+	uint64_t inbox_cap;
+	uint64_t *lists;                 /* region lists, `cap` entries each */
+	unsigned long long *cursors;
+	uint64_t cap;
+	uint64_t *table;
+	uint32_t region_bits, rslot_bits;
+	unsigned long long *stats;
+};
+cudaError_t launch_route(const RouteArgs &a, cudaStream_t stream);
 cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream); /* extract into per-owner lists */
 cudaError_t launch_insert(const InsertArgs &a, cudaStream_t stream);
 cudaError_t launch_histogram(const uint64_t *table, uint64_t n_slots, unsigned long long *hist256, int n_sm,
@@ -108,9 +125,17 @@ KC_HD unsigned long long *kc_cursors_of(uint64_t *base, uint64_t n_slots, uint64
 {
 	return reinterpret_cast<unsigned long long *>(base + n_slots + (list_cap << region_bits));
 }
+/* one cursor per region and one more, the inbox's */
+KC_HD uint64_t kc_cursor_bytes(uint32_t region_bits) { return (((uint64_t)1 << region_bits) + 1) * KC_CURSOR_STRIDE * 8; }
 KC_HD uint64_t kc_alloc_bytes(uint64_t n_slots, uint64_t list_cap, uint32_t region_bits)
 {
-	return (n_slots + (list_cap << region_bits)) * 8 + ((uint64_t)KC_CURSOR_STRIDE * 8 << region_bits);
+	return (n_slots + (list_cap << region_bits)) * 8 + kc_cursor_bytes(region_bits);
+}
+/* several owners: the first half of the list area is the inbox, the second half the region lists */
+KC_HD uint64_t kc_inbox_cap(uint64_t list_cap, uint32_t region_bits) { return (list_cap << region_bits) / 2; }
+KC_HD unsigned long long *kc_inbox_cursor(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits)
+{
+	return kc_cursors_of(base, n_slots, list_cap, region_bits) + ((uint64_t)KC_CURSOR_STRIDE << region_bits);
 }
 
 } // namespace kcgpu

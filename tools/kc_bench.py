@@ -137,6 +137,7 @@ def main():
             handles = [None] * world
             dist.all_gather_object(handles, ctr.ipc_export())
             ctr.set_owners(rank, [None if r == rank else ctr.ipc_open(handles[r]) for r in range(world)])
+            _, st = ctr.histogram()  # flush_bytes depends on the number of owners
         return ctr, got_slots, st["flush_bytes"]
     # a stream of our own: the legacy default stream has handle 0, which the C ABI reads as "the context's stream"
     work = torch.cuda.Stream(device=dev)

@@ -65,3 +65,51 @@ def test_dealing_covers_every_read_once():
     for world in (1, 2, 3, 8):
         got = sorted(sum((sharding.split_reads(reads, r, world, block=100) for r in range(world)), []))
         assert got == reads
+
+
+# ---------------------------------------------------------------------------------------------
+# counting mode: owners partition the hash space, the per-owner histograms add up
+
+
+def _kc_rank(rank, world, port, k, reads, q):
+    """what one rank of tools/kc_bench.py does, with the oracle standing in for the device: extract
+    the k-mers of its share of the reads, keep those it owns and the lists for the others, exchange
+    the lists (the staged form's all-to-all, spelt as an all-gather because gloo lacks it), count what it owns, all-reduce the 256 bins"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kco = util.KcOracle()
+    mine = sharding.split_reads(reads, rank, world, block=64)
+    hashed = np.concatenate([kco.hashed_kmers(r, k) for r in mine if len(r) >= k] or [np.zeros(0, np.uint64)])
+    own = util.kcgpu.owner_of(hashed, world)
+    send = [hashed[own == p] for p in range(world)]
+    everybody = [None] * world
+    dist.all_gather_object(everybody, send)  # gloo has no all_to_all: everybody sees every list and takes its own
+    owned = np.concatenate([everybody[src][rank] for src in range(world)])
+    assert np.all(util.kcgpu.owner_of(owned, world) == rank)
+    hist, n_inst, n_dist = kco.count_hashed(owned, k)
+    t = torch.from_numpy(hist.view(np.int64).copy())
+    extra = torch.tensor([n_inst, n_dist], dtype=torch.int64)
+    dist.all_reduce(t)
+    dist.all_reduce(extra)
+    if rank == 0:
+        q.put((t.numpy().view(np.uint64).copy(), extra.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_counting_mode_two_owners_add_up():
+    k = 31
+    rng = np.random.default_rng(6)
+    reads = util.make_genome_reads(rng, 15000, 1200, jitter=30, repeat=4)
+    want, n_inst, n_dist = util.KcOracle().count_reads(reads, k)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 1000
+    procs = [ctx.Process(target=_kc_rank, args=(r, 2, port, k, reads, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged, (inst, dist_) = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(merged, want) and inst == n_inst and dist_ == n_dist

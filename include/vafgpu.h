@@ -41,6 +41,10 @@ extern "C" {
                                         verification mode */
 #define VAFGPU_F_HOST_MERGE       2u /* merge per-device counters on the host instead of
                                         with an NCCL all-reduce                            */
+#define VAFGPU_F_STRICT_BYTES     4u /* vafgpu_add_read classifies every byte by the strict table
+                                        (vaf-counter.c:73-90 = snp-pattern-gen.c:30-47): what a
+                                        build without SSSE3 does, and what snp-pattern-gen's
+                                        genome scan does (snp-pattern-gen.c:162-190) */
 
 typedef struct vafgpu_ctx vafgpu_ctx;
 typedef struct vafgpu_producer vafgpu_producer;

@@ -461,7 +461,7 @@ int vafgpu_producer_add_read(vafgpu_producer *p, const char *seq, size_t len)
 	if (len < (size_t)c->k) return VAFGPU_OK; /* vaf-counter.c:494 */
 	p->n_reads++;
 	p->n_bases += len;
-	const bool simd = true; /* the Makefile builds the reference with -mssse3 (Makefile:44) */
+	const bool simd = !(c->flags & VAFGPU_F_STRICT_BYTES); /* the Makefile builds the reference with -mssse3 (Makefile:44) */
 	if (len + 1 <= c->block_bytes) {
 		int rc = ensure_room(p, len + 1);
 		if (rc) return rc;

@@ -21,7 +21,7 @@ struct fastx {
 	size_t beg, end;
 	int eof;
 	int header_seen; /* a '>' or '@' has been consumed and its name follows */
-	fx_str_t seq;
+	fx_str_t seq, name;
 	size_t qual_len;
 	int qual_last; /* last quality byte gathered so far, -1 if none */
 };
@@ -111,6 +111,7 @@ void fastx_close(fastx_t *fx)
 	gzclose(fx->fp);
 	free(fx->buf);
 	free(fx->seq.s);
+	free(fx->name.s);
 	free(fx);
 }
 
@@ -118,6 +119,8 @@ static inline int fx_isspace(int c)
 {
 	return c == ' ' || (c >= '\t' && c <= '\r');
 }
+
+const char *fastx_name(const fastx_t *fx) { return fx->name.s ? fx->name.s : ""; }
 
 long fastx_next(fastx_t *fx, const char **seq)
 {
@@ -132,7 +135,13 @@ long fastx_next(fastx_t *fx, const char **seq)
 	fx->qual_last = -1;
 	/* name: up to the first white space; nothing left at all means end of input */
 	if (fx->beg >= fx->end && !fx_fill(fx)) return -1;
-	while ((c = fx_getc(fx)) != -1 && !fx_isspace(c)) {}
+	fx->name.l = 0;
+	while ((c = fx_getc(fx)) != -1 && !fx_isspace(c)) {
+		fx_reserve(&fx->name, 1);
+		fx->name.s[fx->name.l++] = (char)c;
+	}
+	fx_reserve(&fx->name, 0);
+	fx->name.s[fx->name.l] = 0;
 	if (c != '\n' && c != -1) { /* comment: rest of the header line */
 		size_t dummy = 0;
 		int dlast = -1;

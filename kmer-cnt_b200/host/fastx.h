@@ -29,6 +29,10 @@ void fastx_close(fastx_t *fx);
  * exactly where kseq_read would (kseq.h:187-191,227-231). */
 long fastx_next(fastx_t *fx, const char **seq);
 
+/* Name of the record fastx_next returned last: the header up to the first white space
+ * (kseq.h:199-204), NUL-terminated, valid until the next call. */
+const char *fastx_name(const fastx_t *fx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ LIB_PATH = os.environ.get("VAFGPU_LIB") or os.path.join(_HERE, "libvafgpu.so")  
 
 F_REFERENCE_RECIPE = 1
 F_HOST_MERGE = 2
+F_STRICT_BYTES = 4
 
 OK, EINVAL, ENOGPU, ECUDA, ENOMEM, ENCCL, ESTATE = 0, -1, -2, -3, -4, -5, -6
 

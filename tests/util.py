@@ -23,7 +23,7 @@ import vafgpu  # noqa: E402
 
 
 def build_oracle() -> None:
-    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "liboracle.so", "vaf_oracle", "synth"], check=True)
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "liboracle.so", "vaf_oracle", "kc_oracle", "spg_oracle", "synth"], check=True)
 
 
 def build_sim() -> str:
@@ -388,3 +388,73 @@ def make_genome_reads(rng: np.random.Generator, genome_len: int, n_reads: int, *
         unit = [b"A", b"AC", b"T", b"ACG", b"GT"][i % 5]
         reads.append((unit * 400)[: 300 + 7 * i])
     return reads
+
+
+# ---------------------------------------------------------------------------------------------
+# snp-pattern-gen cases
+
+
+def make_spg_case(seed: int, k: int, n_snps: int = 400):
+    """(fasta bytes, bed bytes) that exercise every branch of snp-pattern-gen: several contigs
+    (one shorter than k), multi-line records with a comment on the header, lower case and U,
+    N runs, a stretch copied to another contig forward and one reverse-complemented (reference
+    k-mers that occur twice), copies that carry the ALT allele (alternative k-mers that occur),
+    SNPs at contig ends, on unknown contigs, with alt '-' / 'N' / lower case, duplicated rows."""
+    rng = np.random.default_rng(seed)
+    lens = {"chrA": 90000, "chrB": 60000, "chrC": 5000, "tiny": max(k - 3, 1)}
+    g = {n: ACGT[rng.integers(0, 4, ln)].copy() for n, ln in lens.items()}
+    g["chrB"][1000:4000] = g["chrA"][20000:23000]                      # forward duplicate
+    g["chrC"][500:2500] = COMP[g["chrA"][40000:42000]][::-1]           # reverse-complement duplicate
+    for n in ("chrA", "chrB"):
+        for _ in range(6):
+            at = int(rng.integers(0, lens[n] - 50))
+            g[n][at:at + int(rng.integers(1, 40))] = ord("N")
+        at = int(rng.integers(0, lens[n] - 3000))
+        g[n][at:at + 2500] |= 0x20                                       # soft-masked stretch
+    rows = []
+    flank = k // 2
+    for i in range(n_snps):
+        n = ["chrA", "chrB", "chrC"][int(rng.integers(0, 3))]
+        r = rng.random()
+        if r < 0.04:
+            pos = int(rng.integers(0, flank + 1))                         # too close to the start
+        elif r < 0.08:
+            pos = lens[n] - 1 - int(rng.integers(0, flank + 1))           # too close to the end
+        elif r < 0.30 and n == "chrA":
+            pos = int(rng.integers(20000 + flank, 23000 - flank))         # inside the duplicated stretch
+        elif r < 0.40 and n == "chrA":
+            pos = int(rng.integers(40000 + flank, 42000 - flank))         # inside the reverse-complemented one
+        else:
+            pos = int(rng.integers(flank, lens[n] - flank))
+        ref = chr(g[n][pos])
+        alt = "ACGT"[int(rng.integers(0, 4))]
+        while alt.upper() == ref.upper():
+            alt = "ACGT"[int(rng.integers(0, 4))]
+        r2 = rng.random()
+        if r2 < 0.03:
+            alt = "-"
+        elif r2 < 0.05:
+            alt = "N"
+        elif r2 < 0.10:
+            alt = alt.lower()
+        elif r2 < 0.20 and flank <= pos < lens[n] - flank:
+            # plant the alternative k-mer somewhere else: the SNP must be rejected
+            km = g[n][pos - flank:pos - flank + k].copy()
+            km[flank] = ord(alt)
+            if rng.random() < 0.5:
+                km = COMP[km][::-1]
+            at = int(rng.integers(50000, 59000 - k))
+            g["chrB"][at:at + k] = km
+        chrom = n if rng.random() > 0.03 else "chrUn_missing"
+        rows.append((chrom, pos, pos + 1, "rs%d" % i, ref, alt))
+        if rng.random() < 0.03:
+            rows.append((chrom, pos, pos + 1, "rs%d_dup" % i, ref, alt))
+    g["chrA"][70000:70050] = np.frombuffer(b"ACGU" * 12 + b"ug", dtype=np.uint8)  # U counts as T
+    fa = []
+    for n in ("chrA", "tiny", "chrB", "chrC"):
+        fa.append(b">%s some comment here\n" % n.encode())
+        s = g[n].tobytes()
+        fa.extend(s[j:j + 61] + b"\n" for j in range(0, len(s), 61))
+    bed = b"".join(b"%s\t%d\t%d\t%s\t%s\t%s\n" % (c.encode(), s0, e0, rs.encode(), r.encode(), a.encode())
+                   for c, s0, e0, rs, r, a in rows)
+    return b"".join(fa), bed

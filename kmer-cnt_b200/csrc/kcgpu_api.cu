@@ -120,7 +120,6 @@ CountArgs count_args(const kcgpu_ctx *c, const void *bytes, size_t n)
 	a.n_slots = c->n_slots;
 	a.list_cap = c->list_cap;
 	a.k = c->k;
-	a.exp = getenv("KCGPU_EXP") ? atoi(getenv("KCGPU_EXP")) : 0;
 	a.n_parts = c->n_parts;
 	a.region_bits = c->region_bits;
 	a.rslot_bits = c->rslot_bits;

@@ -160,9 +160,10 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 			rv = rv >> 2 | (3ull - code) << top;
 			run = kc_is_base(b) ? run + 1 : 0;
 		}
-		/* four positions at a time: their memory operations are independent, so a thread has
-		 * four round trips to L2 in flight instead of one (the kernel waits for memory, not for
-		 * issue slots: profiles/r1_kc_part_v1) */
+		/* four positions at a time: the push form pays one pair of barriers and one cursor
+		 * atomic per owner for four positions of every thread; for the other forms four
+		 * independent round trips per thread measured the same as one (the list stores are
+		 * throughput-bound, profiles/r1_kc_ablation.txt) */
 #pragma unroll 1
 		for (int g = 0; g < 4; ++g) {
 			uint32_t word = own.x;
@@ -192,8 +193,7 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 					const uint64_t region = q[j] & ((1ull << a.region_bits) - 1ull);
 					unsigned long long *cursor =
 					    kc_cursors_of(a.tables[owner[j]], a.n_slots, a.list_cap, a.region_bits) + region * KC_CURSOR_STRIDE;
-					if (a.exp & 1) at[j] = (c * 16 + g * 4 + j) % a.list_cap;
-					else at[j] = ok[j] ? atomicAdd(cursor, 1ull) : 0ull;
+					at[j] = ok[j] ? atomicAdd(cursor, 1ull) : 0ull;
 				}
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 					uint64_t *base = a.tables[owner[j]];
 					const uint64_t region = q[j] & ((1ull << a.region_bits) - 1ull);
 					if (at[j] < a.list_cap) {
-						if (!(a.exp & 2)) kc_lists_of(base, a.n_slots)[region * a.list_cap + at[j]] = q[j];
+						kc_lists_of(base, a.n_slots)[region * a.list_cap + at[j]] = q[j];
 					} else {
 						++n_direct;
 						kc_insert(base, a.region_bits, a.rslot_bits, q[j], n_new, n_overflow);

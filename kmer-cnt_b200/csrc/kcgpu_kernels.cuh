@@ -70,7 +70,6 @@ struct CountArgs {
 	uint64_t first_chunk, end_chunk; /* the 16-byte chunks this launch owns (it reads up to two before them) */
 	uint64_t n_slots, list_cap;      /* geometry of every owner's allocation; list_cap 0 = no lists */
 	int k;
-	int exp;              /* development: 1 = no cursor atomics, 2 = no list stores, 3 = neither */
 	uint32_t n_parts;     /* owners of the hash space                          */
 	uint32_t region_bits, rslot_bits;
 	uint64_t *tables[KC_MAX_PARTS]; /* table of every owner (peer memory over NVLink for the others) */

@@ -129,7 +129,8 @@ int kcgpu_insert_device(kcgpu_ctx *ctx, const uint64_t *d_hashed_keys, size_t n,
  * kcgpu_ipc_open maps a peer's allocation into this process.  kcgpu_set_owners names the
  * allocation of every owner (all created with the same k, table_slots and list_slots as this
  * context; tables[my_part] may be NULL = this context's own); from then on this context's
- * kernels file a k-mer with owner hash mod n_parts.  The owners may live in other processes, so
+ * kernels file a k-mer with owner hash mod n_parts (what it filed before is flushed first: name
+ * the owners before counting, or between two barriers).  The owners may live in other processes, so
  * such a context never flushes by itself: the caller calls kcgpu_flush on every owner, between
  * two barriers (nobody may be filing while lists are emptied), at the latest when the contexts
  * together have taken n_parts * kcgpu_stats.flush_bytes of stream since the last flush.  Lists

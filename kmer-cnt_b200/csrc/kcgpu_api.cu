@@ -709,7 +709,10 @@ static int kc_set_owners(kcgpu_ctx *c, int n_parts, int my_part, void *const *ta
 {
 	if (n_parts < 1 || n_parts > KC_MAX_PARTS || my_part < 0 || my_part >= n_parts || !tables)
 		return kfail(c, VAFGPU_EINVAL, "owner %d of %d", my_part, n_parts);
-	int rc = kc_flush_group(c); /* nothing of this context may still be running, or waiting in a list, under the old owners */
+	/* nothing this context filed may still be running, or waiting in a list, under the old
+	 * owners.  A context that has filed nothing leaves its lists alone: a peer that already
+	 * knows this allocation may be filing into them right now */
+	int rc = c->pending_bytes ? kc_flush_group(c) : kc_sync_one(c);
 	if (rc) return rc;
 	c->external_owners = true;
 	for (int i = 0; i < n_parts; ++i) {

@@ -128,7 +128,7 @@ CountArgs count_args(const kcgpu_ctx *c, const void *bytes, size_t n)
 	return a;
 }
 
-int kc_flush_group(kcgpu_ctx *c);
+int kc_flush_group(kcgpu_ctx *c, bool submit_staged = true);
 
 cudaError_t kc_launch_scan(const kcgpu_ctx *c, const CountArgs &a, cudaStream_t s)
 {
@@ -167,7 +167,9 @@ int kc_make_room(kcgpu_ctx *c, uint64_t n_bytes)
 	if (!c->list_cap || c->external_owners) return VAFGPU_OK;
 	uint64_t pending = 0;
 	for (const kcgpu_ctx *m : c->group) pending += m->pending_bytes;
-	if (pending && pending + n_bytes > c->flush_bytes * c->group.size()) return kc_flush_group(c);
+	/* a flush that is merely due does not touch what the built-in producers have staged: their
+	 * threads may be writing there */
+	if (pending && pending + n_bytes > c->flush_bytes * c->group.size()) return kc_flush_group(c, false);
 	return VAFGPU_OK;
 }
 
@@ -229,15 +231,26 @@ int kc_ensure_room(kcgpu_producer *p, size_t need)
 				int rc = kc_submit_current(p);
 				if (rc) return rc;
 			}
+			/* an idle block if there is one, else the first one in flight in ring order */
+			KcBlock *pick = nullptr;
+			KCU(c, cudaSetDevice(c->device));
 			for (size_t tries = 0; tries < c->blocks.size(); ++tries) {
-				KcBlock *b = c->blocks[c->next_block];
-				c->next_block = (c->next_block + 1) % c->blocks.size();
+				KcBlock *b = c->blocks[(c->next_block + tries) % c->blocks.size()];
 				if (b->owned) continue;
-				int rc = kc_wait_block(c, *b);
+				if (!b->in_flight || cudaEventQuery(b->e2) == cudaSuccess) {
+					pick = b;
+					break;
+				}
+				if (!pick) pick = b;
+			}
+			cudaGetLastError(); /* cudaErrorNotReady of the query is not an error */
+			if (pick) {
+				c->next_block = (c->next_block + 1) % c->blocks.size();
+				int rc = kc_wait_block(c, *pick);
 				if (rc) return rc;
-				b->owned = true;
-				b->used = 0;
-				p->cur = b;
+				pick->owned = true;
+				pick->used = 0;
+				p->cur = pick;
 				return VAFGPU_OK;
 			}
 		}
@@ -247,9 +260,9 @@ int kc_ensure_room(kcgpu_producer *p, size_t need)
 
 /* lock held.  Submit what the context's own producer has staged (other producers submit
  * their own when they are flushed or destroyed) and wait for everything in flight. */
-int kc_sync_one(kcgpu_ctx *c)
+int kc_sync_one(kcgpu_ctx *c, bool submit_staged = true)
 {
-	int rc = c->def ? kc_submit_current(c->def) : VAFGPU_OK;
+	int rc = c->def && submit_staged ? kc_submit_current(c->def) : VAFGPU_OK;
 	if (rc) return rc;
 	KCU(c, cudaSetDevice(c->device));
 	for (KcBlock *b : c->blocks) {
@@ -262,10 +275,10 @@ int kc_sync_one(kcgpu_ctx *c)
 }
 
 /* every member: wait for what was filed, empty the lists into the table, wait for that */
-int kc_flush_group(kcgpu_ctx *c)
+int kc_flush_group(kcgpu_ctx *c, bool submit_staged)
 {
 	for (kcgpu_ctx *m : c->group) {
-		int rc = kc_sync_one(m);
+		int rc = kc_sync_one(m, submit_staged);
 		if (rc) {
 			if (m != c) c->err = m->err;
 			return rc;

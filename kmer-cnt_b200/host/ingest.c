@@ -133,9 +133,11 @@ static int engine_failed(pool_t *pl)
 }
 
 /* one whole file: the step-0 loop of vaf-counter.c:486-517 feeding the engine.  The reference
- * closes a block when it holds >= block_len bases or the reader returns < 0, and stops the file
- * when a block comes out empty; reproduced so that a malformed FASTQ record ends (or does not
- * end) the file at the same place. */
+ * closes a block when it holds >= block_len bases or the reader returns < 0.  An empty block
+ * retires the pipeline worker that read it (kthread.c:97-125: a worker leaves when ITS step 0
+ * returns NULL), the other two of kt_pipeline(3, ...) go on calling step 0 in order, so the file
+ * ends with the third empty block; reproduced so that a malformed FASTQ record ends (or does
+ * not end) the file at the same place.  kc-c4.c:133-183 is the same loop. */
 static int run_sequential(pool_t *pl, file_t *f, void *prod)
 {
 	fastx_t *fx = fastx_open(f->fn);
@@ -143,6 +145,7 @@ static int run_sequential(pool_t *pl, file_t *f, void *prod)
 	double t0 = now();
 	if (!fx) return 0; /* vaf-counter.c:557: silently skipped */
 	f->out->opened = 1;
+	int lives = 3; /* the three workers of kt_pipeline(3, ...), see below */
 	for (;;) {
 		long l, sum_len = 0;
 		const char *s;
@@ -157,7 +160,7 @@ static int run_sequential(pool_t *pl, file_t *f, void *prod)
 			bases += (uint64_t)l;
 			if (sum_len >= pl->block_len) break;
 		}
-		if (sum_len == 0) break;
+		if (sum_len == 0 && --lives == 0) break;
 	}
 	fastx_close(fx);
 	add_totals(pl, f, seqs, bases, t0, now());

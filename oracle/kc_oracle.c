@@ -136,13 +136,29 @@ void kco_add_read(kco_t *o, const char *seq, long len)
 	for (long i = 0; i < n; ++i) kco_add_hashed(o, o->scratch[i]);
 }
 
-int kco_add_file(kco_t *o, const char *fn)
+/* kc-c4.c:133-183 step 0: a block is read until it holds block_len bases or the reader
+ * reports anything below zero -- end of input, or a FASTQ record whose quality does not fit
+ * (kseq.h:230).  A bad record in the middle of a block only closes the block: the next one goes
+ * on behind it.  An empty block retires the pipeline worker that read it (kthread.c:97-125: a
+ * worker leaves when ITS step 0 returns NULL) while the other workers of kt_pipeline(3, ...)
+ * (kc-c4.c:173) go on calling step 0, in order: the file ends with the third empty block. */
+int kco_add_file(kco_t *o, const char *fn, long block_len)
 {
 	fastx_t *fx = fastx_open(fn);
 	const char *seq;
 	long len;
 	if (!fx) return -1;
-	while ((len = fastx_next(fx, &seq)) >= 0) kco_add_read(o, seq, len);
+	int lives = 3;
+	for (;;) {
+		long sum_len = 0;
+		while ((len = fastx_next(fx, &seq)) >= 0) {
+			if (len < o->k) continue;
+			kco_add_read(o, seq, len);
+			sum_len += len;
+			if (sum_len >= block_len) break;
+		}
+		if (sum_len == 0 && --lives == 0) break;
+	}
 	fastx_close(fx);
 	return 0;
 }

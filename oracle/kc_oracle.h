@@ -42,8 +42,10 @@ void kco_destroy(kco_t *o);
 void kco_add_read(kco_t *o, const char *seq, long len);
 /* one hashed k-mer, as the insert step sees it                (kc-c4.c:116-128) */
 void kco_add_hashed(kco_t *o, uint64_t h);
-/* whole file through the FASTA/FASTQ reader; -1 if it cannot be opened (kc-c4.c:166) */
-int kco_add_file(kco_t *o, const char *fn);
+/* whole file through the FASTA/FASTQ reader, in blocks of block_len bases as kc-c4.c:133-153
+ * reads it (that decides where a malformed FASTQ record ends the file); -1 if it cannot be
+ * opened (kc-c4.c:166) */
+int kco_add_file(kco_t *o, const char *fn, long block_len);
 /* hist[c] = distinct k-mers seen min(c, 255) times            (kc-c4.c:186-215) */
 void kco_hist(const kco_t *o, uint64_t hist[256]);
 uint64_t kco_distinct(const kco_t *o);

@@ -331,9 +331,12 @@ int vo_count_file(const vo_map_t *m, int k, const char *fn, int simd, int n_thre
 		if (USED(m, i) && m->val[i] + 1 > n_counts) n_counts = m->val[i] + 1;
 	n_counts = (n_counts + 1) & ~(size_t)1;
 	if (n_threads > 1) priv = (uint32_t *)calloc((size_t)n_threads * n_counts, 4);
+	int lives = 3; /* kt_pipeline(3, ...), vaf-counter.c:568 */
 	for (;;) {
 		/* one block: vaf-counter.c:486-517.  Any negative return (end of input or a bad
-		 * FASTQ record) closes the block; an empty block ends the file. */
+		 * FASTQ record) closes the block.  An empty block retires the pipeline worker that
+		 * read it (kthread.c:97-125: a worker leaves when ITS step 0 returns NULL); the other
+		 * workers go on calling step 0, in order, so the file ends with the third empty block. */
 		size_t n = 0;
 		long l, sum_len = 0;
 		const char *s;
@@ -353,7 +356,10 @@ int vo_count_file(const vo_map_t *m, int k, const char *fn, int simd, int n_thre
 			if (st) st->n_reads++, st->n_bases += (uint64_t)l;
 			if (sum_len >= block_len) break;
 		}
-		if (sum_len == 0) break;
+		if (sum_len == 0) {
+			if (--lives == 0) break;
+			continue;
+		}
 		if (n_threads == 1) {
 			for (size_t i = 0; i < n; ++i) {
 				uint64_t nk = vo_count_read(m, k, seq[i], len[i], simd, counts);

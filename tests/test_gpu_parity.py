@@ -253,3 +253,25 @@ def test_cli_parallel_ingest_is_byte_identical(tmp_path, oracle, lib, threads):
     assert open(out).read() == vafgpu.format_vaf(pats, want)
     n_ok = sum(1 for x in reads if len(x) >= 21)
     assert ("Sequences processed:   %d" % n_ok).encode() in r.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_cli_malformed_records_end_the_file_where_the_reference_does(tmp_path, oracle, lib, threads):
+    """a FASTQ record with a short quality string closes the block being read; three of them at
+    block starts end the file (the three workers of kt_pipeline, kthread.c:97-125)"""
+    rng = np.random.default_rng(12)
+    pats = util.make_patterns(rng, 50, 21)
+    reads = util.make_reads(rng, pats, 21, 400, plant=0.9, n_rate=0)
+    pf, fq = str(tmp_path / "p.txt"), str(tmp_path / "bad.fq")
+    util.write_patterns(pf, pats)
+    for bad in ({10, 22, 34}, {57, 59, 300, 302, 304}):
+        with open(fq, "wb") as fh:
+            for i, r in enumerate(reads):
+                fh.write(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * (len(r) - 3 if i in bad else len(r))))
+        for block in ("1500", "1000", "10000000"):
+            a, b = str(tmp_path / "cli.vaf"), str(tmp_path / "orc.vaf")
+            subprocess.run([os.path.join(util.PKG, "vaf-counter"), "-k", "21", "-t", str(threads), "-b", block, "-p", pf, "-o", a, fq],
+                           check=True, capture_output=True, env=dict(os.environ, VAFGPU_SLICE_BYTES="20000"))
+            subprocess.run([os.path.join(util.ORACLE_DIR, "vaf_oracle"), "-k", "21", "-t", "1", "-b", block, "-p", pf, "-o", b, fq],
+                           check=True, capture_output=True)
+            assert open(a, "rb").read() == open(b, "rb").read(), (sorted(bad), block)

@@ -354,6 +354,24 @@ def test_cli_parallel_readers(kco, lib, tmp_path):
             assert out == kcgpu.format_histogram(want), (k, t)
 
 
+def test_cli_malformed_records_end_the_file_where_the_reference_does(kco, lib, tmp_path):
+    """kc-c4.c:139-156 under kt_pipeline(3, ...): a bad FASTQ record closes the block being read,
+    the third empty block ends the file; where that is depends on -b"""
+    rng = np.random.default_rng(8)
+    reads = util.make_genome_reads(rng, 20000, 600, n_rate=0)
+    fq = str(tmp_path / "bad.fq")
+    for bad in ({10, 22, 34}, {57, 59, 300, 302, 304}):
+        with open(fq, "wb") as fh:
+            for i, r in enumerate(reads):
+                fh.write(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * (len(r) - 3 if i in bad else len(r))))
+        for block in (1500, 1000, 10_000_000):
+            want, _, _ = kco.count_file(fq, 21, block)
+            for t in (1, 4):
+                out = subprocess.run([KC_CLI, "-k", "21", "-t", str(t), "-b", str(block), fq], check=True, capture_output=True,
+                                     env=dict(os.environ, VAFGPU_SLICE_BYTES="20000")).stdout.decode()
+                assert out == kcgpu.format_histogram(want), (sorted(bad), block, t)
+
+
 def test_cli_usage_and_errors(lib, tmp_path):
     r = subprocess.run([KC_CLI], capture_output=True)
     assert r.returncode == 1 and r.stderr.startswith(b"Usage: kc-c4 [options] <in.fa>\n")

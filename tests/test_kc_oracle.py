@@ -92,6 +92,44 @@ def test_histogram_matches_live_reference(kco, tmp_path):
                 assert np.array_equal(hist, hist2)
 
 
+def malformed_fastq(path, reads, bad_at):
+    """a FASTQ whose records number bad_at[...] have a quality string that is too short (kseq.h:230)"""
+    with open(path, "wb") as fh:
+        for i, r in enumerate(reads):
+            q = b"I" * (len(r) - 3 if i in bad_at and len(r) > 3 else len(r))
+            fh.write(b"@r%d\n%s\n+\n%s\n" % (i, r, q))
+
+
+@pytest.mark.skipif(not os.path.exists(KC_REF), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_malformed_record_closes_the_block_not_the_file(kco, tmp_path):
+    """kc-c4.c:139-156: a record the reader rejects ends the block being read; the file goes on
+    behind it unless that block is empty.  Where that is depends on -b."""
+    rng = np.random.default_rng(8)
+    reads = util.make_genome_reads(rng, 20000, 600, n_rate=0)  # 150 bases each: -b 1500 closes a block every 10 reads
+    fn = str(tmp_path / "bad.fq")
+    # a bad record swallows the header of the next one as quality, so it costs two reads.  Records
+    # 10, 22 and 34 are the first of their block at -b 1500: three empty blocks, the three workers
+    # of kt_pipeline(3, ...) retire one after the other and the file ends there; at any other
+    # block size the three bad records cost nothing but themselves and their successors
+    malformed_fastq(fn, reads, {10, 22, 34})
+    got = {}
+    for b in (1500, 1000, 30000, 10_000_000):
+        ref = subprocess.run([KC_REF, "-k", "21", "-b", str(b), "-t", "2", fn], check=True, capture_output=True).stdout.decode()
+        hist, n_inst, _ = kco.count_file(fn, 21, b)
+        assert kcgpu.format_histogram(hist) == ref, b
+        got[b] = n_inst
+    assert got[1500] == 30 * 130
+    assert got[1000] == got[30000] == got[10_000_000] == 594 * 130
+    # bad records right behind each other (every second one, since each swallows its successor):
+    # each but the first opens an empty block, whatever -b is
+    malformed_fastq(fn, reads, {57, 59, 300, 302, 304})
+    for b in (1000, 10_000_000):
+        ref = subprocess.run([KC_REF, "-k", "21", "-b", str(b), fn], check=True, capture_output=True).stdout.decode()
+        hist, n_inst, _ = kco.count_file(fn, 21, b)
+        assert kcgpu.format_histogram(hist) == ref, b
+        assert n_inst == (300 - 4) * 130  # 57..60 lost, then the file ends at 304: the third empty block
+
+
 def test_saturation_and_top_bin(kco):
     """a k-mer seen more than 1023 times stays at 1023 (kc-c4.c:125) and lands in bin 255"""
     hist, n_inst, n_dist = kco.count_reads([b"A" * 2000], 11)

@@ -147,3 +147,30 @@ def test_live_reference_agrees_on_a_fresh_synthetic_case(tmp_path):
         subprocess.run([os.path.join(util.ORACLE_DIR, "vaf_oracle"), "-k", "21", "-t", t, "-p", pre + ".pat", "-o", pre + f".orc{t}.vaf", pre + ".fq"],
                        check=True, capture_output=True)
         assert open(pre + f".ref{t}.vaf", "rb").read() == open(pre + f".orc{t}.vaf", "rb").read()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref is only built where /root/reference is mounted")
+def test_live_reference_agrees_on_malformed_records_at_block_starts(tmp_path):
+    """kthread.c:97-125: a pipeline worker leaves when ITS step 0 returns NULL; the two others of
+    kt_pipeline(3, ...) (vaf-counter.c:568) go on reading, so the file ends with the THIRD empty
+    block.  A FASTQ record with a short quality string returns -2 (kseq.h:230), swallows the next
+    header, and -- when it is the first record of a block -- makes that block empty."""
+    rng = np.random.default_rng(12)
+    pats = util.make_patterns(rng, 50, 21)
+    reads = util.make_reads(rng, pats, 21, 400, plant=0.9, n_rate=0)  # 150 bases each: -b 1500 = 10 reads
+    pf, fq = str(tmp_path / "p.txt"), str(tmp_path / "bad.fq")
+    util.write_patterns(pf, pats)
+    totals = {}
+    for bad in ({10, 22, 34}, {10, 22}, {57, 59, 300, 302, 304}):
+        with open(fq, "wb") as fh:
+            for i, r in enumerate(reads):
+                fh.write(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * (len(r) - 3 if i in bad else len(r))))
+        for block in ("1500", "1000", "10000000"):
+            a, b = str(tmp_path / "ref.vaf"), str(tmp_path / "orc.vaf")
+            for exe, out in ((os.path.join(util.REF_DIR, "vaf-counter"), a), (os.path.join(util.ORACLE_DIR, "vaf_oracle"), b)):
+                subprocess.run([exe, "-k", "21", "-t", "2", "-b", block, "-p", pf, "-o", out, fq], check=True, capture_output=True)
+            assert open(a, "rb").read() == open(b, "rb").read(), (sorted(bad), block)
+            totals[(min(bad), len(bad), block)] = sum(int(l.split("\t")[7]) for l in open(a).read().splitlines()[2:])
+    # three bad block starts end the file at -b 1500 and nowhere else; two do not
+    assert totals[(10, 3, "1500")] < totals[(10, 3, "1000")] == totals[(10, 3, "10000000")]
+    assert totals[(10, 2, "1500")] == totals[(10, 2, "10000000")]

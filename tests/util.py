@@ -313,7 +313,7 @@ class KcOracle:
         lib.kco_destroy.argtypes = [C.c_void_p]
         lib.kco_add_read.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
         lib.kco_add_hashed.argtypes = [C.c_void_p, C.c_uint64]
-        lib.kco_add_file.argtypes = [C.c_void_p, C.c_char_p]
+        lib.kco_add_file.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
         lib.kco_hist.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         lib.kco_distinct.argtypes = [C.c_void_p]
         lib.kco_distinct.restype = C.c_uint64
@@ -340,9 +340,9 @@ class KcOracle:
             self.lib.kco_add_read(o, r, len(r))
         return self._finish(o)
 
-    def count_file(self, fn: str, k: int) -> Tuple[np.ndarray, int, int]:
+    def count_file(self, fn: str, k: int, block_len: int = 10_000_000) -> Tuple[np.ndarray, int, int]:
         o = self.lib.kco_create(k)
-        assert self.lib.kco_add_file(o, fn.encode()) == 0, fn
+        assert self.lib.kco_add_file(o, fn.encode(), block_len) == 0, fn
         return self._finish(o)
 
     def count_hashed(self, hashed: np.ndarray, k: int) -> Tuple[np.ndarray, int, int]:

@@ -176,3 +176,51 @@ def test_owner_split_partitions_the_histogram(kco):
                 total += h
                 dist += d
             assert np.array_equal(total, whole) and dist == n_dist
+
+
+# ---------------------------------------------------------------------------------------------
+# the kernels' bookkeeping on the host (tests/cpu_sim/kc_sim.cpp over csrc/kcgpu_kernels.cuh)
+
+
+@pytest.fixture(scope="module")
+def ksim():
+    return util.KcSim()
+
+
+def test_header_hash_is_the_reference_hash(kco, ksim):
+    for k, x, want in kat_rows("hash64"):
+        assert ksim.lib.sim_kc_hash64(int(x, 16), int(k)) == int(want, 16)
+
+
+def test_geometry_of_the_allocation(ksim):
+    """table, lists, cursors and the inbox's cursor follow each other without overlap, the two
+    halves of the list area (several owners) end where the cursors begin, and the tag of any
+    2k-bit hash fits beside the 10-bit count once the region bits are taken off"""
+    for k in range(1, 32):
+        need = ksim.geometry(k, 4096, 64, 0)["need_bits"]
+        assert 2 * k - need <= 54 and (need == 0 or 2 * k - need == 54)
+        for table_bits in (12, 21, 27, 33, 36):
+            for rb in sorted({need, min(max(need, table_bits - 21), 20), 12} & set(range(need, table_bits - 3))):
+                for cap in (64, 96, 1 << 20):
+                    g = ksim.geometry(k, 1 << table_bits, cap, rb)
+                    assert g["lists"] == 8 << table_bits
+                    assert g["cursors"] == g["lists"] + 8 * (cap << rb)
+                    assert g["inbox_cursor"] == g["cursors"] + 256 * (1 << rb)
+                    assert g["alloc"] == g["inbox_cursor"] + 256
+                    assert g["inbox_cap"] == (cap << rb) // 2
+                    assert g["lists2_end"] == g["cursors"]
+
+
+@pytest.mark.parametrize("n_parts", [1, 2, 3, 8, 16])
+def test_push_route_flush_on_the_host(kco, ksim, n_parts):
+    """the several-owner form step by step on the host: inbox, region lists, table -- with lists
+    that take everything and with lists so short that most k-mers go straight to the table"""
+    rng = np.random.default_rng(40 + n_parts)
+    reads = util.make_genome_reads(rng, 8000, 500, jitter=50, lower_rate=0.05, repeat=5)
+    for k in (5, 21, 31):
+        want, n_inst, _ = kco.count_reads(reads, k)
+        stream = util.pack_stream_strict(reads, k)
+        for cap in (1 << 15, 64):
+            hist, lost, n_direct = ksim.count(k, n_parts, 18, cap, stream)
+            assert lost == 0 and np.array_equal(hist, want), (k, cap)
+            assert (n_direct > 0) == (cap == 64), (k, cap, n_direct)

@@ -352,6 +352,42 @@ class KcOracle:
         return self._finish(o)
 
 
+def build_kc_sim() -> str:
+    """tests/_build/libkc_sim.so: host emulation of the counting mode's bookkeeping (test-only)."""
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    out = os.path.join(BUILD_DIR, "libkc_sim.so")
+    src = os.path.join(ROOT, "tests", "cpu_sim", "kc_sim.cpp")
+    deps = [src, os.path.join(PKG, "csrc", "kcgpu_kernels.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + cuda_inc, "-o", out, src], check=True)
+    return out
+
+
+class KcSim:
+    def __init__(self):
+        lib = C.CDLL(build_kc_sim())
+        lib.sim_kc_geometry.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+        lib.sim_kc_hash64.argtypes = [C.c_uint64, C.c_int]
+        lib.sim_kc_hash64.restype = C.c_uint64
+        lib.sim_kc_count.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.sim_kc_count.restype = C.c_uint64
+        self.lib = lib
+
+    def geometry(self, k, n_slots, list_cap, region_bits):
+        out = (C.c_uint64 * 7)()
+        self.lib.sim_kc_geometry(k, n_slots, list_cap, region_bits, out)
+        return dict(zip(("need_bits", "alloc", "lists", "cursors", "inbox_cursor", "inbox_cap", "lists2_end"), map(int, out)))
+
+    def count(self, k, n_parts, table_bits, list_cap, stream: np.ndarray):
+        hist = np.zeros(256, dtype=np.uint64)
+        nd = C.c_uint64()
+        lost = self.lib.sim_kc_count(k, n_parts, table_bits, list_cap, stream.ctypes.data, stream.size,
+                                     hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(nd))
+        return hist, int(lost), int(nd.value)
+
+
 def pack_stream_strict(reads: Sequence[bytes], k: int) -> np.ndarray:
     """What kcgpu_add_read builds in a staging block (strict base table everywhere)."""
     return pack_stream(reads, k, simd_rule=False)

@@ -277,7 +277,8 @@ int main(int argc, char *argv[])
 	if (n_feed > 8) n_feed = 8;
 	if (n_feed > db->n) n_feed = db->n;
 	if (n_feed < 1) n_feed = 1;
-	if (vafgpu_create(&ctx, k, cand.keys, vals, cand.n, n_pairs, 0, n_feed + 2, 0, VAFGPU_F_STRICT_BYTES) != VAFGPU_OK) {
+	/* one GPU: a human genome is a second of kernel time, more devices only add start-up */
+	if (vafgpu_create(&ctx, k, cand.keys, vals, cand.n, n_pairs, 0, n_feed + 2, 1, VAFGPU_F_STRICT_BYTES) != VAFGPU_OK) {
 		fprintf(stderr, "Error: %s\n", vafgpu_strerror(NULL));
 		return 1;
 	}

@@ -39,8 +39,8 @@ extern "C" {
                                         349-427, khashl.h:98,137-150) instead of the
                                         anchor-filter kernel; used as the on-device
                                         verification mode */
-#define VAFGPU_F_HOST_MERGE       2u /* merge per-device counters on the host instead of
-                                        with an NCCL all-reduce                            */
+#define VAFGPU_F_HOST_MERGE       2u /* merge per-device counters through host memory instead
+                                        of over NVLink (peer access is not required then)  */
 #define VAFGPU_F_STRICT_BYTES     4u /* vafgpu_add_read classifies every byte by the strict table
                                         (vaf-counter.c:73-90 = snp-pattern-gen.c:30-47): what a
                                         build without SSSE3 does, and what snp-pattern-gen's
@@ -64,6 +64,11 @@ typedef struct vafgpu_stats {
 	int      anchor_len;    /* L: anchor length in bases                                   */
 	uint32_t filter_bytes;  /* shared-memory filter size                                   */
 	uint32_t table_slots;   /* slots of the L2-resident exact table                        */
+	/* which form of the anchor kernel this panel selected (all 0 in recipe mode) */
+	int      filter_canon;    /* 1: strand-symmetric filter keys (large panels)              */
+	int      lookup_deferred; /* 1: deferred two-level lookup (large panels, stride >= 4)    */
+	int      kernel_threads;  /* CTA size of the instantiation                               */
+	uint32_t filter2_bytes;   /* second filter level (L2-resident), 0 if not in use          */
 } vafgpu_stats;
 
 /*
@@ -121,7 +126,9 @@ int vafgpu_producer_destroy(vafgpu_producer *producer); /* flushes first */
  * other than A,C,G,T,U (either case) end a k-mer.  The buffer is copied to a staging
  * block (or used in place if it is pinned) and processed asynchronously; n_bytes may
  * exceed block_bytes, in which case it is cut at separators.  n_reads/n_bases are only
- * added to the statistics.
+ * added to the statistics.  A page-locked buffer is read by the copy engines AFTER this
+ * call returns: it must stay valid and unmodified until vafgpu_finish() (or vafgpu_reset())
+ * has returned.  Pageable memory has been copied when the call returns.
  */
 int vafgpu_submit_stream(vafgpu_ctx *ctx, const char *bytes, size_t n_bytes,
                          uint64_t n_reads, uint64_t n_bases);
@@ -137,8 +144,11 @@ int vafgpu_count_device(vafgpu_ctx *ctx, int device, const void *d_bytes, size_t
                         uint32_t *d_counts, void *stream);
 
 /*
- * Drain all streams, merge the per-device counters (one ncclAllReduce of 2*n_patterns
- * uint32 over NVLink when more than one device is in use) and copy them out.  Replaces
+ * Drain all streams and copy the counters out.  With several devices there is nothing to
+ * merge: every device's kernels add their hits straight into device 0's vector through
+ * NVLink peer memory (hits are rare and the additions need no answer), which stands in
+ * for the all-reduce of a one-vector-per-device design; devices without peer access or
+ * native peer atomics (or VAFGPU_F_HOST_MERGE) keep a vector each, summed here.  Replaces
  * the end of kt_pipeline plus the shared-memory atomics of worker_lookup
  * (vaf-counter.c:473-477): counts[2i] / counts[2i+1] are what the reference leaves in
  * pattern_t.ref_count / alt_count.  Counters keep accumulating across calls (several
@@ -147,6 +157,17 @@ int vafgpu_count_device(vafgpu_ctx *ctx, int device, const void *d_bytes, size_t
 int vafgpu_finish(vafgpu_ctx *ctx, uint32_t *counts, vafgpu_stats *stats);
 
 int vafgpu_reset(vafgpu_ctx *ctx);   /* zero counters and statistics */
+
+/*
+ * One counter vector for several PROCESSES (one process per GPU, e.g. under torchrun):
+ * the owner exports a CUDA IPC handle of its vector (handle_bytes >= 64), the others attach
+ * it, after which their kernels add into the owner's vector over NVLink and their own
+ * vafgpu_finish() only drains (it returns zeros); the owner reads the totals with
+ * vafgpu_finish() once every process has drained (a barrier of the caller's).  The devices
+ * must be NVLink peers with native atomics.  Stands in for the all-reduce across ranks.
+ */
+int vafgpu_export_counters(vafgpu_ctx *ctx, void *handle, size_t handle_bytes);
+int vafgpu_attach_counters(vafgpu_ctx *ctx, const void *handle, size_t handle_bytes);
 void vafgpu_destroy(vafgpu_ctx *ctx);
 
 /* message for the last error on ctx (ctx may be NULL: error of the last failed create) */

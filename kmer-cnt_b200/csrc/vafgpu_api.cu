@@ -1,19 +1,19 @@
 /*
  * vafgpu_api.cu -- the C ABI of include/vafgpu.h: contexts, pinned staging blocks, one
- * stream per block for copy/compute overlap, round-robin over the devices, one NCCL
- * all-reduce of the counters at the end.  Host logic only; the kernels are in
- * vafgpu_kernels.cu.
+ * stream per block for copy/compute overlap, round-robin over the devices.  With several
+ * devices every kernel adds its hits straight into ONE counter vector (device 0's, or one
+ * attached from another process) over NVLink peer memory, so there is no merge step and no
+ * collective.  Host logic only; the kernels are in vafgpu_kernels.cu.
  */
 #include "../../include/vafgpu.h"
 
 #include <cuda_runtime.h>
-#include <dlfcn.h>
-#include <nccl.h> /* types only; the library is loaded at run time when it is needed */
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -50,22 +50,13 @@ struct Device {
 	vg_slot_t *d_slots = nullptr;
 	uint64_t *d_rkeys = nullptr;
 	uint32_t *d_rvals = nullptr;
-	uint32_t *d_counts = nullptr;
+	uint32_t *d_counts = nullptr;  /* this device's own counter vector                          */
+	uint32_t *counts_to = nullptr; /* where its kernels add: d_counts, device 0's vector mapped
+	                                  as peer memory, or a vector attached from another process */
+	void *attached = nullptr;      /* the mapping cudaIpcOpenMemHandle made on this device       */
 	unsigned long long *d_stats = nullptr;
 	cudaStream_t main_stream = nullptr;
 	std::vector<Block> blocks;
-	ncclComm_t comm = nullptr;
-};
-
-struct Nccl {
-	void *lib = nullptr;
-	ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
-	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
-	                          cudaStream_t) = nullptr;
-	ncclResult_t (*GroupStart)() = nullptr;
-	ncclResult_t (*GroupEnd)() = nullptr;
-	const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
 } // namespace
@@ -80,8 +71,10 @@ struct vafgpu_ctx {
 	uint32_t filter_words = 0, filter2_words = 0, n_buckets = 0, rbits = 0;
 	bool canon = false, defer = false;
 	std::vector<Device> devs;
-	Nccl nccl;
+	bool host_merge = false; /* counters stay per device and are summed on the host */
+	bool attached = false;   /* the counters live in another context (vafgpu_attach_counters) */
 	std::mutex mu;    /* guards seq, block ownership, st and err: several producers may run */
+	std::condition_variable block_free; /* a producer handed a staging block back */
 	uint64_t seq = 0; /* blocks handed out so far: round-robin over devices, then buffers */
 	vafgpu_stats st{};
 	std::string err;
@@ -143,10 +136,10 @@ int acquire(vafgpu_producer *p)
 	const size_t nd = c->devs.size();
 	Block *b = nullptr;
 	int di = 0;
-	for (;;) {
-		{
-			std::lock_guard<std::mutex> lk(c->mu);
-			const size_t total = nd * c->devs[0].blocks.size();
+	{
+		std::unique_lock<std::mutex> lk(c->mu);
+		const size_t total = nd * c->devs[0].blocks.size();
+		for (;;) {
 			for (size_t tries = 0; tries < total && !b; ++tries) {
 				di = (int)(c->seq % nd);
 				Device &d = c->devs[di];
@@ -157,9 +150,9 @@ int acquire(vafgpu_producer *p)
 					b = &cand;
 				}
 			}
+			if (b) break;
+			c->block_free.wait(lk); /* more producers than blocks: wait for one to be submitted */
 		}
-		if (b) break;
-		std::this_thread::yield(); /* more producers than blocks: wait for one to be submitted */
 	}
 	int rc = wait_block(c, *b);
 	if (rc) return rc;
@@ -174,7 +167,7 @@ ScanArgs scan_args(const vafgpu_ctx *c, const Device &d, const uint8_t *bytes, s
 	ScanArgs a{};
 	a.bytes = bytes;
 	a.n_bytes = n;
-	a.counts = counts ? counts : d.d_counts;
+	a.counts = counts ? counts : d.counts_to;
 	a.stats = d.d_stats;
 	a.k = c->k;
 	a.stride = c->plan.stride;
@@ -219,13 +212,16 @@ int submit_current(vafgpu_producer *p)
 		CU(c, launch(c, d, scan_args(c, d, b->d, n, nullptr), b->stream));
 		CU(c, cudaEventRecord(b->e2, b->stream));
 	}
-	std::lock_guard<std::mutex> lk(c->mu);
-	if (b->used) {
-		b->in_flight = true;
-		c->st.n_blocks++;
-		c->st.n_bytes += n;
+	{
+		std::lock_guard<std::mutex> lk(c->mu);
+		if (b->used) {
+			b->in_flight = true;
+			c->st.n_blocks++;
+			c->st.n_bytes += n;
+		}
+		b->owned = false;
 	}
-	b->owned = false;
+	c->block_free.notify_one();
 	return VAFGPU_OK;
 }
 
@@ -237,26 +233,6 @@ int ensure_room(vafgpu_producer *p, size_t need)
 		if (rc) return rc;
 	}
 	if (!p->cur) return acquire(p);
-	return VAFGPU_OK;
-}
-
-int load_nccl(vafgpu_ctx *c)
-{
-	Nccl &n = c->nccl;
-	if (n.lib) return VAFGPU_OK;
-	n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-	if (!n.lib) n.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-	if (!n.lib) return fail(c, VAFGPU_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
-#define SYM(field, name)                                                          \
-	*(void **)(&n.field) = dlsym(n.lib, name);                                    \
-	if (!n.field) return fail(c, VAFGPU_ENCCL, "libnccl lacks %s", name);
-	SYM(CommInitAll, "ncclCommInitAll")
-	SYM(CommDestroy, "ncclCommDestroy")
-	SYM(AllReduce, "ncclAllReduce")
-	SYM(GroupStart, "ncclGroupStart")
-	SYM(GroupEnd, "ncclGroupEnd")
-	SYM(GetErrorString, "ncclGetErrorString")
-#undef SYM
 	return VAFGPU_OK;
 }
 
@@ -273,6 +249,7 @@ void destroy_device(Device &d)
 		if (b.stream) cudaStreamDestroy(b.stream);
 	}
 	if (d.main_stream) cudaStreamDestroy(d.main_stream);
+	if (d.attached) cudaIpcCloseMemHandle(d.attached);
 	cudaFree(d.d_filter);
 	cudaFree(d.d_buckets);
 	cudaFree(d.d_filter2);
@@ -373,10 +350,10 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			lap("context");
 			CU(c, kernels_make_policy(&d.keep_policy));
 			lap("module load + policy kernel");
-			if (const char *env = getenv("VAFGPU_L2_PERSIST_MB")) { /* tuning knob: L2 set-aside for evict-last lines */
-				size_t want = (size_t)atoi(env) << 20;
-				if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-				CU(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+			if (!(flags & VAFGPU_F_REFERENCE_RECIPE)) {
+				ScanArgs form{};
+				form.stride = c->plan.stride, form.len = c->plan.len, form.canon = c->canon, form.defer = c->defer;
+				CU(c, kernels_prepare(form)); /* dynamic shared-memory opt-in of the instantiation this panel selects */
 			}
 			CU(c, cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
 			CU(c, cudaMalloc(&d.d_filter, at.filter.size() * 4));
@@ -395,6 +372,7 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			CU(c, cudaMemcpy(d.d_rvals, rt.vals.data(), rt.vals.size() * 4, cudaMemcpyHostToDevice));
 			CU(c, cudaMemset(d.d_counts, 0, c->n_counts * 4));
 			CU(c, cudaMemset(d.d_stats, 0, ST_N * sizeof(unsigned long long)));
+			d.counts_to = d.d_counts;
 			lap("tables to device");
 			d.blocks.resize(n_buffers);
 			for (Block &b : d.blocks) {
@@ -409,16 +387,28 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			return VAFGPU_OK;
 		}();
 	}
-	if (rc == VAFGPU_OK && n_devices > 1 && !(flags & VAFGPU_F_HOST_MERGE)) {
-		rc = load_nccl(c);
-		if (rc == VAFGPU_OK) {
-			std::vector<ncclComm_t> comms(n_devices);
-			std::vector<int> ids(n_devices);
-			for (int i = 0; i < n_devices; ++i) ids[i] = i;
-			ncclResult_t nr = c->nccl.CommInitAll(comms.data(), n_devices, ids.data());
-			if (nr != ncclSuccess) rc = fail(c, VAFGPU_ENCCL, "ncclCommInitAll: %s", c->nccl.GetErrorString(nr));
-			else for (int i = 0; i < n_devices; ++i) c->devs[i].comm = comms[i];
+	/* Several devices: every kernel adds into device 0's counter vector through NVLink peer
+	 * memory (hits are rare -- tens of thousands per 10^10 bases -- and RED.ADD needs no answer),
+	 * so the result is final when the streams have drained.  Without peer access between all
+	 * devices and device 0 the counters stay per device and are summed through host memory. */
+	c->host_merge = (flags & VAFGPU_F_HOST_MERGE) != 0;
+	if (rc == VAFGPU_OK && n_devices > 1 && !c->host_merge) {
+		for (int i = 1; i < n_devices && !c->host_merge; ++i) {
+			int can = 0, atomics = 0;
+			if (cudaDeviceCanAccessPeer(&can, i, 0) != cudaSuccess || !can) c->host_merge = true;
+			else if (cudaDeviceGetP2PAttribute(&atomics, cudaDevP2PAttrNativeAtomicSupported, i, 0) != cudaSuccess || !atomics)
+				c->host_merge = true;
 		}
+		for (int i = 1; i < n_devices && !c->host_merge; ++i) {
+			cudaSetDevice(i);
+			cudaError_t pe = cudaDeviceEnablePeerAccess(0, 0);
+			if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+			else if (pe != cudaSuccess) c->host_merge = true;
+		}
+		cudaGetLastError();
+		if (!c->host_merge)
+			for (int i = 1; i < n_devices; ++i) c->devs[i].counts_to = c->devs[0].d_counts;
+		lap("peer access");
 	}
 	if (rc != VAFGPU_OK) {
 		g_create_error = c->err;
@@ -430,6 +420,13 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	c->st.anchor_len = c->plan.len;
 	c->st.filter_bytes = c->filter_words * 4;
 	c->st.table_slots = 3u * c->n_buckets;
+	if (!(flags & VAFGPU_F_REFERENCE_RECIPE)) {
+		ScanArgs form{};
+		form.stride = c->plan.stride, form.len = c->plan.len, form.canon = c->canon, form.defer = c->defer;
+		c->st.filter_canon = c->canon, c->st.lookup_deferred = c->defer;
+		c->st.kernel_threads = kernels_threads(form);
+		c->st.filter2_bytes = c->defer ? c->filter2_words * 4 : 0;
+	}
 	*out = c;
 	return VAFGPU_OK;
 }
@@ -582,6 +579,7 @@ int vafgpu_submit_stream(vafgpu_ctx *c, const char *bytes, size_t n_bytes, uint6
 			c->st.n_blocks++;
 			c->st.n_bytes += n16;
 		}
+		c->block_free.notify_one();
 		at += advance;
 	}
 	return vafgpu_producer_flush(p);
@@ -614,25 +612,11 @@ int vafgpu_finish(vafgpu_ctx *c, uint32_t *counts, vafgpu_stats *stats)
 		}
 		CU(c, cudaStreamSynchronize(d.main_stream));
 	}
-	const size_t nd = c->devs.size();
 	std::vector<uint32_t> total(c->n_counts, 0);
-	if (nd > 1 && !(c->flags & VAFGPU_F_HOST_MERGE)) {
-		/* the one collective of the path: sum the per-device counter vectors over NVLink */
-		ncclResult_t nr = c->nccl.GroupStart();
-		for (size_t i = 0; i < nd && nr == ncclSuccess; ++i) {
-			Device &d = c->devs[i];
-			nr = c->nccl.AllReduce(d.d_counts, d.d_counts, c->n_counts, ncclUint32, ncclSum, d.comm, d.main_stream);
-		}
-		if (nr == ncclSuccess) nr = c->nccl.GroupEnd();
-		if (nr != ncclSuccess) return fail(c, VAFGPU_ENCCL, "ncclAllReduce: %s", c->nccl.GetErrorString(nr));
-		for (size_t i = 0; i < nd; ++i) {
-			Device &d = c->devs[i];
-			CU(c, cudaSetDevice(d.ordinal));
-			CU(c, cudaStreamSynchronize(d.main_stream));
-			/* every device now holds the total; keep it on device 0 only so that counting can
-			 * go on (more input files) and a later finish() still sums to the right answer */
-			if (i) CU(c, cudaMemset(d.d_counts, 0, c->n_counts * 4));
-		}
+	if (c->attached) {
+		/* the counters live in the context this one is attached to; that one reports them */
+	} else if (!c->host_merge) {
+		/* one vector: every device's kernels have added into it (peer memory); nothing to merge */
 		CU(c, cudaSetDevice(c->devs[0].ordinal));
 		CU(c, cudaMemcpy(total.data(), c->devs[0].d_counts, c->n_counts * 4, cudaMemcpyDeviceToHost));
 	} else {
@@ -659,6 +643,33 @@ int vafgpu_finish(vafgpu_ctx *c, uint32_t *counts, vafgpu_stats *stats)
 	return VAFGPU_OK;
 }
 
+int vafgpu_export_counters(vafgpu_ctx *c, void *handle, size_t handle_bytes)
+{
+	if (!c || !handle || handle_bytes < sizeof(cudaIpcMemHandle_t)) return VAFGPU_EINVAL;
+	if (c->attached || c->host_merge) return fail(c, VAFGPU_ESTATE, "this context does not own a single counter vector");
+	cudaIpcMemHandle_t h;
+	CU(c, cudaSetDevice(c->devs[0].ordinal));
+	CU(c, cudaIpcGetMemHandle(&h, c->devs[0].d_counts));
+	memset(handle, 0, handle_bytes);
+	memcpy(handle, &h, sizeof h);
+	return VAFGPU_OK;
+}
+
+int vafgpu_attach_counters(vafgpu_ctx *c, const void *handle, size_t handle_bytes)
+{
+	if (!c || !handle || handle_bytes < sizeof(cudaIpcMemHandle_t)) return VAFGPU_EINVAL;
+	if (c->attached) return fail(c, VAFGPU_ESTATE, "counters are already attached");
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof h);
+	for (Device &d : c->devs) {
+		CU(c, cudaSetDevice(d.ordinal));
+		CU(c, cudaIpcOpenMemHandle(&d.attached, h, cudaIpcMemLazyEnablePeerAccess));
+		d.counts_to = static_cast<uint32_t *>(d.attached);
+	}
+	c->attached = true;
+	return VAFGPU_OK;
+}
+
 int vafgpu_reset(vafgpu_ctx *c)
 {
 	if (!c) return VAFGPU_EINVAL;
@@ -676,16 +687,17 @@ int vafgpu_reset(vafgpu_ctx *c)
 	c->st.anchor_len = keep.anchor_len;
 	c->st.filter_bytes = keep.filter_bytes;
 	c->st.table_slots = keep.table_slots;
+	c->st.filter_canon = keep.filter_canon;
+	c->st.lookup_deferred = keep.lookup_deferred;
+	c->st.kernel_threads = keep.kernel_threads;
+	c->st.filter2_bytes = keep.filter2_bytes;
 	return VAFGPU_OK;
 }
 
 void vafgpu_destroy(vafgpu_ctx *c)
 {
 	if (!c) return;
-	for (Device &d : c->devs) {
-		if (d.comm && c->nccl.CommDestroy) c->nccl.CommDestroy(d.comm);
-		destroy_device(d);
-	}
+	for (Device &d : c->devs) destroy_device(d);
 	delete c->def;
 	delete c;
 }

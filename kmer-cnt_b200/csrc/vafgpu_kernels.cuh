@@ -41,6 +41,11 @@ struct ScanArgs {
 /* one-time per-device set-up: the L2 evict-last access policy the table loads carry */
 cudaError_t kernels_make_policy(uint64_t *policy);
 
+/* one-time per-device set-up of the anchor kernel instantiation these arguments select (its
+ * dynamic shared-memory opt-in); call with the device current, before the first launch */
+cudaError_t kernels_prepare(const ScanArgs &a);
+int kernels_threads(const ScanArgs &a); /* CTA size of that instantiation */
+
 /* asynchronous launches on `stream` */
 cudaError_t launch_anchor_scan(const ScanArgs &a, int n_sm, cudaStream_t stream);
 cudaError_t launch_recipe_scan(const ScanArgs &a, int n_sm, cudaStream_t stream);

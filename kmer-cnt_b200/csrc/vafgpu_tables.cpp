@@ -127,18 +127,18 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	out.filter_words = nw;
 	out.filter.assign((nw + 3u) & ~3u, 0);
 	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_filter_mask(key, nw);
-	/* second level: 4 words (128 bits) per key, at least a page */
-	const uint32_t nw2 = out.defer ? (uint32_t)std::max<uint64_t>(1024, (uint64_t)out.n_filter_keys * 4) : 4;
+	/* second level: one bit per key in an array of 4 words (128 bits) per key, at least a page,
+	 * between a first and a last word that stay zero (what anchors that failed the first level read) */
+	const uint32_t nw2 = out.defer ? (uint32_t)std::max<uint64_t>(1024, (uint64_t)out.n_filter_keys * 4) + 2u : 4;
 	out.filter2.assign(nw2, 0);
 	if (out.defer)
-		for (uint32_t key : fkeys) out.filter2[vg_filter2_word(key, nw, nw2)] |= vg_filter_mask(key, nw);
+		for (uint32_t key : fkeys) out.filter2[vg_filter2_word(key, nw, nw2)] |= vg_filter2_mask(key, nw);
 
 	/* exact table at <= 1/6 load, buckets of three tags: a full home bucket (a second L2
 	 * round trip) is then rare.  Items are placed in the order they were generated, so a
 	 * bucket's entries are consecutive in the payload array if we emit payloads bucket by
 	 * bucket afterwards. */
-	const char *bf = getenv("VAFGPU_BUCKET_FACTOR"); /* tuning knob */
-	const uint32_t nb = (uint32_t)std::max<uint64_t>(64, (uint64_t)items.size() * (bf ? atoi(bf) : 2));
+	const uint32_t nb = (uint32_t)std::max<uint64_t>(64, (uint64_t)items.size() * 2);
 	out.n_buckets = nb;
 	std::vector<uint32_t> fill(nb, 0), where(items.size());
 	std::vector<uint8_t> more(nb, 0);

@@ -33,7 +33,7 @@ EXPORTS = (
     "vafgpu_finish", "vafgpu_reset", "vafgpu_destroy", "vafgpu_strerror", "vafgpu_plan",
     "vafgpu_canonicalise_read", "vafgpu_version",
     "vafgpu_producer_create", "vafgpu_producer_add_read", "vafgpu_producer_flush",
-    "vafgpu_producer_destroy",
+    "vafgpu_producer_destroy", "vafgpu_export_counters", "vafgpu_attach_counters",
 )
 
 
@@ -44,6 +44,8 @@ class Stats(C.Structure):
         ("n_kmers", C.c_uint64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
         ("n_devices", C.c_int), ("anchor_stride", C.c_int), ("anchor_len", C.c_int),
         ("filter_bytes", C.c_uint32), ("table_slots", C.c_uint32),
+        ("filter_canon", C.c_int), ("lookup_deferred", C.c_int), ("kernel_threads", C.c_int),
+        ("filter2_bytes", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -100,6 +102,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.vafgpu_producer_flush.restype = C.c_int
     lib.vafgpu_producer_destroy.argtypes = [C.c_void_p]
     lib.vafgpu_producer_destroy.restype = C.c_int
+    lib.vafgpu_export_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.vafgpu_export_counters.restype = C.c_int
+    lib.vafgpu_attach_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.vafgpu_attach_counters.restype = C.c_int
     _lib = lib
     return lib
 
@@ -173,6 +179,17 @@ class Engine:
 
     def reset(self) -> None:
         self._check(self._lib.vafgpu_reset(self._h))
+
+    def export_counters(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this engine's counter vector, for attach_counters elsewhere."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.vafgpu_export_counters(self._h, buf, 64))
+        return buf.raw
+
+    def attach_counters(self, handle: bytes) -> None:
+        """From now on this engine's kernels add into the exporting engine's vector (another process)."""
+        buf = C.create_string_buffer(bytes(handle), 64)
+        self._check(self._lib.vafgpu_attach_counters(self._h, buf, 64))
 
     def close(self) -> None:
         if self._h:

@@ -15,7 +15,17 @@ for r in rows[2:]:
             "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
-            "smsp__warps_eligible.avg.per_cycle_active"]
+            "smsp__warps_eligible.avg.per_cycle_active",
+            # L2 by eviction class: the stream is loaded evict-first, the filter/table evict-last, the prefetch evict-normal
+            "lts__t_sectors_lookup_hit.sum", "lts__t_sectors_lookup_miss.sum",
+            "lts__t_sectors_srcunit_tex_op_read_evict_first_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_evict_first_lookup_miss.sum",
+            "lts__t_sectors_srcunit_tex_op_read_evict_last_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_evict_last_lookup_miss.sum",
+            "lts__t_sectors_srcunit_tex_op_read_evict_normal_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_evict_normal_lookup_miss.sum",
+            "lts__t_sectors_srcunit_ltcfabric_op_read_lookup_hit.sum", "lts__t_sectors_srcunit_ltcfabric_op_read_lookup_miss.sum",
+            # atomics (counter updates of the probe): requests and sectors at L2, set accesses at L1
+            "lts__t_requests_srcunit_tex_op_red.sum", "lts__t_requests_srcunit_tex_op_atom.sum",
+            "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum",
+            "nvlrx__bytes.sum", "nvltx__bytes.sum"]
     for k in keys:
         if k in d: print(f"  {k:82s} {d[k]:>16s} {u[k]}")
     st = [(float(v), k) for k, v in d.items() if "warps_issue_stalled" in k and k.endswith("per_issue_active.ratio") and v]

@@ -9,15 +9,22 @@ Workload at N = 1: BASELINE config 2 -- k = 21, the full NGSCheckMate GRCh38 pan
 hg38-length genome), 100 M x 150 bp synthetic reads (15 Gbases) drawn at ~5x from a diploid
 donor that carries the panel's SNPs, 1 % substitutions, 0.5 % N, both strands.  The reads are
 generated on the GPU (torch is plumbing: device memory, RNG, streams, torch.distributed) as the
-stream the engine consumes: reads separated by '\\n'.  One step = one pass of the hot path over
+stream the engine consumes: reads separated by '\n'.  One step = one pass of the hot path over
 the whole resident stream.  N > 1: weak scaling, every rank holds its own 100 M reads, the
-pattern tables are replicated, and the per-SNP counters are summed with one NCCL all-reduce
-per step (the path's only collective).
+pattern tables are replicated, and every rank's kernel adds its hits straight into rank 0's
+counter vector over NVLink (CUDA IPC; vafgpu_export_counters / vafgpu_attach_counters): the
+path's only exchange is fused into the kernel and there is no collective in the step.
 
   value     kernel-only Gbases/s: stream already in HBM, CUDA events on the launch stream
   e2e       the same through the C ABI from page-locked HOST memory: vafgpu_submit_stream
             (H2D copies overlapped with the kernel on the engine's streams) + vafgpu_finish
-            (counter read-back), wall clock around a device synchronize
+            (counter read-back), wall clock around a device synchronize.  The host buffer holds
+            PARSED reads (the boundary of the path): no FASTQ parsing in it
+  e2e_cli   whole process against whole process on one FASTQ file in /dev/shm: this
+            repository's vaf-counter and the unmodified reference's (N = 1 only)
+  strong_scaling  BASELINE config 3: 600 M reads IN TOTAL sharded over the N ranks
+  k_sweep   BASELINE config 4: k = 15 / 21 / 31 on reads with 7.5 % N in runs (N = 1 only)
+  modes.kc  BASELINE config 5 (kc-c4 full counting) on a fixed slice (N = 1 only; tools/kc_bench.py)
   roofline  algorithmic bytes (1 byte per base) per second of the anchor kernel against the
             measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference
@@ -29,6 +36,7 @@ checker (parity of a sample) and as the timed CPU baseline.
 """
 import argparse
 import gzip
+import numpy as np  # noqa: F401  (make_stream)
 import json
 import os
 import re
@@ -73,10 +81,11 @@ def load_cfg2_patterns(tmpdir):
     return path, pats, keys, vals, n_coll
 
 
-def build_donor(torch, pats, genome_len, seed, device):
+def build_donor(torch, pats, genome_len, seed, device, k=None):
     """Two haplotypes of a random genome of `genome_len` bases that carries every pattern's
     21-mer at its (scaled) position: 1/4 of the SNPs hom-ref, 1/2 het, 1/4 hom-alt."""
     import numpy as np
+    K = k or globals()["K"]
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
@@ -110,8 +119,10 @@ def build_donor(torch, pats, genome_len, seed, device):
     return torch.cat([hap0, hap1]), genome_len
 
 
-def make_stream(torch, donor, genome_len, n_reads, seed, device, sub_rate=0.01, n_rate=0.005):
-    """n_reads x 150 bp as the engine's stream: bytes + '\\n' per read, padded to 16."""
+def make_stream(torch, donor, genome_len, n_reads, seed, device, sub_rate=0.01, n_rate=0.005, n_run_mean=0.0):
+    """n_reads x 150 bp as the engine's stream: bytes + '\\n' per read, padded to 16.
+    n_run_mean > 0: the N's come in runs of geometric length with that mean (config 4), n_rate
+    being the fraction of bases that are N."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     rec = READ_LEN + 1
@@ -132,7 +143,20 @@ def make_stream(torch, donor, genome_len, n_reads, seed, device, sub_rate=0.01, 
         seq = torch.where(rev, comp[seq.long()].flip(1), seq)
         sub = torch.rand((r, READ_LEN), device=device, generator=g) < sub_rate * 4 / 3
         seq = torch.where(sub, acgt[torch.randint(0, 4, (r, READ_LEN), device=device, generator=g)], seq)
-        isn = torch.rand((r, READ_LEN), device=device, generator=g) < n_rate
+        if n_run_mean > 1.0:
+            # a run starts with probability n_rate / mean and lasts a geometric number of bases:
+            # +1 at its start, -1 after its end, running sum > 0 inside (clipped at the read end)
+            start = torch.rand((r, READ_LEN), device=device, generator=g) < n_rate / n_run_mean
+            u = torch.rand((r, READ_LEN), device=device, generator=g).clamp_(1e-9, 1.0)
+            length = (torch.log(u) / float(np.log1p(-1.0 / n_run_mean))).floor_().to(torch.int64) + 1
+            delta = torch.zeros((r, READ_LEN + 1), dtype=torch.int32, device=device)
+            delta[:, :READ_LEN] += start.to(torch.int32)
+            rows, cols = torch.nonzero(start, as_tuple=True)
+            ends = torch.clamp(cols + length[rows, cols], max=READ_LEN)
+            delta.index_put_((rows, ends), torch.full((rows.numel(),), -1, dtype=torch.int32, device=device), accumulate=True)
+            isn = delta[:, :READ_LEN].cumsum(1) > 0
+        else:
+            isn = torch.rand((r, READ_LEN), device=device, generator=g) < n_rate
         seq = torch.where(isn, torch.full_like(seq, ord("N")), seq)
         stream[lo * rec:(lo + r) * rec].view(r, rec)[:, :READ_LEN] = seq
     return stream, n_bytes
@@ -147,6 +171,142 @@ def write_fastq(path, reads):
     with open(path, "wb") as fh:
         q = b"I" * READ_LEN
         fh.write(b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, q[:len(r)]) for i, r in enumerate(reads)))
+
+
+def write_fastq_fixed(path, stream_bytes, n_reads):
+    """n_reads fixed-length records of a host copy of the stream as a plain 4-line FASTQ file,
+    assembled with numpy (a Python loop over 10^7 reads would take minutes)."""
+    rec = READ_LEN + 1
+    seqs = stream_bytes[:n_reads * rec].reshape(n_reads, rec)[:, :READ_LEN]
+    name_w = 10                                         # "@r" + 8 digits
+    row = name_w + 1 + READ_LEN + 1 + 2 + READ_LEN + 1
+    chunk = 1 << 20
+    with open(path, "wb") as fh:
+        for lo in range(0, n_reads, chunk):
+            n = min(chunk, n_reads - lo)
+            out = np.empty((n, row), dtype=np.uint8)
+            out[:, 0], out[:, 1] = ord("@"), ord("r")
+            idx = np.arange(lo, lo + n, dtype=np.int64)
+            for d in range(8):
+                out[:, 2 + d] = (idx // 10 ** (7 - d)) % 10 + ord("0")
+            out[:, name_w] = 10
+            out[:, name_w + 1:name_w + 1 + READ_LEN] = seqs[lo:lo + n]
+            at = name_w + 1 + READ_LEN
+            out[:, at], out[:, at + 1], out[:, at + 2] = 10, ord("+"), 10
+            out[:, at + 3:at + 3 + READ_LEN] = ord("I")
+            out[:, at + 3 + READ_LEN] = 10
+            fh.write(out.tobytes())
+
+
+def bind_to_gpu_numa_node(torch, dev):
+    """Run this process (and so allocate its page-locked buffers, first touch) on the NUMA node
+    the GPU hangs off: with one process per GPU, eight ranks otherwise pin their host buffers
+    wherever the launcher happened to start them.  Returns the node, None if it is not known."""
+    try:
+        p = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def sweep_patterns(vafgpu, k, n, genome_len, seed):
+    """n pattern rows with random k-mers at evenly spaced positions of a genome_len-base contig"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    ref = acgt[rng.integers(0, 4, (n, k))]
+    mid = k // 2
+    alt_base = acgt[(np.searchsorted(acgt, ref[:, mid]) + rng.integers(1, 4, n)) % 4]
+    alt = ref.copy()
+    alt[:, mid] = alt_base
+    step = genome_len // (n + 2)
+    pats = []
+    for i in range(n):
+        r, a = ref[i].tobytes().decode(), alt[i].tobytes().decode()
+        pats.append(vafgpu.Pattern("chrS", (i + 1) * step, (i + 1) * step + 1, "rs%d" % i, r[mid], a[mid], r, a))
+    return pats
+
+
+def run_k_sweep(torch, vafgpu, dev, ts, n_reads, peak):
+    """BASELINE config 4: k = 15 / 21 / 31, a 1 000-SNP panel and a full-size one, reads with 7.5 %
+    N in runs of geometric length (mean 5).  Kernel-only Gbases/s and fraction of the HBM roofline
+    per case; the anchor kernel is checked against the literal recipe kernel on the same reads."""
+    global HG38
+    out = []
+    glen = 1 << 28
+    saved = HG38
+    HG38 = [("chrS", glen)]
+    try:
+        for k in (15, 21, 31):
+            for n_pat in (1000, 20797):
+                pats = sweep_patterns(vafgpu, k, n_pat, glen, 100 + k)
+                keys, vals, _ = vafgpu.build_key_list(pats, k)
+                donor, _ = build_donor(torch, pats, glen, 4321, dev, k=k)
+                stream, n_bytes = make_stream(torch, donor, glen, n_reads, 55 + k, dev, n_rate=0.075, n_run_mean=5.0)
+                del donor
+                n16 = stream.numel()
+                launches = (n16 + (1 << 31) - 1) >> 31
+                frac_n = float((stream[:1 << 24] == ord("N")).float().mean().item()) * (READ_LEN + 1) / READ_LEN
+                with vafgpu.Engine(k, keys, vals, n_pat, n_devices=1) as eng:
+                    c = torch.zeros(2 * n_pat, dtype=torch.int32, device=dev)
+                    with torch.cuda.stream(ts):
+                        for _ in range(3):
+                            eng.count_device(stream.data_ptr(), n16, d_counts=c.data_ptr(), stream=ts.cuda_stream)
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        reps = 5
+                        e0.record()
+                        for _ in range(reps):
+                            eng.count_device(stream.data_ptr(), n16, d_counts=c.data_ptr(), stream=ts.cuda_stream)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        ms = e0.elapsed_time(e1) / reps
+                        c.zero_()
+                        eng.count_device(stream.data_ptr(), n16, d_counts=c.data_ptr(), stream=ts.cuda_stream)
+                        torch.cuda.synchronize()
+                    _, st = eng.finish()
+                with vafgpu.Engine(k, keys, vals, n_pat, n_devices=1, flags=vafgpu.F_REFERENCE_RECIPE) as rec_eng:
+                    c2 = torch.zeros_like(c)
+                    rec_eng.count_device(stream.data_ptr(), n16, d_counts=c2.data_ptr())
+                    torch.cuda.synchronize()
+                assert torch.equal(c, c2), "k sweep: anchor kernel and literal recipe kernel disagree at k=%d, %d patterns" % (k, n_pat)
+                gbs = n_reads * READ_LEN / ms / 1e6
+                out.append({"k": k, "patterns": n_pat, "reads": n_reads, "n_fraction": round(frac_n, 4),
+                            "value": gbs, "unit": "Gbases/s", "ms_per_pass": ms, "launches_per_pass": launches,
+                            "roofline_frac": gbs / peak, "hits": int(c.to(torch.int64).sum().item()),
+                            "kernel": "S=%d L=%d canon=%d deferred=%d" % (st["anchor_stride"], st["anchor_len"], st["filter_canon"],
+                                                                         st["lookup_deferred"]),
+                            "parity": "equal to the literal recipe kernel on all %d reads" % n_reads})
+                log("k sweep:", out[-1])
+                del stream
+                torch.cuda.empty_cache()
+    finally:
+        HG38 = saved
+    return out
+
+
+def run_kc_mode(n_reads):
+    """BASELINE config 5 (kc-c4 full counting, k = 31) on a fixed slice: tools/kc_bench.py in a
+    process of its own, its JSON line embedded (value, e2e, roofline, cpu_baseline, parity)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "kc_bench.py"), "--reads", str(n_reads), "--genome", str(max(n_reads * 10, 1 << 24)),
+           "--steps", "2", "--warmup", "1", "--sample", str(min(500_000, n_reads))]
+    try:
+        r = subprocess.run(cmd, check=True, capture_output=True, timeout=900)
+        line = [l for l in r.stdout.decode().splitlines() if l.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as exc:  # reported, not hidden
+        return {"error": repr(exc)[:500]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -246,6 +406,11 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
     ap.add_argument("--e2e-max-gb", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong-reads", type=int, default=600_000_000, help="config 3: reads in total over all GPUs")
+    ap.add_argument("--strong-steps", type=int, default=3)
+    ap.add_argument("--e2e-cli-reads", type=int, default=10_000_000, help="reads of the whole-process comparison (0 = skip)")
+    ap.add_argument("--sweep-reads", type=int, default=10_000_000, help="reads per case of the k sweep (0 = skip)")
+    ap.add_argument("--kc-reads", type=int, default=20_000_000, help="reads of the counting-mode slice (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -284,7 +449,8 @@ def main():
                           "hg38-length reference), %d x %d bp synthetic reads per GPU" % (n_pat, args.reads, READ_LEN),
               "k": K, "patterns": n_pat, "reads_per_gpu": args.reads, "read_len": READ_LEN,
               "l2": "inputs (%.1f GB per GPU) are far larger than L2" % (args.reads * (READ_LEN + 1) / 1e9),
-              "parallelism": "reads sharded per rank, tables replicated, one all-reduce of the counters per step"}
+              "parallelism": "reads sharded per rank, tables replicated, every rank's kernel adds its hits into rank 0's "
+                             "counter vector over NVLink (no collective in the step; all-reduce only where peer access is missing)"}
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path); --impl reference also builds its "
@@ -331,6 +497,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist = None
+    numa = bind_to_gpu_numa_node(torch, dev)         # page-locked buffers then come from the GPU's own node
     t_gen = time.perf_counter()
     donor, glen = build_donor(torch, pats, args.genome, 1234, dev)
     stream, n_bytes = make_stream(torch, donor, glen, args.reads, 1000 + rank, dev)
@@ -338,18 +507,12 @@ def main():
     torch.cuda.synchronize()
     log(f"generated {args.reads} reads ({n_bytes / 1e9:.2f} GB) in {time.perf_counter() - t_gen:.1f} s")
     bases_per_step = args.reads * READ_LEN
+    rec = READ_LEN + 1
 
     eng = vafgpu.Engine(K, keys, vals, n_pat, n_devices=1, block_bytes=256 << 20, n_buffers=3)
-    counts = torch.zeros(2 * n_pat, dtype=torch.int32, device=dev)
     ts = torch.cuda.Stream()
     n16 = stream.numel()
     launches_per_step = (n16 + (1 << 31) - 1) >> 31
-
-    def step():
-        counts.zero_()
-        eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
-        if world > 1:
-            sharding.all_reduce_counts(counts, dist)
 
     def barrier():
         torch.cuda.synchronize()
@@ -357,70 +520,147 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def scan(n_bytes16, d_counts=0):
+        eng.count_device(stream.data_ptr(), n_bytes16, d_counts=d_counts, stream=ts.cuda_stream)
+
+    def new_vec():
+        return torch.zeros(2 * n_pat, dtype=torch.int32, device=dev)
+
+    # what one pass over this rank's reads counts (the expectation for everything below)
+    one, scratch = new_vec(), new_vec()
+    with torch.cuda.stream(ts):
+        scan(n16, one.data_ptr())
+    torch.cuda.synchronize()
+    hits_per_step = int(one.to(torch.int64).sum().item())
+    # one counter vector for all ranks: rank 0's, the others' kernels add into it over NVLink
+    merge = sharding.share_counters(eng, dist, rank)
+    log(f"counters: {merge}")
+    shared = merge != "all_reduce"      # hits land in the engine's (shared) vector: nothing to merge
+    own = None if shared else new_vec()
+
+    def step():
+        if shared:
+            scan(n16)
+        else:
+            own.zero_()
+            scan(n16, own.data_ptr())
+            sharding.all_reduce_counts(own, dist)
+
+    # strong scaling, BASELINE config 3: 600 M reads IN TOTAL over the ranks; a rank scans its
+    # share as whole passes over its resident stream plus a partial one
+    share = sharding.strong_share(args.strong_reads, rank, world)
+    full_passes, part = divmod(share, args.reads)
+    part16 = (part * rec + 15) // 16 * 16
+
+    def strong_step():
+        tgt = 0 if shared else scratch.data_ptr()
+        if not shared:
+            scratch.zero_()
+        for _ in range(full_passes):
+            scan(n16, tgt)
+        if part:
+            scan(part16, tgt)
+        if not shared:
+            sharding.all_reduce_counts(scratch, dist)
+
+    eng.reset()
+    barrier()
     with torch.cuda.stream(ts):
         for _ in range(args.warmup):
             step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clk = ClockSampler(phys_index)
-        with clk:  # clocks are sampled over both timed loops (each lasts only tens of milliseconds)
+        with clk:  # clocks are sampled over the timed loops (each lasts only tens of milliseconds)
             e0.record()
             for _ in range(args.steps):
                 step()
             e1.record()
             barrier()
             ms = e0.elapsed_time(e1)
-            # the dominant kernel alone (no counter reset, no collective), for the roofline
+            # the dominant kernel alone, for the roofline
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             k0.record()
             for _ in range(args.steps):
-                eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
+                scan(n16, scratch.data_ptr())
             k1.record()
             barrier()
             kernel_ms = k0.elapsed_time(k1) / (args.steps * launches_per_step)
+            scratch.zero_()
+            strong_step()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.strong_steps):
+                strong_step()
+            s1.record()
+            barrier()
+            strong_ms = s0.elapsed_time(s1) / args.strong_steps
     if world > 1:
-        t = torch.tensor([ms], device=dev)
+        t = torch.tensor([ms, strong_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, strong_ms = float(t[0].item()), float(t[1].item())
     ms_per_step = ms / args.steps
     value = bases_per_step * world / (ms_per_step * 1e-3) / 1e9
+    strong = {"workload": "config 3: %d x %d bp reads in total, sharded over %d GPU(s)" % (args.strong_reads, READ_LEN, world),
+              "value": args.strong_reads * READ_LEN / (strong_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": strong_ms,
+              "steps": args.strong_steps, "scaling": "strong", "merge": merge,
+              "note": "a rank's share is scanned as passes over its resident %d-read stream" % args.reads}
 
-    # ---- parity at full size: linearity over a split, the literal recipe kernel on a slice,
-    #      the oracle and the reference on a sample
+    # ---- parity at full size: the merged counters, linearity over a split, the literal recipe
+    #      kernel on a slice, the oracle and the reference on a sample
+    parity = {}
+    part_counts = new_vec()
     with torch.cuda.stream(ts):
-        counts.zero_()
-        eng.count_device(stream.data_ptr(), n16, d_counts=counts.data_ptr(), stream=ts.cuda_stream)
-        torch.cuda.synchronize()
-        full = counts.clone()
-        rec = READ_LEN + 1
+        if part:
+            scan(part16, part_counts.data_ptr())
         cut = (args.reads // 2) * rec
         cut16 = (cut + 15) // 16 * 16
         head = torch.full((cut16,), 10, dtype=torch.uint8, device=dev)
         head[:cut] = stream[:cut]
         tail = torch.full(((n_bytes - cut + 15) // 16 * 16,), 10, dtype=torch.uint8, device=dev)
         tail[:n_bytes - cut] = stream[cut:n_bytes]
-        counts.zero_()
-        eng.count_device(head.data_ptr(), head.numel(), d_counts=counts.data_ptr(), stream=ts.cuda_stream)
-        eng.count_device(tail.data_ptr(), tail.numel(), d_counts=counts.data_ptr(), stream=ts.cuda_stream)
-        torch.cuda.synchronize()
-        assert torch.equal(full, counts), "linearity over a split of the stream failed"
-        del head, tail
+        halves = new_vec()
+        eng.count_device(head.data_ptr(), head.numel(), d_counts=halves.data_ptr(), stream=ts.cuda_stream)
+        eng.count_device(tail.data_ptr(), tail.numel(), d_counts=halves.data_ptr(), stream=ts.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(halves, one), "linearity over a split of the stream failed"
+    parity["split_linearity"] = "ok"
+    del head, tail, halves
+    # everything the ranks counted into the merged vector: weak passes and strong shares
+    share_counts = one.to(torch.int64) * full_passes + part_counts.to(torch.int64)
+    if shared:
+        want = one.to(torch.int64) * (args.warmup + args.steps) + share_counts * (1 + args.strong_steps)
+        barrier()                          # every rank has drained before rank 0 reads the shared vector
+        got_shared, _ = eng.finish()
+    else:
+        want = share_counts                  # the last strong step, summed over the ranks
+        got_shared = scratch.cpu().numpy().view(np.uint32)
+    if world > 1:
+        dist.all_reduce(want)
+    if rank == 0:
+        assert np.array_equal(want.cpu().numpy().astype(np.uint32), got_shared), \
+            "the merged counters are not the sum of what the ranks counted"
+        parity["merged_counters"] = "identical to the sum of the ranks' counts (%s)" % merge
+    if world > 1:
+        dist.barrier()
     _, st_kernel = eng.finish()
-    hits_per_step = int(full.to(torch.int64).sum().item())
     slice_reads = min(args.reads, 2_000_000)
     sl = stream[:(slice_reads * rec + 15) // 16 * 16].clone()
     sl[slice_reads * rec:] = 10
     with vafgpu.Engine(K, keys, vals, n_pat, n_devices=1, flags=vafgpu.F_REFERENCE_RECIPE) as rec_eng:
-        c2 = torch.zeros_like(counts)
+        c2 = new_vec()
         rec_eng.count_device(sl.data_ptr(), sl.numel(), d_counts=c2.data_ptr())
         torch.cuda.synchronize()
-    c1 = torch.zeros_like(counts)
+    c1 = new_vec()
     eng.count_device(sl.data_ptr(), sl.numel(), d_counts=c1.data_ptr())
     torch.cuda.synchronize()
     assert torch.equal(c1, c2), "anchor kernel and literal recipe kernel disagree"
-    parity = {"split_linearity": "ok", "recipe_kernel_on_%d_reads" % slice_reads: "ok"}
+    parity["recipe_kernel_on_%d_reads" % slice_reads] = "ok"
+    del sl
 
-    # ---- end to end through the C ABI from page-locked host memory
+    # ---- end to end through the C ABI from page-locked host memory (its own engine: the shared
+    #      vector stays out of it; counters are merged the way a caller without NVLink would)
     avail_gb = 0.0
     try:
         for l in open("/proc/meminfo"):
@@ -428,22 +668,22 @@ def main():
                 avail_gb = int(l.split()[1]) / 1e6
     except OSError:
         pass
-    e2e_bytes = int(min(n_bytes, args.e2e_max_gb * 1e9, max(avail_gb, 1.0) * 1e9 / 3))
+    e2e_bytes = int(min(n_bytes, args.e2e_max_gb * 1e9, max(avail_gb, 1.0) * 1e9 / (3 * max(1, min(world, 8)))))
     e2e_reads = e2e_bytes // rec
     e2e_bytes = e2e_reads * rec
     host = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True)
     host.copy_(stream[:e2e_bytes])
     torch.cuda.synchronize()
-    eng.reset()
+    e2e_eng = vafgpu.Engine(K, keys, vals, n_pat, n_devices=1, block_bytes=256 << 20, n_buffers=3)
     e2e_times, got = [], None
     for i in range(args.warmup + args.steps):
         if world > 1:
             dist.barrier()
-        eng.reset()
+        e2e_eng.reset()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng.submit_stream((host.data_ptr(), e2e_bytes), n_reads=e2e_reads, n_bases=e2e_reads * READ_LEN)
-        got, st_e2e = eng.finish()
+        e2e_eng.submit_stream((host.data_ptr(), e2e_bytes), n_reads=e2e_reads, n_bases=e2e_reads * READ_LEN)
+        got, st_e2e = e2e_eng.finish()
         if world > 1:
             g = torch.from_numpy(got.astype(np.int32)).to(dev)
             dist.all_reduce(g)
@@ -458,20 +698,22 @@ def main():
         e2e_dt = float(t.item())
     e2e_value = e2e_reads * READ_LEN * world / e2e_dt / 1e9
     # what came back must be what the resident pass counted for the same reads
-    chk = torch.zeros_like(counts)
+    chk = new_vec()
     n_e16 = (e2e_bytes + 15) // 16 * 16
     if n_e16 <= n16:
-        part = stream[:n_e16].clone()
-        part[e2e_bytes:] = 10
-        eng2 = vafgpu.Engine(K, keys, vals, n_pat, n_devices=1)
-        eng2.count_device(part.data_ptr(), part.numel(), d_counts=chk.data_ptr())
+        part_s = stream[:n_e16].clone()
+        part_s[e2e_bytes:] = 10
+        eng.count_device(part_s.data_ptr(), part_s.numel(), d_counts=chk.data_ptr())
         torch.cuda.synchronize()
         assert np.array_equal(chk.cpu().numpy().view(np.uint32), got), "e2e counters differ from the resident pass"
-        eng2.close()
+        del part_s
         parity["e2e_equals_resident"] = "ok"
+    e2e_eng.close()
+    del host
 
     # ---- CPU baseline + byte parity of the .vaf on a sample (rank 0 only)
     cpu = None
+    e2e_cli = None
     if rank == 0 and not args.no_cpu_baseline:
         exe, kind = reference_binary()
         n_s = min(args.cpu_sample_reads, args.reads)
@@ -496,36 +738,74 @@ def main():
         assert ours_txt == ref_txt, "VAF text differs from the reference's on the sample"
         assert open(os.path.join(tmp, "refn.vaf")).read() == ref_txt
         parity["vaf_bytes_vs_%s_on_%d_reads" % (kind, len(reads))] = "identical"
-        # the vaf-counter command line of this repo on the same file: same bytes out, timed the same
-        # way (whole process, which for a sample this small is mostly CUDA start-up) and by its own
-        # clock around the counting phase; -t is the number of host reader threads
-        cli_exe = os.path.join(PKG, "vaf-counter")
-        cli = {}
-        for th in sorted({1, ncpu}):
-            out_vaf = os.path.join(tmp, "cli%d.vaf" % th)
-            t0 = time.perf_counter()
-            r = subprocess.run([cli_exe, "-k", str(K), "-t", str(th), "-v", "-p", pattern_file, "-o", out_vaf, fq],
-                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
-            wall = time.perf_counter() - t0
-            assert open(out_vaf).read() == ref_txt, "CLI output differs from the reference's at -t %d" % th
-            m = re.search(rb"K-mer counting:\s+([0-9.]+) sec", r.stderr)
-            cli["t%d" % th] = {"whole_process_gbases_s": bases / wall / 1e9,
-                               "counting_phase_gbases_s": bases / max(float(m.group(1)), 1e-9) / 1e9 if m else None}
-        parity["cli_vaf_bytes_vs_%s" % kind] = "identical at -t 1 and -t %d" % ncpu
-        cpu["this_repo_cli_same_file"] = cli
         try:
             import util
-            want, _, _ = util.Oracle().count_reads(pattern_file, K, reads)
-            assert np.array_equal(want, mine)
+            want_o, _, _ = util.Oracle().count_reads(pattern_file, K, reads)
+            assert np.array_equal(want_o, mine)
             parity["oracle_counts_on_sample"] = "identical"
         except Exception as exc:  # the oracle is a checker; its absence is reported, not hidden
             parity["oracle_counts_on_sample"] = "not run: %r" % (exc,)
+        del reads
+        # ---- whole process against whole process on one FASTQ file (N = 1): this repository's
+        #      vaf-counter and the reference's, same file in /dev/shm, same patterns, -t as given
+        if world == 1 and args.e2e_cli_reads > 0:
+            n_c = min(args.e2e_cli_reads, args.reads)
+            big = os.path.join(tmp, "e2e_cli.fq")
+            t0 = time.perf_counter()
+            write_fastq_fixed(big, stream[:n_c * rec].cpu().numpy(), n_c)
+            log(f"e2e_cli: wrote {os.path.getsize(big) / 1e9:.2f} GB FASTQ in {time.perf_counter() - t0:.1f} s")
+            cli_bases = n_c * READ_LEN
+            t_ref = time_reference(exe, pattern_file, big, os.path.join(tmp, "big_ref.vaf"), threads)
+            cli_exe = os.path.join(PKG, "vaf-counter")
+            ours = {}
+            for th in sorted({1, ncpu}):
+                out_vaf = os.path.join(tmp, "big_cli%d.vaf" % th)
+                t0 = time.perf_counter()
+                r = subprocess.run([cli_exe, "-k", str(K), "-t", str(th), "-v", "-p", pattern_file, "-o", out_vaf, big],
+                                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+                wall = time.perf_counter() - t0
+                assert open(out_vaf, "rb").read() == open(os.path.join(tmp, "big_ref.vaf"), "rb").read(), \
+                    "CLI output differs from the reference's at -t %d" % th
+                m = re.search(rb"K-mer counting:\s+([0-9.]+) sec", r.stderr)
+                ours["t%d" % th] = {"whole_process_s": wall, "whole_process_gbases_s": cli_bases / wall / 1e9,
+                                    "counting_phase_gbases_s": cli_bases / max(float(m.group(1)), 1e-9) / 1e9 if m else None}
+            best_th = min(ours, key=lambda x: ours[x]["whole_process_s"])
+            e2e_cli = {"workload": "%d reads x %d bp of this workload as one plain FASTQ file in %s (%.2f GB)"
+                                   % (n_c, READ_LEN, os.path.dirname(big), os.path.getsize(big) / 1e9),
+                       "value": ours[best_th]["whole_process_gbases_s"], "unit": "Gbases/s",
+                       "reference": {"value": cli_bases / t_ref / 1e9, "unit": "Gbases/s", "threads": threads, "whole_process_s": t_ref,
+                                     "kind": kind},
+                       "speedup_whole_process": t_ref / ours[best_th]["whole_process_s"], "this_repo": ours,
+                       "vaf_bytes": "identical",
+                       "note": "process start (CUDA context creation, 0.5-3 s on these boxes), pattern load, FASTQ parse, "
+                               "count and VAF write on both sides"}
+            os.unlink(big)
+            parity["cli_vaf_bytes_vs_%s_on_%d_reads" % (kind, n_c)] = "identical at -t 1 and -t %d" % ncpu
+
+    # ---- BASELINE config 4: k sweep on reads with N runs (N = 1 only)
+    k_sweep = None
+    if rank == 0 and world == 1 and args.sweep_reads > 0:
+        del stream
+        torch.cuda.empty_cache()
+        k_sweep = run_k_sweep(torch, vafgpu, dev, ts, args.sweep_reads, peak)
+    # ---- BASELINE config 5: the counting mode on a fixed slice (N = 1 only)
+    modes = None
+    if rank == 0 and world == 1 and args.kc_reads > 0:
+        eng.close()
+        eng = None
+        torch.cuda.empty_cache()
+        modes = {"kc": run_kc_mode(args.kc_reads)}
 
     if rank == 0:
-        traffic = None
+        traffic, traffic_note = None, None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = prof["dram_bytes_per_stream_byte"] * (n16 / launches_per_step)
+            if prof.get("library_version") == vafgpu.load_library().vafgpu_version().decode():
+                traffic = prof["dram_bytes_per_stream_byte"] * (n16 / launches_per_step)
+                traffic_note = prof.get("source")
+            else:
+                traffic_note = "profiles/traffic.json was measured on %r, this library is %r: not used" % (
+                    prof.get("library_version"), vafgpu.load_library().vafgpu_version().decode())
         except (OSError, KeyError, ValueError):
             pass
         algo_bytes_per_launch = bases_per_step / launches_per_step            # 1 byte per base
@@ -535,25 +815,38 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 in, u32/u64 integer arithmetic", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": 8 * n_pat,
-                    "sample": "%d of %d reads per GPU from page-locked host memory through vafgpu_submit_stream + "
-                              "vafgpu_finish" % (e2e_reads, args.reads)},
+                    "sample": "%d of %d reads per GPU, already parsed (the path's boundary: no FASTQ parsing, no process "
+                              "start; see e2e_cli for those), from page-locked host memory%s through vafgpu_submit_stream + "
+                              "vafgpu_finish" % (e2e_reads, args.reads, " on the GPU's NUMA node" if numa is not None else "")},
+            "e2e_cli": e2e_cli,
+            "strong_scaling": strong,
+            "k_sweep": k_sweep,
+            "modes": modes,
             "gpu_launches": int(args.steps * launches_per_step),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "anchor_scan_kernel<S=8,CANON,DEFER,L=14>",
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                         "kernel": "anchor_scan_kernel<S=%d,CANON=%d,DEFER=%d,L=%d> (%d threads)" % (
+                             st_kernel["anchor_stride"], st_kernel["filter_canon"], st_kernel["lookup_deferred"],
+                             st_kernel["anchor_len"], st_kernel["kernel_threads"]),
                          "algorithmic_bytes_per_launch": algo_bytes_per_launch, "ms_per_launch": kernel_ms},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
             "parity": parity,
+            "merge": merge,
+            "numa_node": numa,
             "stats": {"hits_per_step": hits_per_step, "resolver_entries_per_base":
                       st_kernel["n_candidates"] / max(st_kernel["n_bytes"], 1), "anchor_stride": st_kernel["anchor_stride"],
                       "anchor_len": st_kernel["anchor_len"], "filter_bytes": st_kernel["filter_bytes"],
-                      "pattern_collisions": n_coll},
+                      "filter2_bytes": st_kernel["filter2_bytes"], "pattern_collisions": n_coll,
+                      "library": vafgpu.load_library().vafgpu_version().decode()},
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
+    if eng is not None:
+        eng.close()
     return 0
 
 

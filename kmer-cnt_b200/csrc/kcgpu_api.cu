@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -31,6 +32,7 @@ thread_local std::string g_kc_create_error;
  * threads (producers) fill their staging blocks outside it and take it only to fetch a block
  * and to submit one.  Contexts linked into a group flush together, hence not one lock each. */
 std::mutex g_kc_mu;
+std::condition_variable g_kc_block_free; /* a producer handed a staging block back */
 
 struct KcBlock {
 	char *h = nullptr;
@@ -155,7 +157,7 @@ cudaError_t kc_launch_flush(const kcgpu_ctx *m, cudaStream_t s)
 	a.region_bits = m->region_bits;
 	a.rslot_bits = m->rslot_bits;
 	a.stats = m->d_stats;
-	cudaError_t e = launch_route(a, s);
+	cudaError_t e = launch_route(a, m->n_sm, s);
 	if (e != cudaSuccess) return e;
 	return launch_flush(m->d_table, a.lists, cursors, a.cap, m->region_bits, m->rslot_bits, m->d_stats, s);
 }
@@ -200,6 +202,7 @@ int kc_submit_current(kcgpu_producer *p)
 	if (!b) return VAFGPU_OK;
 	p->cur = nullptr;
 	b->owned = false;
+	g_kc_block_free.notify_one();
 	if (!b->used) return VAFGPU_OK;
 	const size_t n = (b->used + 15) & ~(size_t)15;
 	memset(b->h + b->used, '\n', n - b->used);
@@ -224,15 +227,15 @@ int kc_ensure_room(kcgpu_producer *p, size_t need)
 {
 	kcgpu_ctx *c = p->c;
 	if (p->cur && p->cur->used + need <= c->block_bytes) return VAFGPU_OK;
-	for (;;) {
-		{
-			std::lock_guard<std::mutex> lk(g_kc_mu);
-			if (p->cur) {
-				int rc = kc_submit_current(p);
-				if (rc) return rc;
-			}
+	KcBlock *pick = nullptr;
+	{
+		std::unique_lock<std::mutex> lk(g_kc_mu);
+		if (p->cur) {
+			int rc = kc_submit_current(p);
+			if (rc) return rc;
+		}
+		for (;;) {
 			/* an idle block if there is one, else the first one in flight in ring order */
-			KcBlock *pick = nullptr;
 			KCU(c, cudaSetDevice(c->device));
 			for (size_t tries = 0; tries < c->blocks.size(); ++tries) {
 				KcBlock *b = c->blocks[(c->next_block + tries) % c->blocks.size()];
@@ -244,18 +247,33 @@ int kc_ensure_room(kcgpu_producer *p, size_t need)
 				if (!pick) pick = b;
 			}
 			cudaGetLastError(); /* cudaErrorNotReady of the query is not an error */
-			if (pick) {
-				c->next_block = (c->next_block + 1) % c->blocks.size();
-				int rc = kc_wait_block(c, *pick);
-				if (rc) return rc;
-				pick->owned = true;
-				pick->used = 0;
-				p->cur = pick;
-				return VAFGPU_OK;
-			}
+			if (pick) break;
+			g_kc_block_free.wait(lk); /* more producers than blocks: wait for one to be submitted */
 		}
-		std::this_thread::yield(); /* more producers than blocks: wait for one to be submitted */
+		c->next_block = (c->next_block + 1) % c->blocks.size();
+		pick->owned = true; /* ours from here on: nobody else looks at it */
 	}
+	/* wait for the block's last use OUTSIDE the lock: other producers, of this and of every other
+	 * context, go on fetching and submitting meanwhile */
+	float h2d = 0, ker = 0;
+	const bool was_in_flight = pick->in_flight;
+	if (was_in_flight) {
+		KCU(c, cudaSetDevice(c->device));
+		KCU(c, cudaEventSynchronize(pick->e2));
+		cudaEventElapsedTime(&h2d, pick->e0, pick->e1);
+		cudaEventElapsedTime(&ker, pick->e1, pick->e2);
+	}
+	{
+		std::lock_guard<std::mutex> lk(g_kc_mu);
+		if (was_in_flight && pick->in_flight) { /* a flush in between may have accounted for it already */
+			c->st.h2d_ms += h2d;
+			c->st.kernel_ms += ker;
+			pick->in_flight = false;
+		}
+	}
+	pick->used = 0;
+	p->cur = pick;
+	return VAFGPU_OK;
 }
 
 /* lock held.  Submit what the context's own producer has staged (other producers submit
@@ -384,14 +402,12 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 			return kfail(c, VAFGPU_ENOGPU, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", device, prop.name,
 			             prop.major, prop.minor);
 		c->n_sm = prop.multiProcessorCount;
-		if (const char *env = getenv("KCGPU_L2_FETCH")) /* tuning knob: 32, 64 or 128 */
-			KCU(c, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env)));
 		const uint32_t need_bits = kc_region_bits(k); /* regions the slot word needs (tag beside the count) */
 		const uint64_t min_slots = (uint64_t)4096 > ((uint64_t)16 << need_bits) ? (uint64_t)4096 : ((uint64_t)16 << need_bits);
 		const bool lists = list_slots != KCGPU_NO_LISTS;
+		size_t free_b = 0, total_b = 0;
+		KCU(c, cudaMemGetInfo(&free_b, &total_b));
 		if (table_slots == 0) {
-			size_t free_b = 0, total_b = 0;
-			KCU(c, cudaMemGetInfo(&free_b, &total_b));
 			uint64_t budget = (uint64_t)free_b / 4 * 3 / 8; /* 8-byte words */
 			if (lists) budget = list_slots ? (budget > list_slots ? budget - list_slots : 0) : budget / 3 * 2;
 			table_slots = min_slots;
@@ -402,28 +418,33 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 			if (n >> 40) return kfail(c, VAFGPU_EINVAL, "table_slots too large");
 			n *= 2;
 		}
-		c->n_slots = n;
-		uint32_t bits = 0;
-		while ((1ull << bits) < n) ++bits;
-		/* regions: what the slot word needs, and small enough (16 MiB) to stay in L2 while the
-		 * lists of one region are emptied into it */
-		uint32_t slice_bits = KC_REGION_SLOT_BITS;
-		if (const char *env = getenv("KCGPU_REGION_SLOT_BITS")) /* tuning knob */
-			if (atoi(env) >= 8 && atoi(env) <= 30) slice_bits = (uint32_t)atoi(env);
-		c->region_bits = need_bits;
-		if (lists && bits > slice_bits && bits - slice_bits > c->region_bits) c->region_bits = bits - slice_bits;
-		if (c->region_bits > 20) c->region_bits = 20;
-		c->rslot_bits = bits - c->region_bits;
-		if (lists) {
-			if (list_slots == 0) list_slots = n / 2;
-			uint64_t cap = (list_slots >> c->region_bits) + 31 & ~(uint64_t)31;
-			if (cap < 64) cap = 64;
-			if (cap >> 40) return kfail(c, VAFGPU_EINVAL, "list_slots too large");
-			c->list_cap = cap;
-			c->flush_bytes = (cap << c->region_bits) / 20 * 19; /* a byte is at most one k-mer; what a list cannot take goes to the table */
-			if (c->flush_bytes > ((uint64_t)1 << 40)) c->flush_bytes = (uint64_t)1 << 40;
+		/* the geometry of a table of n slots; a request that does not fit the device is halved
+		 * until it does (the caller reads the size it got from kcgpu_stats.table_slots) */
+		const uint64_t want_lists = list_slots;
+		uint64_t alloc = 0;
+		for (;; n /= 2) {
+			c->n_slots = n;
+			uint32_t bits = 0;
+			while ((1ull << bits) < n) ++bits;
+			/* regions: what the slot word needs, and small enough (16 MiB) to stay in L2 while the
+			 * lists of one region are emptied into it */
+			c->region_bits = need_bits;
+			if (lists && bits > KC_REGION_SLOT_BITS && bits - KC_REGION_SLOT_BITS > c->region_bits) c->region_bits = bits - KC_REGION_SLOT_BITS;
+			if (c->region_bits > 20) c->region_bits = 20;
+			c->rslot_bits = bits - c->region_bits;
+			c->list_cap = 0;
+			if (lists) {
+				list_slots = want_lists ? want_lists : n / 2;
+				uint64_t cap = (list_slots >> c->region_bits) + 31 & ~(uint64_t)31;
+				if (cap < 64) cap = 64;
+				if (cap >> 40) return kfail(c, VAFGPU_EINVAL, "list_slots too large");
+				c->list_cap = cap;
+				c->flush_bytes = (cap << c->region_bits) / 20 * 19; /* a byte is at most one k-mer; what a list cannot take goes to the table */
+				if (c->flush_bytes > ((uint64_t)1 << 40)) c->flush_bytes = (uint64_t)1 << 40;
+			}
+			alloc = kc_alloc_bytes(n, c->list_cap, c->region_bits);
+			if (alloc + ((uint64_t)256 << 20) <= (uint64_t)free_b || n <= min_slots) break;
 		}
-		const uint64_t alloc = kc_alloc_bytes(n, c->list_cap, c->region_bits);
 		cudaError_t me = cudaMalloc(&c->d_table, alloc);
 		if (me != cudaSuccess) {
 			cudaGetLastError();
@@ -578,6 +599,7 @@ int kcgpu_submit_stream(kcgpu_ctx *c, const char *bytes, size_t n_bytes)
 		std::lock_guard<std::mutex> lk(g_kc_mu);
 		p->cur = nullptr;
 		b->owned = false;
+		g_kc_block_free.notify_one();
 		const size_t n16 = (n + (add_nl ? 1 : 0) + 15) & ~(size_t)15;
 		rc = kc_make_room(c, n16);
 		if (rc) return rc;
@@ -672,7 +694,7 @@ int kcgpu_insert_device(kcgpu_ctx *c, const uint64_t *d_hashed_keys, size_t n, i
 	std::lock_guard<std::mutex> lk(g_kc_mu);
 	KCU(c, cudaSetDevice(c->device));
 	cudaStream_t s = stream ? (cudaStream_t)stream : c->main_stream;
-	KCU(c, launch_insert(a, s));
+	KCU(c, launch_insert(a, c->n_sm, s));
 	return kc_note_user_stream(c, s);
 }
 

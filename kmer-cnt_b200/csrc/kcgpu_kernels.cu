@@ -25,13 +25,11 @@
  *  kc_insert_kernel        the same for lists that came from an exchange
  *  kc_hist_kernel          worker_hist (kc-c4.c:186-197) over the slots
  *
- * No tensor cores: shifts, multiplies and atomics (DESIGN.md section 10).
+ * No tensor cores: shifts, multiplies and atomics (DESIGN.md section 9).
  */
 #include "kcgpu_kernels.cuh"
 
 #include <cooperative_groups.h>
-
-#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -308,18 +306,11 @@ __global__ void __launch_bounds__(KC_THREADS) kc_insert_kernel(const InsertArgs 
 {
 	uint32_t n_new = 0, n_overflow = 0, n_kmers = 0;
 	const uint64_t stride = (uint64_t)gridDim.x * KC_THREADS;
-	uint64_t n = a.n;
-	if (a.n_ptr) { /* an inbox: as many as its cursor says, at most its capacity */
-		const uint64_t filled = *a.n_ptr;
-		n = filled < n ? filled : n;
-	}
-	for (uint64_t i = (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x; i < n; i += stride) {
+	for (uint64_t i = (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x; i < a.n; i += stride) {
 		uint64_t q = __ldcs(reinterpret_cast<const unsigned long long *>(a.hashed + i));
-		if (!a.split) {
-			uint32_t owner;
-			kc_owner(q, a.n_parts, part_shift, owner, q);
-			++n_kmers;
-		}
+		uint32_t owner;
+		kc_owner(q, a.n_parts, part_shift, owner, q);
+		++n_kmers;
 		kc_insert(a.table, a.region_bits, a.rslot_bits, q, n_new, n_overflow);
 	}
 	for (int o = 16; o; o >>= 1) {
@@ -437,7 +428,7 @@ cudaError_t launch_flush(uint64_t *base, const uint64_t *lists, const unsigned l
                          uint32_t region_bits, uint32_t rslot_bits, unsigned long long *stats, cudaStream_t stream)
 {
 	if (!list_cap) return cudaSuccess;
-	static const uint32_t tile = getenv("KCGPU_FLUSH_TILE") ? (uint32_t)atoi(getenv("KCGPU_FLUSH_TILE")) : (uint32_t)KC_FLUSH_TILE; /* tuning knob */
+	const uint32_t tile = KC_FLUSH_TILE;
 	const uint64_t tiles = (list_cap + tile - 1) / tile;
 	const uint64_t blocks = tiles << region_bits;
 	if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
@@ -445,18 +436,19 @@ cudaError_t launch_flush(uint64_t *base, const uint64_t *lists, const unsigned l
 	return cudaGetLastError();
 }
 
-cudaError_t launch_route(const RouteArgs &a, cudaStream_t stream)
+cudaError_t launch_route(const RouteArgs &a, int n_sm, cudaStream_t stream)
 {
 	if (!a.inbox_cap) return cudaSuccess;
-	kc_route_kernel<<<148 * 8, KC_THREADS, 0, stream>>>(a);
+	kc_route_kernel<<<(unsigned)(n_sm > 0 ? n_sm : 1) * 8, KC_THREADS, 0, stream>>>(a); /* 8 CTAs of 256 threads per SM */
 	return cudaGetLastError();
 }
 
-cudaError_t launch_insert(const InsertArgs &a, cudaStream_t stream)
+cudaError_t launch_insert(const InsertArgs &a, int n_sm, cudaStream_t stream)
 {
 	if (a.n == 0) return cudaSuccess;
 	uint64_t blocks = (a.n + KC_THREADS - 1) / KC_THREADS;
-	if (blocks > 148ull * 64) blocks = 148ull * 64;
+	const uint64_t most = (uint64_t)(n_sm > 0 ? n_sm : 1) * 64;
+	if (blocks > most) blocks = most;
 	kc_insert_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(a, shift_of(a.n_parts));
 	return cudaGetLastError();
 }
@@ -464,7 +456,7 @@ cudaError_t launch_insert(const InsertArgs &a, cudaStream_t stream)
 cudaError_t launch_histogram(const uint64_t *table, uint64_t n_slots, unsigned long long *hist256, int n_sm, cudaStream_t stream)
 {
 	uint64_t blocks = ((n_slots >> 1) + KC_THREADS - 1) / KC_THREADS;
-	const uint64_t resident = (uint64_t)(n_sm > 0 ? n_sm : 148) * 8; /* 8 CTAs of 256 threads per SM */
+	const uint64_t resident = (uint64_t)(n_sm > 0 ? n_sm : 1) * 8; /* 8 CTAs of 256 threads per SM */
 	if (blocks > resident) blocks = resident;
 	if (blocks < 1) blocks = 1;
 	kc_hist_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(table, n_slots, hist256);

@@ -83,8 +83,6 @@ struct CountArgs {
 struct InsertArgs {
 	const uint64_t *hashed; /* hash64 values owned by this table */
 	uint64_t n;
-	const unsigned long long *n_ptr; /* if set: the count is min(*n_ptr, n), read on the device */
-	int split;              /* the values are already hash div n_parts (an inbox), not hashes */
 	uint32_t n_parts;
 	uint32_t region_bits, rslot_bits;
 	uint64_t *table;
@@ -113,9 +111,9 @@ struct RouteArgs {
 	uint32_t region_bits, rslot_bits;
 	unsigned long long *stats;
 };
-cudaError_t launch_route(const RouteArgs &a, cudaStream_t stream);
+cudaError_t launch_route(const RouteArgs &a, int n_sm, cudaStream_t stream);
 cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream); /* extract into per-owner lists */
-cudaError_t launch_insert(const InsertArgs &a, cudaStream_t stream);
+cudaError_t launch_insert(const InsertArgs &a, int n_sm, cudaStream_t stream);
 cudaError_t launch_histogram(const uint64_t *table, uint64_t n_slots, unsigned long long *hist256, int n_sm,
                              cudaStream_t stream);
 

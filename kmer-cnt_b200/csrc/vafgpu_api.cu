@@ -264,7 +264,7 @@ void destroy_device(Device &d)
 
 extern "C" {
 
-const char *vafgpu_version(void) { return "vafgpu 0.1 (sm_100a)"; }
+const char *vafgpu_version(void) { return "vafgpu 0.2 (sm_100a; anchor kernel v17)"; }
 
 int vafgpu_plan(int k, int *stride, int *len)
 {
@@ -288,6 +288,8 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 	if (k < 1 || k > 31) return fail(nullptr, VAFGPU_EINVAL, "k = %d is outside 1..31", k);
 	if (n_entries && (!keys || !vals)) return fail(nullptr, VAFGPU_EINVAL, "keys/vals are NULL");
 	if (n_patterns > 0x3FFFFFFFu) return fail(nullptr, VAFGPU_EINVAL, "too many patterns (%u)", n_patterns);
+	if ((uint64_t)n_entries * 2 * (uint64_t)make_plan(k).stride >= 0x7FFFFFFFull) /* payload indices are 31 bits */
+		return fail(nullptr, VAFGPU_EINVAL, "too many k-mers (%u) for the exact table", n_entries);
 	const uint64_t kmask = (1ULL << 2 * k) - 1;
 	for (uint32_t i = 0; i < n_entries; ++i) {
 		if (keys[i] > kmask) return fail(nullptr, VAFGPU_EINVAL, "key %u does not fit 2k bits", i);

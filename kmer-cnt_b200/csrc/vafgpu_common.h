@@ -21,8 +21,13 @@
 #endif
 
 #define VG_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-#define VG_SMEM_BUDGET (227 * 1024) /* dynamic shared memory per CTA on sm_100: filter + candidate queues */
+#define VG_SMEM_BUDGET (227 * 1024) /* dynamic shared memory per CTA on sm_100: filter + bit-pair table + candidate queues */
 #define VG_MIN_FILTER_WORDS 1024u
+#ifndef VG_PAIR_ALU
+#define VG_PAIR_ALU 1               /* bit pair of a key: made with shifts (1) or read from a shared-memory table (0) */
+#endif
+#define VG_PAIRS 992u               /* ordered pairs of distinct bit positions in a 32-bit word */
+#define VG_PAIR_TABLE_BYTES (VG_PAIR_ALU ? 0 : 4096)
 
 /* Launch geometry of the anchor kernel, shared with the table builder because the candidate
  * queues and the filter split one shared-memory budget.
@@ -38,7 +43,8 @@
 #define VG_THREADS(S, DEFER) ((DEFER) ? VG_THREADS_DEFER(S) : (S) >= 4 ? 1024 : 256) /* tiny k: fewer warps, deeper queues */
 #define VG_QUEUE_ENTRIES(S) (32 + 32 * (16 / (S)) + 32)  /* per warp: a drain's leftovers + one tile, + 32 tag matches awaiting verification */
 #define VG_QUEUE_BYTES(S, DEFER) ((VG_THREADS(S, DEFER) / 32) * VG_QUEUE_ENTRIES(S) * 8)
-#define VG_FILTER_BUDGET_WORDS(S, DEFER) ((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S, DEFER)) / 4) & ~3))
+#define VG_FILTER_BUDGET_WORDS(S, DEFER) \
+	((uint32_t)(((VG_SMEM_BUDGET - VG_QUEUE_BYTES(S, DEFER) - VG_PAIR_TABLE_BYTES) / 4) & ~3))
 
 /* exact-table payload: an oriented pattern k-mer (stream encoding) with the offset of the
  * anchor it is filed under.  16 bytes so one LDG.128 fetches it. */
@@ -84,6 +90,16 @@ VG_HD uint32_t vg_rc32(uint32_t x, int L)
 	return r >> (32 - 2 * L); /* the L bases sit at the top after reversal */
 }
 
+/* Filter key of an anchor.  Large panels (canon) use a function that is the same for an
+ * anchor and its reverse complement, so one filter entry serves both strands: the product
+ * a * rc(a) mod 2^32 -- symmetric like min(a, rc(a)) but a multiply (FMA pipe) instead of a
+ * compare-select (the integer ALU pipe is the scarce resource of the kernel). */
+VG_HD uint32_t vg_filter_key(uint32_t a, int L, int canon) { return canon ? a * vg_rc32(a, L) : a; }
+
+/* One multiply chain places an anchor everywhere.  h = key * odd constant; the 64-bit product
+ * h * n_words gives the filter word (high half) and a second, well mixed 32-bit value (low
+ * half) whose top bits pick the bit pair and the home bucket of the exact table.  On the
+ * device this is IMAD, IMAD.WIDE, IMAD.HI, IMAD.HI: all on the FMA pipe. */
 VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)
@@ -92,44 +108,37 @@ VG_HD uint32_t vg_mulhi(uint32_t a, uint32_t b)
 	return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-
-/* Filter key of an anchor.  Large panels (canon) use a function that is the same for an
- * anchor and its reverse complement, so one filter entry serves both strands: the upper half
- * of the product of the two, each moved to the top of its word -- symmetric like
- * min(a, rc(a)) but multiplies (FMA pipe) instead of a compare-select, and the shifts to the
- * top drop whatever a 32-bit window of the stream holds beyond the anchor, so the kernel never
- * masks (the integer ALU pipe is the scarce resource of the kernel). */
-VG_HD uint32_t vg_filter_key(uint32_t a, int L, int canon)
-{
-	const int up = 32 - 2 * L;
-	return canon ? vg_mulhi(a << up, vg_rc32(a, L) << up) : a;
-}
-
-/* One multiply chain places an anchor everywhere.  h = key * odd constant; the 64-bit product
- * h * n_words gives the filter word (high half) and a second, well mixed 32-bit value `lo`
- * (low half; n_words is odd, so key -> lo is a bijection); a third, g = high half of
- * h * another constant.  On the device: IMAD, IMAD.WIDE, IMAD.HI -- all on the FMA pipe.
- *   filter (shared memory)  word = hi(h * n_words), bits lo & 31 and g & 31: the kernel tests
- *                           them by shifting the word (the shifter takes the amount modulo 32)
- *   second level (L2)       word = 1 + hi(lo * (n_words2 - 2)), bit lo & 31; the first and the
- *                           last word of the array stay zero: anchors that failed the first
- *                           level read one of them
- *   exact table             home bucket = hi(lo * n_buckets)                                   */
-#define VG_HASH_C1 0x9E3779B1u
-#define VG_HASH_C2 0x85EBCA6Bu
-VG_HD uint32_t vg_hash1(uint32_t key) { return key * VG_HASH_C1; }
-VG_HD uint32_t vg_hash_g(uint32_t h) { return vg_mulhi(h, VG_HASH_C2); }
+VG_HD uint32_t vg_hash1(uint32_t key) { return key * 0x9E3779B1u; }
 VG_HD uint32_t vg_filter_word(uint32_t key, uint32_t n_words) { return vg_mulhi(vg_hash1(key), n_words); }
 VG_HD uint32_t vg_hash_lo(uint32_t key, uint32_t n_words) { return vg_hash1(key) * n_words; }
-VG_HD uint32_t vg_filter_mask(uint32_t key, uint32_t n_words)
+
+/* Blocked Bloom filter: one 32-bit word per key, two bits in it (the same bit twice for one key
+ * in 32).  VG_PAIR_ALU: the bit positions are the top two 5-bit fields of `lo` and the mask is
+ * made with four shifts; otherwise the pair comes from a 992-entry table (shared memory on
+ * the device): entry i * 31 + j names bits i and (j < i ? j : j + 1). */
+VG_HD uint32_t vg_pair_index(uint32_t lo) { return vg_mulhi(lo, VG_PAIRS); }
+VG_HD uint32_t vg_pair_mask(uint32_t idx)
 {
-	return (1u << (vg_hash_lo(key, n_words) & 31u)) | (1u << (vg_hash_g(vg_hash1(key)) & 31u));
+	const uint32_t i = idx / 31u, j = idx % 31u;
+	return (1u << i) | (1u << (j < i ? j : j + 1u));
 }
+#if VG_PAIR_ALU
+VG_HD uint32_t vg_lo_mask(uint32_t lo) { return (1u << (lo >> 27)) | (1u << ((lo >> 22) & 31u)); }
+VG_HD uint32_t vg_pair_frac(uint32_t lo) { return lo << 10; } /* the bits of lo the pair did not use */
+#else
+VG_HD uint32_t vg_lo_mask(uint32_t lo) { return vg_pair_mask(vg_pair_index(lo)); }
+VG_HD uint32_t vg_pair_frac(uint32_t lo) { return lo * VG_PAIRS; } /* the low half of the same product: where in the pair's cell lo falls */
+#endif
+VG_HD uint32_t vg_filter_mask(uint32_t key, uint32_t n_words) { return vg_lo_mask(vg_hash_lo(key, n_words)); }
+
+/* Second filter level (large panels): the same two bits in a word of a much bigger array that
+ * lives in L2 (a few MB: >= 128 bits per key).  Only anchors that passed the on-chip filter
+ * look at it, one 4-byte load each; what passes both goes to the exact table.  The word comes
+ * from the part of the hash the pair did not use. */
 VG_HD uint32_t vg_filter2_word(uint32_t key, uint32_t n_words, uint32_t n_words2)
 {
-	return 1u + vg_mulhi(vg_hash_lo(key, n_words), n_words2 - 2u);
+	return vg_mulhi(vg_pair_frac(vg_hash_lo(key, n_words)), n_words2);
 }
-VG_HD uint32_t vg_filter2_mask(uint32_t key, uint32_t n_words) { return 1u << (vg_hash_lo(key, n_words) & 31u); }
 
 /* Exact table: buckets of 16 bytes (one LDG.128) = three 32-bit tags + one control word.
  *   tag   the forward anchor (low 31 bits | bit 31 when L = 16, so that it never equals

@@ -95,56 +95,59 @@ struct AnchorParams {
 	                          IMAD (FMA pipe) instead of LEA (integer ALU pipe) */
 };
 
-/* distance of the L2 prefetch ahead of the register pipeline, in bytes (8 tiles) */
+/* Distance of the L2 prefetch ahead of the register pipeline, in bytes, and the cache policy
+ * of every global load, per form of the kernel -- measured, not derived (profiles/r2_anchor_knobs.txt):
+ *   queue form (small panels)     8 tiles ahead; the stream is read once and evict-first in L1
+ *                                 and L2 (ld.global.cs), the exact table evict-last in L2;
+ *   deferred form (large panels)  2 tiles ahead of a raw chunk that is itself loaded two steps
+ *                                 before it is packed (three register buffers); stream, second
+ *                                 filter level and exact table all through L2 only with the
+ *                                 default priority (ld.global.cg).  With evict-first stream loads
+ *                                 and evict-last table loads the same kernel runs 9 % slower:
+ *                                 half of every GPU's L2 traffic crosses the die-to-die link and
+ *                                 the priorities cost more there than they save. */
 #ifndef VG_PF_BYTES
 #define VG_PF_BYTES 4096
 #endif
-#define VG_PF_CLAMP 1
-/* how many tiles ahead of its use a raw chunk is loaded in the deferred form (1: two register
- * buffers, 2: three) */
+#ifndef VG_PF_BYTES_DEFER
+#define VG_PF_BYTES_DEFER 1024
+#endif
+/* how many steps before it is packed a raw chunk of the deferred form is loaded (1: two
+ * register buffers, 2: three) */
 #ifndef VG_AHEAD
-#define VG_AHEAD 1
+#define VG_AHEAD 2
 #endif
-/* second-level word index of a non-survivor: by select (1) or by multiplies only (0) */
-#ifndef VG_IDX_SELECT
-#define VG_IDX_SELECT 1
-#endif
+template <bool DEFER> struct Knobs {
+	static constexpr int kPrefetch = DEFER ? VG_PF_BYTES_DEFER : VG_PF_BYTES;
+};
 
 __device__ __forceinline__ void l2_prefetch(const void *ptr)
 {
 	asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
-__device__ __forceinline__ void l2_prefetch_ahead(const void *ptr)
+template <int BYTES> __device__ __forceinline__ void l2_prefetch_ahead(const void *ptr)
 {
-#if VG_PF_BYTES > 0
-	asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(ptr), "n"(VG_PF_BYTES));
-#endif
+	if (BYTES > 0) asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(ptr), "n"(BYTES));
 }
 
-/* the stream load: read once, 16 bytes per lane, evict-first in L1 and L2 */
-__device__ __forceinline__ uint4 ld_stream(const uint4 *ptr) { return __ldcs(ptr); }
+/* the stream load: 16 bytes per lane, read once */
+template <bool DEFER> __device__ __forceinline__ uint4 ld_stream(const uint4 *ptr) { return DEFER ? __ldcg(ptr) : __ldcs(ptr); }
 
-/* The exact table is hit at random while gigabytes stream past it: its lines are loaded
- * with an evict-last L2 policy so the stream (loaded evict-first) does not push them out. */
+/* The exact table is hit at random while gigabytes stream past it.  Queue form: its lines are
+ * loaded with an evict-last L2 policy so the stream (loaded evict-first) does not push them out. */
 __device__ __forceinline__ uint64_t l2_keep_policy()
 {
 	uint64_t pol;
 	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 	return pol;
 }
-__device__ __forceinline__ uint4 ldg_keep(const uint4 *ptr, uint64_t pol)
+template <bool DEFER> __device__ __forceinline__ uint4 ldg_table(const uint4 *ptr, uint64_t pol)
 {
+	if (DEFER) return __ldcg(ptr);
 	uint4 v;
 	asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
 	             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
 	             : "l"(ptr), "l"(pol));
-	return v;
-}
-
-__device__ __forceinline__ uint32_t ldg_keep(const uint32_t *ptr, uint64_t pol)
-{
-	uint32_t v;
-	asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
 	return v;
 }
 
@@ -162,14 +165,14 @@ __device__ __forceinline__ uint32_t rc16(uint32_t x)
  * ends; the k raw bytes of that place in the stream decide.  Batching them makes the two
  * dependent L2 round trips (payload, then bytes) happen once per 32 verifications instead of
  * once each, and lets the counter update aggregate over the warp. */
-template <int S>
+template <int S, bool DEFER>
 __device__ __forceinline__ uint32_t verify_batch(const AnchorParams &p, const uint2 *vq, uint32_t n, uint32_t lane)
 {
 	bool ok = false;
 	uint32_t val = 0;
 	if (lane < n) {
 		const uint2 e = vq[lane];
-		const uint4 raw = ldg_keep(reinterpret_cast<const uint4 *>(p.slots) + e.x, p.keep);
+		const uint4 raw = ldg_table<DEFER>(reinterpret_cast<const uint4 *>(p.slots) + e.x, p.keep);
 		const uint64_t okey = (uint64_t)raw.y << 32 | raw.x;
 		const uint64_t end = p.range_lo + (uint64_t)e.y * (uint32_t)S + raw.w; /* the k-mer would occupy [end - k, end) */
 		val = raw.z;
@@ -195,15 +198,14 @@ __device__ __forceinline__ uint32_t verify_batch(const AnchorParams &p, const ui
 /* filter key of an anchor as the kernel's generic (slow) paths compute it */
 template <bool CANON> __device__ __forceinline__ uint32_t anchor_key(uint32_t a, int L)
 {
-	const int up = 32 - 2 * L; /* rc16 leaves the L bases at the top of the word, complemented padding below them */
-	return CANON ? __umulhi(a << up, rc16(a) >> up << up) : a;
+	return CANON ? a * (rc16(a) >> (32 - 2 * L)) : a;
 }
 
 /* First stage: resolve n <= 32 queued anchors, one per lane.  Fetch the anchor's home bucket
  * (three tags + control word, one 16-byte load from L2); a matching tag (rare: the anchor
  * really is one a pattern carries) goes to the verify queue; the control word says whether
  * entries of this chain live further on. */
-template <int S, bool CANON>
+template <int S, bool CANON, bool DEFER>
 __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uint2 *wq, uint32_t first, uint32_t n,
                                                 uint2 *vq, uint32_t &vn, uint32_t lane, uint32_t lt_mask)
 {
@@ -215,7 +217,7 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
 	uint32_t b = vg_bucket_home(vg_hash_lo(anchor_key<CANON>(e.x, p.len), p.filter_words), p.n_buckets), hits = 0;
 	while (__any_sync(FULL, active)) {
 		uint4 t = make_uint4(VG_FREE_TAG, VG_FREE_TAG, VG_FREE_TAG, 0u);
-		if (active) t = ldg_keep(p.buckets + b, keep);
+		if (active) t = ldg_table<DEFER>(p.buckets + b, keep);
 		uint32_t mm = (t.x == tag ? 1u : 0u) | (t.y == tag ? 2u : 0u) | (t.z == tag ? 4u : 0u);
 		if (!active) mm = 0;
 		while (__any_sync(FULL, mm != 0)) { /* rare: queue one matching slot per lane and round */
@@ -223,7 +225,7 @@ __device__ __forceinline__ uint32_t drain_queue(const AnchorParams &p, const uin
 			const uint32_t votes = __ballot_sync(FULL, m);
 			if (vn + __popc(votes) > 32) { /* make room: run a full batch first */
 				__syncwarp();
-				hits += verify_batch<S>(p, vq, vn, lane);
+				hits += verify_batch<S, DEFER>(p, vq, vn, lane);
 				vn = 0;
 				__syncwarp();
 			}
@@ -266,32 +268,15 @@ __device__ __forceinline__ uint32_t lds_word(uint32_t base, uint32_t idx, uint32
 	return v;
 }
 
-/* word >> (amount mod 32): the shifter takes the amount modulo 32, so any register whose low
- * five bits are hash bits names a bit position without being masked first */
-__device__ __forceinline__ uint32_t shr_wrap(uint32_t word, uint32_t amount) { return __funnelshift_r(word, 0u, amount); }
-
-/* both filter bits of an anchor set in `word`?  (positions lo & 31 and g & 31); 0 or 1 */
-__device__ __forceinline__ uint32_t both_bits(uint32_t word, uint32_t lo, uint32_t g)
+/* the two filter bits of an anchor whose hash tail is `lo` */
+__device__ __forceinline__ uint32_t pair_mask(uint32_t pairs, uint32_t lo, uint32_t four)
 {
-	return shr_wrap(word, lo) & shr_wrap(word, g) & 1u;
-}
-
-/* the same as a predicate straight out of the logic unit (no compare) */
-__device__ __forceinline__ bool both_bits_p(uint32_t word, uint32_t lo, uint32_t g)
-{
-	uint32_t d, r;
-	asm("{\n\t.reg .pred p;\n\tlop3.or.b32 %0|p, %2, %3, 1, 0x80, 0;\n\tselp.u32 %1, 1, 0, p;\n\t}"
-	    : "=r"(d), "=r"(r)
-	    : "r"(shr_wrap(word, lo)), "r"(shr_wrap(word, g)));
-	return r != 0;
-}
-
-/* (a | b) & 1 != 0, likewise */
-__device__ __forceinline__ bool low_bit_of_either(uint32_t a, uint32_t b)
-{
-	uint32_t d, r;
-	asm("{\n\t.reg .pred p;\n\tlop3.or.b32 %0|p, %2, %3, 1, 0xA8, 0;\n\tselp.u32 %1, 1, 0, p;\n\t}" : "=r"(d), "=r"(r) : "r"(a), "r"(b));
-	return r != 0;
+#if VG_PAIR_ALU
+	/* shf.l.wrap takes the shift amount modulo 32, so the second field needs no masking */
+	return (1u << (lo >> 27)) | __funnelshift_l(0u, 1u, lo >> 22);
+#else
+	return lds_word(pairs, vg_pair_index(lo), four);
+#endif
 }
 
 /* The anchors of one chunk and their fate in the filter.  They end at the chunk's aligned
@@ -300,13 +285,13 @@ __device__ __forceinline__ bool low_bit_of_either(uint32_t a, uint32_t b)
  *   LS  anchor length fixed at compile time (0 = take it from the parameters) */
 template <int S, bool CANON, int LS>
 __device__ __forceinline__ void probe_anchors(const AnchorParams &p, uint32_t cur, uint32_t left, uint32_t rcur, uint32_t rleft,
-                                              uint32_t filter, uint32_t (&a)[16 / S], bool (&hit)[16 / S])
+                                              uint32_t filter, uint32_t pairs, uint32_t (&a)[16 / S], bool (&hit)[16 / S],
+                                              uint32_t (&lo)[16 / S])
 {
 	constexpr int NA = 16 / S;
 	const uint32_t nw = p.filter_words;
 	const int L = LS ? LS : p.len;
 	const uint32_t amask = vg_mask32(L);
-	const int up = 32 - 2 * L;
 #pragma unroll
 	for (int j = 0; j < NA; ++j) {
 		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
@@ -315,18 +300,23 @@ __device__ __forceinline__ void probe_anchors(const AnchorParams &p, uint32_t cu
 		if (L < 16 && !(sh >= 0 && sh + 2 * L == 32)) a[j] &= amask;
 		uint32_t key = a[j];
 		if (CANON) {
-			/* symmetric in an anchor and its reverse complement.  rc(a) is a window of the
-			 * reverse-complemented words: base i of the chunk sits at 15 - i of rcur */
+			/* a * rc(a): the same for an anchor and its reverse complement.  rc(a) is a window of
+			 * the reverse-complemented words: base i of the chunk sits at 15 - i of rcur */
 			const int rsh = 2 * (16 - (j + 1) * S);
-			const uint32_t r = rsh == 0 ? rcur : __funnelshift_r(rcur, rleft, rsh & 31);
-			key = __umulhi(a[j] << up, r << up);
+			uint32_t r = rsh == 0 ? rcur : __funnelshift_r(rcur, rleft, rsh & 31);
+			if (L < 16) r &= amask;
+			key = a[j] * r;
 		}
-		const uint32_t h = vg_hash1(key);
-		const uint64_t prod = (uint64_t)h * nw;
+		const uint64_t prod = (uint64_t)vg_hash1(key) * nw;
+		lo[j] = (uint32_t)prod;
 		const uint32_t word = lds_word(filter, (uint32_t)(prod >> 32), p.c4);
-		hit[j] = both_bits(word, (uint32_t)prod, vg_hash_g(h)) != 0;
+		const uint32_t pm = pair_mask(pairs, lo[j], p.c4);
+		hit[j] = (~word & pm) == 0;
 	}
 }
+
+/* the check of a pending survivor: did it pass the second filter level as well? */
+__device__ __forceinline__ bool passed2(uint32_t w, uint32_t pm) { return (~w & pm) == 0; }
 
 /* ---- queue path ---- */
 
@@ -335,16 +325,13 @@ __device__ __forceinline__ void probe_anchors(const AnchorParams &p, uint32_t cu
  * consumer of loaded data is the pack at the very end. */
 template <int S, bool CANON, int LS, bool INTERIOR>
 __device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint32_t t1, uint4 &fill, const uint4 &use, uint32_t filter,
-                                          uint2 *wq, uint32_t lane, uint32_t lt_mask)
+                                          uint32_t pairs, uint2 *wq, uint32_t lane, uint32_t lt_mask)
 {
 	constexpr int NA = 16 / S;
 	const uint32_t last = p.n_chunks - 1;
-	fill = ld_stream(p.chunks + (INTERIOR ? s.c + 96 : min(s.c + 96, last)));
-#if VG_PF_CLAMP /* prefetch inside the span only: the next span's owner prefetches its own start */
-	if (INTERIOR && s.t + VG_PF_BYTES / 512 < t1) l2_prefetch_ahead(p.chunks + s.c); /* this lane's chunk, some tiles on */
-#else
-	if (INTERIOR) l2_prefetch_ahead(p.chunks + s.c);
-#endif
+	fill = ld_stream<false>(p.chunks + (INTERIOR ? s.c + 96 : min(s.c + 96, last)));
+	/* prefetch inside the span only: the next span's owner prefetches its own start */
+	if (INTERIOR && s.t + VG_PF_BYTES / 512 < t1) l2_prefetch_ahead<VG_PF_BYTES>(p.chunks + s.c); /* this lane's chunk, some tiles on */
 	/* one rotate serves both needs: lanes 1..31 get their left neighbour, lane 0 gets lane 31's
 	 * chunk, which is its left neighbour in the NEXT tile */
 	const uint32_t rot = __shfl_sync(FULL, s.cur, (lane + 31) & 31);
@@ -354,9 +341,9 @@ __device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint32
 		rrot = __shfl_sync(FULL, s.rcur, (lane + 31) & 31);
 		rleft = lane == 0 ? s.rcarry : rrot;
 	}
-	uint32_t a[NA];
+	uint32_t a[NA], lo[NA];
 	bool hit[NA];
-	probe_anchors<S, CANON, LS>(p, s.cur, left, s.rcur, rleft, filter, a, hit);
+	probe_anchors<S, CANON, LS>(p, s.cur, left, s.rcur, rleft, filter, pairs, a, hit, lo);
 #pragma unroll
 	for (int j = 0; j < NA; ++j) {
 		if (!INTERIOR) hit[j] = hit[j] && s.c <= last;
@@ -382,21 +369,21 @@ __device__ __forceinline__ void scan_tile(const AnchorParams &p, Pipe &s, uint32
  * register copies.  INTERIOR: every address touched (loads up to tile t1+2, prefetch some
  * tiles further) is inside the range, so nothing is clamped or predicated. */
 template <int S, bool CANON, int LS, bool INTERIOR>
-__device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, uint32_t filter,
+__device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint32_t t1, uint32_t filter, uint32_t pairs,
                                            uint2 *wq, uint32_t lane, uint32_t lt_mask)
 {
 	for (;;) {
 		if (s.phase == 0) {
-			scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w2, s.w0, filter, wq, lane, lt_mask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w2, s.w0, filter, pairs, wq, lane, lt_mask);
 			s.phase = 1;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
 		if (s.phase == 1) {
-			scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w0, s.w1, filter, wq, lane, lt_mask);
+			scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w0, s.w1, filter, pairs, wq, lane, lt_mask);
 			s.phase = 2;
 			if (s.t >= t1 || s.qn >= 32) break;
 		}
-		scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w1, s.w2, filter, wq, lane, lt_mask);
+		scan_tile<S, CANON, LS, INTERIOR>(p, s, t1, s.w1, s.w2, filter, pairs, wq, lane, lt_mask);
 		s.phase = 0;
 		if (s.t >= t1 || s.qn >= 32) break;
 	}
@@ -408,8 +395,8 @@ __device__ __forceinline__ void scan_tiles(const AnchorParams &p, Pipe &s, uint3
  * registers (opaque to ptxas, which would otherwise re-read them from the constant bank, or
  * recompute them, once per tile) */
 struct DeferCtx {
-	uint32_t filter; /* shared-memory address */
-	uint32_t nw, four, nkw, rot_lane;
+	uint32_t filter, pairs; /* shared-memory addresses */
+	uint32_t nw, four, nw2, rot_lane;
 	const uint4 *chunks;
 	const uint32_t *filter2;
 	uint64_t keep;
@@ -431,49 +418,46 @@ template <typename T> __device__ __forceinline__ const T *pin(const T *v, uint32
 	return reinterpret_cast<const T *>(u);
 }
 
-/* The anchors of one tile on their way through the second filter level, per lane:
- *   t   the anchor, moved to the top of the word (anchor = t >> (32 - 2L))
- *   lo  its hash tail: names the bit (lo & 31) to find in the second-level word
- *   x   first the index of that word -- word 0 of the array, which is zero, for an anchor
- *       that failed the first level -- then, loaded in place, the word itself */
-template <int NA> struct Slots {
-	uint32_t t[NA], lo[NA], x[NA];
-};
-
-/* the rare branch: queue the anchors of `q` that passed the second level as well (c = the
- * lane's chunk in their tile) for the resolver */
+/* the rare branch of the deferred path: queue the flagged anchors of the tile whose lane
+ * chunk is `c`; the caller leaves the streaming loop when 32 are waiting */
 template <int S, int LS>
-__device__ __forceinline__ void defer_slow(const AnchorParams &p, Pipe &s, const Slots<16 / S> &q, uint32_t c, DeferCtx &x)
+__device__ __forceinline__ void defer_slow(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, uint32_t c, DeferCtx &x)
 {
 	constexpr int NA = 16 / S;
-	const int up = 32 - 2 * (LS ? LS : p.len);
 #pragma unroll
 	for (int j = 0; j < NA; ++j) {
-		const bool flag = (shr_wrap(q.x[j], q.lo[j]) & 1u) != 0;
+		const bool flag = passed2(pd.w[j], pd.pm[j]);
 		const uint32_t votes = __ballot_sync(FULL, flag);
-		if (flag) x.wq[s.qn + __popc(votes & x.lt_mask)] = make_uint2(q.t[j] >> up, c * NA + j + 1);
+		if (flag) x.wq[s.qn + __popc(votes & x.lt_mask)] = make_uint2(pd.a[j], c * NA + j + 1);
 		s.qn += __popc(votes);
 	}
 }
 
-/* did any anchor of `q`, anywhere in the warp, pass the second level? */
-template <int NA> __device__ __forceinline__ bool defer_any(const Slots<NA> &q)
+template <int S, int LS>
+__device__ __forceinline__ void defer_check(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, uint32_t c, DeferCtx &x)
 {
-	uint32_t any = 0;
+	constexpr int NA = 16 / S;
+	bool any = false;
 #pragma unroll
-	for (int j = 0; j + 2 < NA; ++j) any |= shr_wrap(q.x[j], q.lo[j]);
-	const bool mine = NA == 1 ? low_bit_of_either(shr_wrap(q.x[0], q.lo[0]), 0u)
-	                          : low_bit_of_either(any | shr_wrap(q.x[NA - 2], q.lo[NA - 2]), shr_wrap(q.x[NA - 1], q.lo[NA - 1]));
-	return __any_sync(FULL, mine);
+	for (int j = 0; j < NA; ++j) any = any || passed2(pd.w[j], pd.pm[j]);
+	if (__any_sync(FULL, any)) defer_slow<S, LS>(p, s, pd, c, x);
 }
 
-/* probe the anchors of the tile in s.cur into `q` */
+/* the probes of one tile, waiting for their turn at the second filter level: the anchors,
+ * their bit pairs, and the word to fetch for those that passed the first level
+ * (VG_NO_WORD otherwise) */
+#define VG_NO_WORD 0xFFFFFFFFu
+template <int NA> struct Probed {
+	uint32_t a[NA], pm[NA], word2[NA];
+};
+
+/* probe the anchors of the tile in s.cur */
 template <int S, int LS, bool INTERIOR>
-__device__ __forceinline__ void defer_probe(const AnchorParams &p, Pipe &s, Slots<16 / S> &q, uint32_t rot, uint32_t rrot, DeferCtx &x)
+__device__ __forceinline__ void defer_probe(const AnchorParams &p, Pipe &s, Probed<16 / S> &nx, uint32_t rot, uint32_t rrot, DeferCtx &x)
 {
 	constexpr int NA = 16 / S;
 	const int L = LS ? LS : p.len;
-	const int up = 32 - 2 * L;
+	const uint32_t amask = vg_mask32(L);
 	/* rot / rrot: s.cur / s.rcur rotated by one lane.  One rotate serves both needs: lanes 1..31
 	 * get their left neighbour, lane 0 gets lane 31's chunk, which is its left neighbour in the
 	 * NEXT tile */
@@ -481,152 +465,113 @@ __device__ __forceinline__ void defer_probe(const AnchorParams &p, Pipe &s, Slot
 	const uint32_t rleft = x.lane == 0 ? s.rcarry : rrot;
 #pragma unroll
 	for (int j = 0; j < NA; ++j) {
-		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0: a 32-bit
-		 * window whose low 2L bits are the anchor; moving it to the top drops the rest */
+		/* bases [s0, s0 + L) relative to the chunk start, s0 = (j+1) S - L, possibly < 0 */
 		const int sh = 2 * ((j + 1) * S - L);
-		const uint32_t a = sh >= 0 ? s.cur >> (sh & 31) : __funnelshift_r(left, s.cur, (sh + 32) & 31);
-		/* rc(a) is a window of the reverse-complemented words: base i of the chunk sits at 15 - i of rcur */
+		uint32_t a = sh >= 0 ? s.cur >> (sh & 31) : __funnelshift_r(left, s.cur, (sh + 32) & 31);
+		if (L < 16 && !(sh >= 0 && sh + 2 * L == 32)) a &= amask;
+		/* a * rc(a): the same for an anchor and its reverse complement.  rc(a) is a window of
+		 * the reverse-complemented words: base i of the chunk sits at 15 - i of rcur */
 		const int rsh = 2 * (16 - (j + 1) * S);
-		const uint32_t r = rsh == 0 ? s.rcur : __funnelshift_r(s.rcur, rleft, rsh & 31);
-		const uint32_t t = a << up;
-		const uint32_t h = vg_hash1(__umulhi(t, r << up));
-		const uint64_t prod = (uint64_t)h * x.nw;
+		uint32_t r = rsh == 0 ? s.rcur : __funnelshift_r(s.rcur, rleft, rsh & 31);
+		if (L < 16) r &= amask;
+		const uint64_t prod = (uint64_t)vg_hash1(a * r) * x.nw;
 		const uint32_t lo = (uint32_t)prod;
 		const uint32_t word = lds_word(x.filter, (uint32_t)(prod >> 32), x.four);
-		q.t[j] = t;
-		q.lo[j] = lo;
-#if VG_IDX_SELECT
-		/* x.filter2 points at word 1: word hi(lo * n) for a survivor, word n (zero) for the rest */
-		bool hit = both_bits_p(word, lo, vg_hash_g(h));
+		const uint32_t pm = pair_mask(x.pairs, lo, x.four);
+		bool hit = (~word & pm) == 0;
 		if (!INTERIOR) hit = hit && s.c <= p.n_chunks - 1;
-		q.x[j] = hit ? __umulhi(lo, x.nkw) : x.nkw;
-#else
-		/* word 1 + hi(lo * n) of the second level for a survivor, word 0 (zero) for the rest,
-		 * without a select: multiplies only */
-		uint32_t hit = both_bits(word, lo, vg_hash_g(h)); /* 0 or 1 */
-		if (!INTERIOR) hit = s.c <= p.n_chunks - 1 ? hit : 0u;
-		q.x[j] = __umulhi(lo, hit * x.nkw) + hit;
-#endif
+		nx.a[j] = a;
+nx.pm[j] = pm;
+		nx.word2[j] = hit ? vg_mulhi(vg_pair_frac(lo), x.nw2) : VG_NO_WORD;
 	}
 	s.carry = rot; /* only lane 0's copy is ever used */
 	s.rcarry = rrot;
 }
 
-/* One step of the deferred path's software pipeline, for tile k whose raw chunk (loaded one
- * or two steps ago) is in `use` and whose lane chunk is s.c.  On entry `probed` holds the
- * probes of tile k-1 and `pending` the second-level words tile k-2's survivors asked for, in
- * flight.  ptxas tracks every global load of this kernel with ONE scoreboard, so whoever waits
- * for a load waits for all loads issued so far.  The step is therefore arranged around a
- * single wait:
- *   first everything that consumes a load: the words in `pending` are looked at, tile k is packed;
- *   then every new load: the words for `probed` (loaded over their own indices: the two sets
- *     of registers swap roles from step to step and nothing is copied), the refill of the raw
- *     buffer an earlier step packed (tile k + VG_AHEAD; the L2 prefetch runs further ahead);
- *   then the probes of tile k, into the registers `pending` no longer needs.
- * Returns false when the resolver has to run: 32 anchors are queued.  Tile k-2 is then done,
- * nothing has been asked for tile k-1: the caller re-opens the span there. */
-template <int S, int LS, bool INTERIOR, bool PREFETCH>
-__device__ __forceinline__ bool defer_step(const AnchorParams &p, Pipe &s, Slots<16 / S> &pending, Slots<16 / S> &probed, uint4 &fill,
-                                           const uint4 &use, DeferCtx &x)
+/* One step of the deferred path's software pipeline.  On entry the probes of tile k-1 are in
+ * `nx`, the second-level words its predecessor's survivors asked for are in flight in `pd`,
+ * s.c is the lane's chunk of tile k (raw in `use`, loaded a step ago).  ptxas tracks every
+ * global load of this kernel with ONE scoreboard, so whoever waits for a load waits for all
+ * loads issued so far.  The step is therefore arranged around a single wait:
+ *   first everything that consumes a load: the words of tile k-2's survivors are looked at,
+ *     tile k is packed;
+ *   then every new load: the words for tile k-1's survivors, and the refill of the raw buffer
+ *     the previous step packed (tile k+1; the L2 prefetch runs further ahead);
+ *   then the probes of tile k, which carry over to the next step.
+ * Each load so gets one whole step to arrive.  (The refill sits behind the previous step's
+ * closing branch, not next to the pack that emptied its buffer: there ptxas hoists it above
+ * the pack's last reads and then needs a temporary -- and a copy that waits for the load.) */
+template <int S, int LS, bool INTERIOR>
+__device__ __forceinline__ void defer_step(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, Probed<16 / S> &nx, uint4 &fill,
+                                           const uint4 &use, uint32_t t1, DeferCtx &x)
 {
 	constexpr int NA = 16 / S;
 	const uint32_t last = p.n_chunks - 1;
 	/* everything that consumes a load first ... */
-	if (defer_any<NA>(pending)) {
-		defer_slow<S, LS>(p, s, pending, s.c - 64, x);
-		if (s.qn >= 32) return false;
-	}
+	defer_check<S, LS>(p, s, pd, s.c - 64, x);
 	s.cur = pack16(use);
 	s.rcur = rc16(s.cur);
-	/* ... then every new load */
+	/* ... then every new load.  A lane without a survivor keeps the word of an older one.  That
+	 * can only cause a false alarm (the stale word happens to hold the new pair), never a miss:
+	 * an anchor some pattern carries passes the first level, so its word is fetched afresh; and
+	 * whatever is flagged is resolved exactly by drain_queue. */
 #pragma unroll
-	for (int j = 0; j < NA; ++j) probed.x[j] = ldg_keep(x.filter2 + probed.x[j], x.keep);
-	const uint4 *const next = x.chunks + (INTERIOR ? s.c + 32 * VG_AHEAD : min(s.c + 32 * VG_AHEAD, last));
-	fill = ld_stream(next);
-	if (PREFETCH) l2_prefetch_ahead(next);
+	for (int j = 0; j < NA; ++j) {
+		pd.a[j] = nx.a[j];
+		pd.pm[j] = nx.pm[j];
+		if (nx.word2[j] != VG_NO_WORD) pd.w[j] = __ldcg(x.filter2 + nx.word2[j]);
+	}
+	fill = ld_stream<true>(x.chunks + (INTERIOR ? s.c + 32 * VG_AHEAD : min(s.c + 32 * VG_AHEAD, last)));
+	/* prefetch inside the span only: the next span's owner prefetches its own start */
+	if (INTERIOR && s.t + VG_AHEAD + VG_PF_BYTES_DEFER / 512 < t1) l2_prefetch_ahead<VG_PF_BYTES_DEFER>(x.chunks + s.c + 32 * VG_AHEAD);
 	{
 		const uint32_t rot = __shfl_sync(FULL, s.cur, x.rot_lane);
 		const uint32_t rrot = NA > 1 ? __shfl_sync(FULL, s.rcur, x.rot_lane) : 0u;
-		defer_probe<S, LS, INTERIOR>(p, s, pending, rot, rrot, x);
+		defer_probe<S, LS, INTERIOR>(p, s, nx, rot, rrot, x);
 	}
+	++s.t;
 	s.c += 32;
-	return true;
 }
 
 /* The hot loop of the deferred path: tiles from s.t up to t1, or until 32 anchors are queued
- * for the resolver (the caller runs it and comes back).  On entry s.cur holds tile s.t, s.w0
- * (and s.w1) the raw tiles after it, s.c is the lane's chunk of tile s.t.  The pipeline probes
- * one tile past the last one whose second-level words it requests (that tile is probed again by
- * whoever scans it).  On return tiles up to s.t - 1 are done except for the words in pd (tile
- * s.t - 1, lane chunk s.c - 32), which the caller looks at; s.c is the lane's chunk of tile s.t. */
+ * for the resolver (the caller runs it and comes back).  s.cur and s.w0 hold tiles s.t and
+ * s.t + 1 on entry, s.c is the lane's chunk of tile s.t, pd is empty.  The pipeline probes one
+ * tile past the last one whose buckets it requests (that tile is probed again by whoever scans
+ * it).  On return tiles up to s.t - 1 are done except for the buckets in pd (tile s.t - 1,
+ * lane chunk s.c - 32), which the caller looks at. */
 template <int S, int LS, bool INTERIOR>
-__device__ __forceinline__ void defer_span(const AnchorParams &p, Pipe &s, Slots<16 / S> &pd, uint32_t t1, DeferCtx &x)
+__device__ __forceinline__ void defer_span(const AnchorParams &p, Pipe &s, Pending<16 / S> &pd, uint32_t t1, DeferCtx &x)
 {
 	constexpr int NA = 16 / S;
-	Slots<NA> qa, qb;
-#pragma unroll
-	for (int j = 0; j < NA; ++j) qb.x[j] = qb.lo[j] = qb.t[j] = 0; /* nothing pending */
+	Probed<NA> nx;
 	{
 		const uint32_t rot = __shfl_sync(FULL, s.cur, x.rot_lane);
 		const uint32_t rrot = NA > 1 ? __shfl_sync(FULL, s.rcur, x.rot_lane) : 0u;
-		defer_probe<S, LS, INTERIOR>(p, s, qa, rot, rrot, x); /* tile s.t */
+		defer_probe<S, LS, INTERIOR>(p, s, nx, rot, rrot, x); /* tile s.t */
 	}
+	++s.t;
 	s.c += 32;
-	/* steps k = s.t + 1 .. t1: step k checks tile k-2, requests the words of tile k-1, probes tile k.
-	 * n counts the steps left; s.c follows k.  The prefetch stays inside the span (the next
-	 * span's owner prefetches its own start): the last VG_PF_TILES + VG_AHEAD steps go without. */
-	uint32_t n = t1 - s.t;
-	const bool odd = (n & 1u) != 0; /* after an odd number of steps qa holds the words in flight, else qb */
-	bool full = false;
-	constexpr uint32_t kTail = VG_PF_BYTES / 512 + VG_AHEAD;
-	/* the registers rotate by name: two sets of slots, two or three raw buffers */
-#define VG_STEP(PF, PENDING, PROBED, FILL, USE)                                               \
-	if (!defer_step<S, LS, INTERIOR, PF>(p, s, PENDING, PROBED, FILL, USE, x)) {              \
-		full = true;                                                                          \
-		break;                                                                                \
-	}                                                                                         \
-	--n;
-#if VG_AHEAD == 1
-#define VG_ROUND(PF, BETWEEN)              \
-	VG_STEP(PF, qb, qa, s.w1, s.w0) BETWEEN \
-	VG_STEP(PF, qa, qb, s.w0, s.w1)
-	constexpr uint32_t kRound = 2;
-#else
-#define VG_ROUND(PF, BETWEEN)              \
-	VG_STEP(PF, qb, qa, s.w2, s.w0) BETWEEN \
-	VG_STEP(PF, qa, qb, s.w0, s.w1) BETWEEN \
-	VG_STEP(PF, qb, qa, s.w1, s.w2) BETWEEN \
-	VG_STEP(PF, qa, qb, s.w2, s.w0) BETWEEN \
-	VG_STEP(PF, qb, qa, s.w0, s.w1) BETWEEN \
-	VG_STEP(PF, qa, qb, s.w1, s.w2)
-	constexpr uint32_t kRound = 6;
-#endif
-	do {
-		if (INTERIOR && VG_PF_BYTES > 0) {
-			while (n >= kRound + kTail) { VG_ROUND(true, ) }
-			if (full) break;
-		}
-		while (n >= kRound) { VG_ROUND(false, ) }
-		if (full) break;
-		/* less than a round left, the registers are back in their first roles */
-		if (!n) break;
-		VG_ROUND(false, if (!n) break;)
-	} while (false);
-#undef VG_ROUND
-#undef VG_STEP
-	/* where the pipeline stands: k = t1 + 1 - n is the step that would come next (or the one that
-	 * bailed out before doing anything but its look at tile k-2) */
-	const uint32_t k = t1 + 1 - n;
-	s.c -= 32;
-	if (full) { /* tile k-2 is done; tile k-1 is probed but has no words requested: resume there, nothing pending */
-		s.t = k - 1;
-#pragma unroll
-		for (int j = 0; j < NA; ++j) pd.x[j] = pd.lo[j] = pd.t[j] = 0;
-		return;
+	/* from here s.t counts probed tiles; a step probes tile s.t and requests the buckets of tile s.t - 1 */
+#if VG_AHEAD == 2
+	for (;;) { /* three raw buffers: a chunk is loaded two steps before it is packed */
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w2, s.w0, t1, x);
+		if (s.t > t1 || s.qn >= 32) break;
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w0, s.w1, t1, x);
+		if (s.t > t1 || s.qn >= 32) break;
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w1, s.w2, t1, x);
+		if (s.t > t1 || s.qn >= 32) break;
 	}
-	/* ran to the end (k = t1 + 1): tile t1 - 1 has its words in flight, tile t1 was probed for nothing */
-	s.t = t1;
-	pd = odd ? qa : qb;
+#else
+	for (;;) {
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w1, s.w0, t1, x);
+		if (s.t > t1 || s.qn >= 32) break;
+		defer_step<S, LS, INTERIOR>(p, s, pd, nx, s.w0, s.w1, t1, x);
+		if (s.t > t1 || s.qn >= 32) break;
+	}
+#endif
+	/* back to "s.t = next tile to scan": the last probed tile (s.t - 1) has no buckets requested */
+	--s.t;
+	s.c -= 32;
 }
 
 /* Spans: warps take spans warp, warp + n_warps, ... so that at any time the resident warps read
@@ -651,7 +596,7 @@ __device__ __forceinline__ uint32_t span_end(const AnchorParams &p, uint32_t spa
 template <int S, bool CANON, bool DEFER, int LS>
 __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_kernel(const __grid_constant__ AnchorParams p)
 {
-	extern __shared__ uint32_t s_filter[]; /* filter words | candidate queues */
+	extern __shared__ uint32_t s_filter[]; /* filter words | bit-pair table | candidate queues */
 	using LC = Launch<S, DEFER>;
 	constexpr int NA = 16 / S;
 	const uint32_t nw = p.filter_words;        /* odd: what the hash is taken modulo */
@@ -660,13 +605,17 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 		const uint4 *src = reinterpret_cast<const uint4 *>(p.filter);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
 		for (uint32_t i = threadIdx.x; i < nwp / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+#if !VG_PAIR_ALU
+		for (uint32_t i = threadIdx.x; i < VG_PAIRS; i += blockDim.x) s_filter[nwp + i] = vg_pair_mask(i);
+#endif
 	}
 	__syncthreads();
 	const uint32_t filter_sa = (uint32_t)__cvta_generic_to_shared(s_filter);
+	const uint32_t pairs_sa = filter_sa + nwp * 4;
 
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nwp) + (threadIdx.x >> 5) * LC::kQueue;
+	uint2 *const wq = reinterpret_cast<uint2 *>(s_filter + nwp + VG_PAIR_TABLE_BYTES / 4) + (threadIdx.x >> 5) * LC::kQueue;
 	uint2 *const vq = wq + LC::kQueue - 32; /* the last 32 entries: tag matches awaiting verification */
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
@@ -689,12 +638,13 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 		 * beyond) lies inside the range.  Otherwise loads are clamped to the last chunk: a
 		 * chunk past the end is never scanned, and as a right neighbour it can only create a
 		 * false candidate, which the bounds check of the verification rejects. */
-		interior = (uint64_t)(t1 + 5 + VG_PF_BYTES / 512) * 32 <= p.n_chunks;
+		constexpr int kPf = Knobs<DEFER>::kPrefetch;
+		interior = (uint64_t)(t1 + 5 + kPf / 512) * 32 <= p.n_chunks;
 		s.c = s.t * 32 + lane;
-		if (interior && VG_PF_BYTES) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * (VG_PF_BYTES / 32));
-		s.cur = pack16(ld_stream(p.chunks + min(s.c, last)));
-		s.w0 = ld_stream(p.chunks + min(s.c + 32, last));
-		if (!DEFER || VG_AHEAD > 1) s.w1 = ld_stream(p.chunks + min(s.c + 64, last));
+		if (interior && kPf) l2_prefetch(reinterpret_cast<const uint8_t *>(p.chunks + s.t * 32) + lane * (kPf / 32));
+		s.cur = pack16(ld_stream<DEFER>(p.chunks + min(s.c, last)));
+		s.w0 = ld_stream<DEFER>(p.chunks + min(s.c + 32, last));
+		if (!DEFER || VG_AHEAD == 2) s.w1 = ld_stream<DEFER>(p.chunks + min(s.c + 64, last));
 		s.phase = 0;
 		/* the chunk before the span: the last one of the previous span, or of the previous
 		 * launch range; nothing ('\n's) at the very start of the stream */
@@ -711,19 +661,22 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 	if (DEFER) {
 		DeferCtx x;
 		const uint32_t z = (uint32_t)__cvta_generic_to_shared(vq + lane); /* scratch: this lane's verify-queue entry, not in use yet */
-		x.filter = pin(filter_sa, z), x.keep = p.keep, x.wq = wq, x.vq = vq, x.lane = lane, x.lt_mask = lt_mask;
-		x.nw = pin(nw, z), x.four = pin(p.c4, z), x.nkw = pin(p.filter2_words - 2u, z), x.rot_lane = pin((lane + 31) & 31, z);
-		x.chunks = pin(p.chunks, z), x.filter2 = pin(p.filter2 + (VG_IDX_SELECT ? 1 : 0), z);
+		x.filter = pin(filter_sa, z), x.pairs = pin(pairs_sa, z), x.keep = p.keep, x.wq = wq, x.vq = vq, x.lane = lane, x.lt_mask = lt_mask;
+		x.nw = pin(nw, z), x.four = pin(p.c4, z), x.nw2 = pin(p.filter2_words, z), x.rot_lane = pin((lane + 31) & 31, z);
+		x.chunks = pin(p.chunks, z), x.filter2 = pin(p.filter2, z);
 		x.vn = x.n_cand = x.n_hits = 0;
-		Slots<NA> pd;
+		Pending<NA> pd;
 #pragma unroll
-		for (int j = 0; j < NA; ++j) pd.x[j] = pd.lo[j] = pd.t[j] = 0;
+		for (int j = 0; j < NA; ++j) {
+			pd.w[j] = pd.a[j] = 0;
+			pd.pm[j] = 1;
+		}
 		auto drain_full = [&]() {
 			while (s.qn >= 32) {
 				s.qn -= 32;
 				x.n_cand += 32;
 				__syncwarp();
-				x.n_hits += drain_queue<S, true>(p, wq, s.qn, 32, vq, x.vn, lane, lt_mask);
+				x.n_hits += drain_queue<S, true, true>(p, wq, s.qn, 32, vq, x.vn, lane, lt_mask);
 				__syncwarp();
 			}
 		};
@@ -734,8 +687,10 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 				else defer_span<S, LS, false>(p, s, pd, t1, x);
 				/* the survivors of the last tile scanned; the queue takes one tile's worth above 31 entries */
 				drain_full();
-				if (defer_any<NA>(pd)) defer_slow<S, LS>(p, s, pd, s.c - 32, x);
+				defer_check<S, LS>(p, s, pd, s.c - 32, x);
 				drain_full();
+#pragma unroll
+				for (int j = 0; j < NA; ++j) pd.w[j] = 0;
 				if (s.t >= t1) break;
 				open_span(s.t, t1); /* back into the span where the resolver interrupted it */
 			}
@@ -743,10 +698,10 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 		if (s.qn) {
 			x.n_cand += s.qn;
 			__syncwarp();
-			x.n_hits += drain_queue<S, true>(p, wq, 0, s.qn, vq, x.vn, lane, lt_mask);
+			x.n_hits += drain_queue<S, true, true>(p, wq, 0, s.qn, vq, x.vn, lane, lt_mask);
 			__syncwarp();
 		}
-		if (x.vn) x.n_hits += verify_batch<S>(p, vq, x.vn, lane);
+		if (x.vn) x.n_hits += verify_batch<S, true>(p, vq, x.vn, lane);
 		if (lane == 0 && (x.n_cand | x.n_hits)) {
 			atomicAdd(&p.stats[ST_CANDIDATES], (unsigned long long)x.n_cand);
 			atomicAdd(&p.stats[ST_HITS], (unsigned long long)x.n_hits);
@@ -762,19 +717,19 @@ __global__ void __launch_bounds__(Launch<S, DEFER>::kThreads, 1) anchor_scan_ker
 		}
 		const bool finished = s.t >= t1; /* no span left */
 		if (!finished) {
-			if (interior) scan_tiles<S, CANON, LS, true>(p, s, t1, filter_sa, wq, lane, lt_mask);
-			else scan_tiles<S, CANON, LS, false>(p, s, t1, filter_sa, wq, lane, lt_mask);
+			if (interior) scan_tiles<S, CANON, LS, true>(p, s, t1, filter_sa, pairs_sa, wq, lane, lt_mask);
+			else scan_tiles<S, CANON, LS, false>(p, s, t1, filter_sa, pairs_sa, wq, lane, lt_mask);
 		}
 		if (s.qn >= 32 || (finished && s.qn)) { /* the one place candidates are resolved */
 			const uint32_t n = min(s.qn, 32u);
 			s.qn -= n;
 			n_cand += n;
 			__syncwarp();
-			n_hits += drain_queue<S, CANON>(p, wq, s.qn, n, vq, vn, lane, lt_mask);
+			n_hits += drain_queue<S, CANON, false>(p, wq, s.qn, n, vq, vn, lane, lt_mask);
 			__syncwarp();
 		} else if (finished) break;
 	}
-	if (vn) n_hits += verify_batch<S>(p, vq, vn, lane);
+	if (vn) n_hits += verify_batch<S, DEFER>(p, vq, vn, lane);
 	if (lane == 0 && (n_cand | n_hits)) {
 		atomicAdd(&p.stats[ST_CANDIDATES], (unsigned long long)n_cand);
 		atomicAdd(&p.stats[ST_HITS], (unsigned long long)n_hits);
@@ -897,7 +852,7 @@ static cudaError_t launch_form(const KernelForm &f, const AnchorParams &p0, int 
 {
 	AnchorParams p = p0;
 	const uint32_t warps = (uint32_t)f.threads / 32;
-	const size_t smem = (size_t)((p.filter_words + 3u) & ~3u) * 4 + f.queue_bytes;
+	const size_t smem = (size_t)((p.filter_words + 3u) & ~3u) * 4 + VG_PAIR_TABLE_BYTES + f.queue_bytes;
 	const uint32_t resident_warps = (uint32_t)n_sm * warps;
 	const uint32_t cap = VG_SPAN_TILES;
 	uint32_t tps = (p.n_tiles + resident_warps * 4u - 1) / (resident_warps * 4u);

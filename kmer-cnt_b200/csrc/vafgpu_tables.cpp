@@ -127,12 +127,11 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	out.filter_words = nw;
 	out.filter.assign((nw + 3u) & ~3u, 0);
 	for (uint32_t key : fkeys) out.filter[vg_filter_word(key, nw)] |= vg_filter_mask(key, nw);
-	/* second level: one bit per key in an array of 4 words (128 bits) per key, at least a page,
-	 * between a first and a last word that stay zero (what anchors that failed the first level read) */
-	const uint32_t nw2 = out.defer ? (uint32_t)std::max<uint64_t>(1024, (uint64_t)out.n_filter_keys * 4) + 2u : 4;
+	/* second level: 4 words (128 bits) per key, at least a page */
+	const uint32_t nw2 = out.defer ? (uint32_t)std::max<uint64_t>(1024, (uint64_t)out.n_filter_keys * 4) : 4;
 	out.filter2.assign(nw2, 0);
 	if (out.defer)
-		for (uint32_t key : fkeys) out.filter2[vg_filter2_word(key, nw, nw2)] |= vg_filter2_mask(key, nw);
+		for (uint32_t key : fkeys) out.filter2[vg_filter2_word(key, nw, nw2)] |= vg_filter_mask(key, nw);
 
 	/* exact table at <= 1/6 load, buckets of three tags: a full home bucket (a second L2
 	 * round trip) is then rare.  Items are placed in the order they were generated, so a

@@ -159,6 +159,7 @@ int main(int argc, char *argv[])
 	const int direct = getenv("KCGPU_DIRECT") && atoi(getenv("KCGPU_DIRECT")); /* no region lists (development) */
 	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn, n_dev);
 	const int timing = getenv("KCGPU_TIMING") != NULL; /* phase times on stderr */
+	uint64_t got_before = 0; /* slots per GPU the previous attempt really had */
 	for (int attempt = 0;; ++attempt) {
 		double t0 = now(), t1;
 		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
@@ -207,10 +208,13 @@ int main(int argc, char *argv[])
 		if (timing) fprintf(stderr, "[kc-c4] destroy                         %8.1f ms\n", (now() - t0) * 1e3);
 		if (overflow) { /* never print a histogram with k-mers missing */
 			struct stat sb;
-			if (attempt >= 12 || stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode)) { /* a pipe cannot be read twice */
+			/* a pipe cannot be read twice; a request the device cannot hold is cut down by
+			 * kcgpu_create, so a table that did not grow is the largest one that fits */
+			if (attempt >= 12 || stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode) || (attempt && slots <= got_before)) {
 				fprintf(stderr, "ERROR: the k-mer table (%llu slots per GPU) is full\n", (unsigned long long)slots);
 				return 1;
 			}
+			got_before = slots;
 			slots *= 2;
 			fprintf(stderr, "[kc-c4] table full, counting again with %llu slots per GPU\n", (unsigned long long)slots);
 			continue;

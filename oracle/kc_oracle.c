@@ -12,7 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../kmer-cnt_b200/host/fastx.h"
+#include "oracle_reader.h"
 
 #define KCO_MAX 1023u /* kc-c4.c:11-12 */
 
@@ -144,14 +144,14 @@ void kco_add_read(kco_t *o, const char *seq, long len)
  * (kc-c4.c:173) go on calling step 0, in order: the file ends with the third empty block. */
 int kco_add_file(kco_t *o, const char *fn, long block_len)
 {
-	fastx_t *fx = fastx_open(fn);
+	orr_t *fx = orr_open(fn);
 	const char *seq;
 	long len;
 	if (!fx) return -1;
 	int lives = 3;
 	for (;;) {
 		long sum_len = 0;
-		while ((len = fastx_next(fx, &seq)) >= 0) {
+		while ((len = orr_next(fx, &seq)) >= 0) {
 			if (len < o->k) continue;
 			kco_add_read(o, seq, len);
 			sum_len += len;
@@ -159,7 +159,7 @@ int kco_add_file(kco_t *o, const char *fn, long block_len)
 		}
 		if (sum_len == 0 && --lives == 0) break;
 	}
-	fastx_close(fx);
+	orr_close(fx);
 	return 0;
 }
 

@@ -13,7 +13,7 @@
 #include <string.h>
 #include <unistd.h>
 
-#include "../kmer-cnt_b200/host/fastx.h"
+#include "oracle_reader.h"
 #include "vaf_oracle.h"
 
 typedef struct {
@@ -80,19 +80,19 @@ int main(int argc, char **argv)
 		else if (c == 'o') out = optarg;
 	}
 	if (k % 2 == 0 || k < 1 || k > 31 || !bed || !fa || !out) return 1;
-	fastx_t *fx = fastx_open(fa);
+	orr_t *fx = orr_open(fa);
 	if (!fx) return 1;
 	const char *s;
 	long l;
-	while ((l = fastx_next(fx, &s)) >= 0) { /* snp-pattern-gen.c:70-104 */
+	while ((l = orr_next(fx, &s)) >= 0) { /* snp-pattern-gen.c:70-104 */
 		g_rec = (rec_t *)realloc(g_rec, (size_t)(g_n + 1) * sizeof *g_rec);
-		g_rec[g_n].name = strdup(fastx_name(fx));
+		g_rec[g_n].name = strdup(orr_name(fx));
 		g_rec[g_n].seq = (char *)malloc((size_t)l + 1);
 		memcpy(g_rec[g_n].seq, s, (size_t)l);
 		g_rec[g_n].seq[l] = 0;
 		g_rec[g_n++].len = l;
 	}
-	fastx_close(fx);
+	orr_close(fx);
 
 	char chr[256], rsid[256], ref, alt, rk[64], ak[64];
 	int start, end;

@@ -8,7 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../kmer-cnt_b200/host/fastx.h"
+#include "oracle_reader.h"
 
 /* ---- byte classification ------------------------------------------------------- */
 
@@ -319,7 +319,7 @@ static void *job_run(void *arg)
 int vo_count_file(const vo_map_t *m, int k, const char *fn, int simd, int n_threads,
                   int block_len, uint32_t *counts, vo_stats_t *st)
 {
-	fastx_t *fx = fastx_open(fn);
+	orr_t *fx = orr_open(fn);
 	size_t n_counts = 0, cap = 0;
 	char **seq = NULL;
 	int *len = NULL;
@@ -340,7 +340,7 @@ int vo_count_file(const vo_map_t *m, int k, const char *fn, int simd, int n_thre
 		size_t n = 0;
 		long l, sum_len = 0;
 		const char *s;
-		while ((l = fastx_next(fx, &s)) >= 0) {
+		while ((l = orr_next(fx, &s)) >= 0) {
 			if (l < k) continue;
 			if (n == cap) {
 				size_t ncap = cap ? cap + (cap >> 1) : 1024;
@@ -387,6 +387,6 @@ int vo_count_file(const vo_map_t *m, int k, const char *fn, int simd, int n_thre
 	for (size_t i = 0; i < cap; ++i) free(seq[i]);
 	free(seq);
 	free(len);
-	fastx_close(fx);
+	orr_close(fx);
 	return 0;
 }

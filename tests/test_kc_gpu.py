@@ -337,6 +337,10 @@ def test_cli_prints_the_reference_histogram(lib, name):
     r = subprocess.run([KC_CLI, "-k", "31", fq], check=True, capture_output=True, env=env)
     assert r.stdout.decode() == open(os.path.join(GOLDEN_KC, f"{name}.k31.hist")).read()
     assert b"counting again" in r.stderr
+    # a request larger than the device's memory is cut down to the largest table that fits
+    env = dict(os.environ, KCGPU_TABLE_SLOTS=str(1 << 36))
+    r = subprocess.run([KC_CLI, "-k", "31", fq], check=True, capture_output=True, env=env)
+    assert r.stdout.decode() == open(os.path.join(GOLDEN_KC, f"{name}.k31.hist")).read()
 
 
 def test_cli_parallel_readers(kco, lib, tmp_path):

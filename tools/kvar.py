@@ -77,7 +77,9 @@ def main():
             print(path, "create failed", rc, lib.vafgpu_strerror(None))
             continue
         counts = torch.zeros(2 * len(pats), dtype=torch.int32, device=dev)
-        cs = torch.cuda.current_stream().cuda_stream
+        side = torch.cuda.Stream()          # a real stream handle: 0 would mean "the engine's own stream"
+        cs = side.cuda_stream
+        torch.cuda.synchronize()
 
         def run():
             rc = lib.vafgpu_count_device(h, 0, stream.data_ptr(), n16, counts.data_ptr(), cs)
@@ -90,9 +92,9 @@ def main():
         tot = 0.0
         for _ in range(args.steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0.record(side)
             run()
-            e1.record()
+            e1.record(side)
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             best = min(best, ms)

@@ -73,6 +73,38 @@ int kcgpu_device_count(void);
 int kcgpu_create(kcgpu_ctx **ctx, int k, uint64_t table_slots, uint64_t list_slots, size_t block_bytes, int device);
 
 /*
+ * The yak-count variant of the counting path (yak-count.c of the reference: the same tables and
+ * the same 10-bit counts as kc-c4, plus a blocked Bloom filter in front of them and a second
+ * pass, yak-count.c:71-104,150-177,445-456).
+ *
+ * kcgpu_create_filtered: a context with a Bloom filter of 2^bloom_bits bits (cut down to a
+ * quarter of the device's memory; 0 = none) and bloom_hashes bits per k-mer (yak-count -b / -H).
+ * kcgpu_set_pass says what the insert step does with the k-mers counted from then on (it
+ * flushes what was filed before):
+ *   KCGPU_PASS_COUNT   make an entry if there is none, count up to 1023      (kc-c4; yak-count -b 0)
+ *   KCGPU_PASS_CLAIM   yak-count's first pass with a filter: an entry, with a count of 0, for every
+ *                      k-mer the filter has seen before -- the second and later occurrences,
+ *                      and false positives; k-mers seen once never reach the table
+ *   KCGPU_PASS_LOOKUP  its second pass: count the k-mers that have an entry, skip the others
+ * kcgpu_histogram1024 is yak-count's histogram (yak-count.c:205-239) after its shrink
+ * (:247-282, 453): hist[c] = entries with a count of c for min_count <= c <= max_count, 0
+ * elsewhere; the reference prints rows 1..1023.
+ * The filter takes one 64-bit word and one atomic per k-mer instead of the reference's 512-bit
+ * block walked bit by bit: with one file the result does not depend on the filter at all (every
+ * k-mer seen twice gets an entry whatever the filter's false positives, and entries seen once
+ * are dropped by the shrink); with a second file it can differ from the reference's by the k-mers
+ * that are false positives of one filter and not of the other, as the reference's own result
+ * differs between two values of -b.
+ */
+#define KCGPU_PASS_COUNT 0
+#define KCGPU_PASS_CLAIM 1
+#define KCGPU_PASS_LOOKUP 2
+int kcgpu_create_filtered(kcgpu_ctx **ctx, int k, uint64_t table_slots, uint64_t list_slots, size_t block_bytes, int device,
+                          int bloom_bits, int bloom_hashes);
+int kcgpu_set_pass(kcgpu_ctx *ctx, int pass);
+int kcgpu_histogram1024(kcgpu_ctx *ctx, uint64_t hist[1024], int min_count, int max_count, kcgpu_stats *stats);
+
+/*
  * Hand one parsed read to the engine: replaces the per-read copy of step 0 and steps 1 and 2
  * (kc-c4.c:133-180).  Reads shorter than k are dropped (kc-c4.c:141).  Bytes are classified by
  * the reference's strict table (kc-c4.c:21-38): A C G T U in either case and the bytes 0..3

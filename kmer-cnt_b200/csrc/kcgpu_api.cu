@@ -57,6 +57,7 @@ struct kcgpu_ctx {
 	std::vector<std::pair<cudaStream_t, cudaEvent_t>> user_streams; /* last launch on each caller stream */
 	cudaEvent_t f0 = nullptr, f1 = nullptr;
 	unsigned long long *d_stats = nullptr, *d_hist = nullptr;
+	InsertCtl ctl{KC_INS_COUNT, 0, 0}; /* what the insert step does, and the Bloom geometry */
 	cudaStream_t main_stream = nullptr;
 	size_t block_bytes = 0;
 	std::vector<KcBlock *> blocks;
@@ -127,6 +128,7 @@ CountArgs count_args(const kcgpu_ctx *c, const void *bytes, size_t n)
 	a.rslot_bits = c->rslot_bits;
 	for (uint32_t i = 0; i < c->n_parts; ++i) a.tables[i] = c->tables[i];
 	a.stats = c->d_stats;
+	a.ctl = c->ctl;
 	return a;
 }
 
@@ -143,8 +145,9 @@ cudaError_t kc_launch_flush(const kcgpu_ctx *m, cudaStream_t s)
 {
 	uint64_t *lists = kc_lists_of(m->d_table, m->n_slots);
 	unsigned long long *cursors = kc_cursors_of(m->d_table, m->n_slots, m->list_cap, m->region_bits);
+	uint32_t *bloom = m->ctl.bloom_bits ? kc_bloom_of(m->d_table, m->n_slots, m->list_cap, m->region_bits) : nullptr;
 	if (m->n_parts == 1)
-		return launch_flush(m->d_table, lists, cursors, m->list_cap, m->region_bits, m->rslot_bits, m->d_stats, s);
+		return launch_flush(m->d_table, lists, cursors, m->list_cap, m->region_bits, m->rslot_bits, bloom, m->ctl, m->d_stats, s);
 	/* the inbox (first half of the list area) into the region lists (second half), then those */
 	RouteArgs a{};
 	a.inbox = lists;
@@ -156,10 +159,12 @@ cudaError_t kc_launch_flush(const kcgpu_ctx *m, cudaStream_t s)
 	a.table = m->d_table;
 	a.region_bits = m->region_bits;
 	a.rslot_bits = m->rslot_bits;
+	a.bloom = bloom;
+	a.ctl = m->ctl;
 	a.stats = m->d_stats;
 	cudaError_t e = launch_route(a, m->n_sm, s);
 	if (e != cudaSuccess) return e;
-	return launch_flush(m->d_table, a.lists, cursors, a.cap, m->region_bits, m->rslot_bits, m->d_stats, s);
+	return launch_flush(m->d_table, a.lists, cursors, a.cap, m->region_bits, m->rslot_bits, bloom, m->ctl, m->d_stats, s);
 }
 
 /* the lists must be able to take n more k-mers: flush first if they might not (a context whose
@@ -377,7 +382,17 @@ const char *kcgpu_strerror(const kcgpu_ctx *ctx) { return ctx ? ctx->err.c_str()
 
 int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slots, size_t block_bytes, int device)
 {
+	return kcgpu_create_filtered(out, k, table_slots, list_slots, block_bytes, device, 0, 0);
+}
+
+int kcgpu_create_filtered(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slots, size_t block_bytes, int device,
+                          int bloom_bits, int bloom_hashes)
+{
 	if (!out) return kfail(nullptr, VAFGPU_EINVAL, "ctx is NULL");
+	if (bloom_bits < 0 || bloom_bits > 40 || bloom_hashes < 0 || bloom_hashes > 64)
+		return kfail(nullptr, VAFGPU_EINVAL, "Bloom filter of 2^%d bits with %d hash functions", bloom_bits, bloom_hashes);
+	if (bloom_bits && bloom_bits < 13) bloom_bits = 13; /* at least a kilobyte */
+	if (!bloom_hashes) bloom_bits = 0;
 	*out = nullptr;
 	if (k < 1 || k > 31) return kfail(nullptr, VAFGPU_EINVAL, "k = %d is outside 1..31", k);
 	int visible = 0;
@@ -407,6 +422,11 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 		const bool lists = list_slots != KCGPU_NO_LISTS;
 		size_t free_b = 0, total_b = 0;
 		KCU(c, cudaMemGetInfo(&free_b, &total_b));
+		/* a filter is worth at most a quarter of the device */
+		while (bloom_bits > 13 && kc_bloom_bytes((uint32_t)bloom_bits) > (uint64_t)free_b / 4) --bloom_bits;
+		free_b -= (size_t)kc_bloom_bytes((uint32_t)bloom_bits);
+		c->ctl.bloom_bits = (uint32_t)bloom_bits;
+		c->ctl.bloom_hashes = (uint32_t)bloom_hashes;
 		if (table_slots == 0) {
 			uint64_t budget = (uint64_t)free_b / 4 * 3 / 8; /* 8-byte words */
 			if (lists) budget = list_slots ? (budget > list_slots ? budget - list_slots : 0) : budget / 3 * 2;
@@ -442,8 +462,8 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 				c->flush_bytes = (cap << c->region_bits) / 20 * 19; /* a byte is at most one k-mer; what a list cannot take goes to the table */
 				if (c->flush_bytes > ((uint64_t)1 << 40)) c->flush_bytes = (uint64_t)1 << 40;
 			}
-			alloc = kc_alloc_bytes(n, c->list_cap, c->region_bits);
-			if (alloc + ((uint64_t)256 << 20) <= (uint64_t)free_b || n <= min_slots) break;
+			alloc = kc_alloc_bytes(n, c->list_cap, c->region_bits, c->ctl.bloom_bits);
+			if (alloc - kc_bloom_bytes(c->ctl.bloom_bits) + ((uint64_t)256 << 20) <= (uint64_t)free_b || n <= min_slots) break;
 		}
 		cudaError_t me = cudaMalloc(&c->d_table, alloc);
 		if (me != cudaSuccess) {
@@ -453,10 +473,12 @@ int kcgpu_create(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t list_slo
 			             (unsigned long long)(c->list_cap << c->region_bits), cudaGetErrorString(me));
 		}
 		KCU(c, cudaMalloc(&c->d_stats, KC_ST_N * sizeof(unsigned long long)));
-		KCU(c, cudaMalloc(&c->d_hist, 256 * sizeof(unsigned long long)));
+		KCU(c, cudaMalloc(&c->d_hist, 1024 * sizeof(unsigned long long)));
 		KCU(c, cudaMemset(c->d_table, 0, n * 8));
 		if (c->list_cap)
 			KCU(c, cudaMemset(kc_cursors_of(c->d_table, n, c->list_cap, c->region_bits), 0, (size_t)kc_cursor_bytes(c->region_bits)));
+		if (c->ctl.bloom_bits)
+			KCU(c, cudaMemset(kc_bloom_of(c->d_table, n, c->list_cap, c->region_bits), 0, (size_t)kc_bloom_bytes(c->ctl.bloom_bits)));
 		KCU(c, cudaMemset(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long)));
 		KCU(c, cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking));
 		KCU(c, cudaEventCreate(&c->f0));
@@ -690,6 +712,9 @@ int kcgpu_insert_device(kcgpu_ctx *c, const uint64_t *d_hashed_keys, size_t n, i
 	a.region_bits = c->region_bits;
 	a.rslot_bits = c->rslot_bits;
 	a.table = c->d_table;
+	a.n_slots = c->n_slots;
+	a.list_cap = c->list_cap;
+	a.ctl = c->ctl;
 	a.stats = c->d_stats;
 	std::lock_guard<std::mutex> lk(g_kc_mu);
 	KCU(c, cudaSetDevice(c->device));
@@ -768,8 +793,9 @@ int kcgpu_link(kcgpu_ctx *const *ctxs, int n)
 	std::lock_guard<std::mutex> lk(g_kc_mu);
 	for (int i = 0; i < n; ++i) {
 		if (!ctxs[i]) return VAFGPU_EINVAL;
-		if (ctxs[i]->n_slots != ctxs[0]->n_slots || ctxs[i]->k != ctxs[0]->k || ctxs[i]->list_cap != ctxs[0]->list_cap)
-			return kfail(ctxs[i], VAFGPU_EINVAL, "linked contexts must share k, the table size and the list size");
+		if (ctxs[i]->n_slots != ctxs[0]->n_slots || ctxs[i]->k != ctxs[0]->k || ctxs[i]->list_cap != ctxs[0]->list_cap ||
+		    ctxs[i]->ctl.bloom_bits != ctxs[0]->ctl.bloom_bits || ctxs[i]->ctl.bloom_hashes != ctxs[0]->ctl.bloom_hashes)
+			return kfail(ctxs[i], VAFGPU_EINVAL, "linked contexts must share k, the table size, the list size and the Bloom filter size");
 	}
 	for (int i = 0; i < n; ++i) {
 		kcgpu_ctx *c = ctxs[i];
@@ -850,6 +876,42 @@ int kcgpu_histogram(kcgpu_ctx *c, uint64_t hist[256], kcgpu_stats *stats)
 	return VAFGPU_OK;
 }
 
+int kcgpu_set_pass(kcgpu_ctx *c, int pass)
+{
+	if (!c) return VAFGPU_EINVAL;
+	if (pass != KCGPU_PASS_COUNT && pass != KCGPU_PASS_CLAIM && pass != KCGPU_PASS_LOOKUP)
+		return kfail(c, VAFGPU_EINVAL, "pass %d", pass);
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	/* what was filed under the old rule is inserted under the old rule */
+	int rc = c->external_owners ? kc_sync_group(c) : kc_flush_group(c);
+	if (rc) return rc;
+	for (kcgpu_ctx *m : c->group) m->ctl.mode = pass;
+	return VAFGPU_OK;
+}
+
+int kcgpu_histogram1024(kcgpu_ctx *c, uint64_t hist[1024], int min_count, int max_count, kcgpu_stats *stats)
+{
+	if (!c) return VAFGPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_kc_mu);
+	int rc = kc_flush_group(c);
+	if (rc) return rc;
+	KCU(c, cudaSetDevice(c->device));
+	if (hist) {
+		KCU(c, cudaMemsetAsync(c->d_hist, 0, 1024 * sizeof(unsigned long long), c->main_stream));
+		KCU(c, launch_histogram1024(c->d_table, c->n_slots, c->d_hist, c->n_sm, c->main_stream));
+		unsigned long long h[1024];
+		KCU(c, cudaMemcpyAsync(h, c->d_hist, sizeof h, cudaMemcpyDeviceToHost, c->main_stream));
+		KCU(c, cudaStreamSynchronize(c->main_stream));
+		for (int i = 0; i < 1024; ++i) hist[i] = i >= min_count && i <= max_count ? h[i] : 0; /* yak_ch_shrink, yak-count.c:247-282 */
+	}
+	if (stats) {
+		rc = kc_read_stats(c);
+		if (rc) return rc;
+		*stats = c->st;
+	}
+	return VAFGPU_OK;
+}
+
 int kcgpu_reset(kcgpu_ctx *c)
 {
 	if (!c) return VAFGPU_EINVAL;
@@ -861,6 +923,9 @@ int kcgpu_reset(kcgpu_ctx *c)
 	if (c->list_cap)
 		KCU(c, cudaMemsetAsync(kc_cursors_of(c->d_table, c->n_slots, c->list_cap, c->region_bits), 0,
 		                       (size_t)kc_cursor_bytes(c->region_bits), c->main_stream));
+	if (c->ctl.bloom_bits)
+		KCU(c, cudaMemsetAsync(kc_bloom_of(c->d_table, c->n_slots, c->list_cap, c->region_bits), 0, (size_t)kc_bloom_bytes(c->ctl.bloom_bits),
+		                       c->main_stream));
 	KCU(c, cudaMemsetAsync(c->d_stats, 0, KC_ST_N * sizeof(unsigned long long), c->main_stream));
 	KCU(c, cudaStreamSynchronize(c->main_stream));
 	const kcgpu_stats keep = c->st;

@@ -64,24 +64,56 @@ enum { KC_PARTITION = 0, KC_DIRECT = 1, KC_EXTRACT = 2, KC_PUSH = 3 };
 
 __device__ __forceinline__ uint64_t kc_home(uint64_t tag, uint32_t rslot_bits) { return (tag * 0x9E3779B97F4A7C15ull) >> (64 - rslot_bits); }
 
-/* kc-c4.c:116-128 on one region of one table: find or claim the slot of `tag`, count up to 1023.
- * `v` is what the home slot `pos` held when the caller looked (callers look at several home
- * slots before they resolve the first, so that the loads overlap). */
-__device__ __forceinline__ void kc_insert_from(uint64_t *base, uint32_t rslot_bits, uint64_t tag, uint64_t pos, uint64_t v,
-                                               uint32_t &n_new, uint32_t &n_overflow)
+/* The Bloom pre-filter of yak-count's first pass (yak-count.c:71-104,159-161): has this k-mer
+ * been seen before?  One 64-bit word per k-mer and ONE atomic: the word comes from the low bits
+ * of the tag, the n bit positions from the bits above them (double hashing with an odd step), and
+ * the k-mer counts as seen when every one of its bits was set before.  (The reference spreads
+ * the bits over a 512-bit block and sets them one by one, which is exact only because one thread
+ * owns a partition; with one atomic per k-mer two occurrences of a k-mer can never both find it
+ * new-ish, however they race -- the second one sees all the bits of the first.  Which k-mers end
+ * up with an entry differs from the reference only by false positives, and those are dropped
+ * again by the shrink, yak-count.c:453.)  `slice` is the region's part of the filter,
+ * 2^slice_bits bits. */
+__device__ __forceinline__ bool kc_bloom_seen(uint32_t *slice, uint32_t slice_bits, uint32_t n_hashes, uint64_t tag)
 {
-	const uint64_t rmask = (1ull << rslot_bits) - 1ull;
+	const uint32_t words_log = slice_bits - 6;
+	unsigned long long *w = reinterpret_cast<unsigned long long *>(slice) + (tag & ((1ull << words_log) - 1ull));
+	const uint32_t first = (uint32_t)(tag >> words_log) & 63u, step = ((uint32_t)(tag >> (words_log + 6)) & 63u) | 1u;
+	unsigned long long mask = 0;
+	for (uint32_t i = 0, z = first; i < n_hashes; ++i, z = (z + step) & 63u) mask |= 1ull << z;
+	return (atomicOr(w, mask) & mask) == mask;
+}
+
+/* the region's slice of an owner's Bloom filter, NULL if there is no filter (or none that leaves
+ * a region at least one word: every k-mer then gets an entry, as when the reference cannot
+ * create its filter, yak-count.c:75,117-121) */
+__device__ __forceinline__ uint32_t *kc_bloom_slice(uint32_t *bloom, const InsertCtl &ctl, uint32_t region_bits, uint64_t region)
+{
+	if (!bloom || ctl.bloom_bits < region_bits + 6) return nullptr;
+	return bloom + (region << (ctl.bloom_bits - region_bits - 5));
+}
+
+/* kc-c4.c:116-128 / yak-count.c:150-177 on one region of one table: find (or, unless the mode
+ * is KC_INS_LOOKUP, claim) the slot of `tag` and count up to 1023 (KC_INS_CLAIM: make the entry,
+ * leave its count at 0).  `v` is what the home slot `pos` held when the caller looked (callers
+ * look at several home slots before they resolve the first, so that the loads overlap). */
+__device__ __forceinline__ void kc_insert_from(uint64_t *base, uint32_t rslot_bits, uint64_t tag, uint64_t pos, uint64_t v,
+                                               const int mode, uint32_t &n_new, uint32_t &n_overflow)
+{
+	const uint64_t rmask = (1ull << rslot_bits) - 1ull, key = tag + 1ull;
 	for (int tries = 0; tries < KC_MAX_PROBES; ++tries) {
 		uint64_t *p = base + pos;
 		if (tries) v = ld_slot(p);
 		if (v == 0) {
-			v = cas_slot(p, 0, (tag << KC_COUNT_BITS) | 1ull);
+			if (mode == KC_INS_LOOKUP) return; /* no entry: not counted */
+			v = cas_slot(p, 0, (key << KC_COUNT_BITS) | (mode == KC_INS_CLAIM ? 0ull : 1ull));
 			if (v == 0) {
 				++n_new;
 				return;
 			}
 		}
-		while ((v >> KC_COUNT_BITS) == tag) {
+		while ((v >> KC_COUNT_BITS) == key) {
+			if (mode == KC_INS_CLAIM) return;
 			if ((v & KC_COUNT_MAX) == KC_COUNT_MAX) return; /* kc-c4.c:125 */
 			const uint64_t old = cas_slot(p, v, v + 1);
 			if (old == v) return;
@@ -89,21 +121,23 @@ __device__ __forceinline__ void kc_insert_from(uint64_t *base, uint32_t rslot_bi
 		}
 		pos = (pos + 1) & rmask;
 	}
-	++n_overflow;
+	if (mode != KC_INS_LOOKUP) ++n_overflow;
 }
 
-__device__ __forceinline__ void kc_insert_region(uint64_t *base, uint32_t rslot_bits, uint64_t tag, uint32_t &n_new,
-                                                 uint32_t &n_overflow)
+__device__ __forceinline__ void kc_insert_region(uint64_t *base, uint32_t rslot_bits, uint64_t tag, uint32_t *bloom_slice,
+                                                 const InsertCtl &ctl, uint32_t slice_bits, uint32_t &n_new, uint32_t &n_overflow)
 {
+	if (ctl.mode == KC_INS_CLAIM && bloom_slice && !kc_bloom_seen(bloom_slice, slice_bits, ctl.bloom_hashes, tag)) return;
 	const uint64_t pos = kc_home(tag, rslot_bits);
-	kc_insert_from(base, rslot_bits, tag, pos, ld_slot(base + pos), n_new, n_overflow);
+	kc_insert_from(base, rslot_bits, tag, pos, ld_slot(base + pos), ctl.mode, n_new, n_overflow);
 }
 
-__device__ __forceinline__ void kc_insert(uint64_t *table, uint32_t region_bits, uint32_t rslot_bits, uint64_t q,
-                                          uint32_t &n_new, uint32_t &n_overflow)
+__device__ __forceinline__ void kc_insert(uint64_t *table, uint32_t region_bits, uint32_t rslot_bits, uint64_t q, uint32_t *bloom,
+                                          const InsertCtl &ctl, uint32_t &n_new, uint32_t &n_overflow)
 {
 	const uint64_t region = q & ((1ull << region_bits) - 1ull);
-	kc_insert_region(table + (region << rslot_bits), rslot_bits, q >> region_bits, n_new, n_overflow);
+	kc_insert_region(table + (region << rslot_bits), rslot_bits, q >> region_bits, kc_bloom_slice(bloom, ctl, region_bits, region), ctl,
+	                 ctl.bloom_bits - region_bits, n_new, n_overflow);
 }
 
 __device__ __forceinline__ void kc_owner(uint64_t h, uint32_t n_parts, int part_shift, uint32_t &owner, uint64_t &q)
@@ -202,7 +236,8 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 						kc_lists_of(base, a.n_slots)[region * a.list_cap + at[j]] = q[j];
 					} else {
 						++n_direct;
-						kc_insert(base, a.region_bits, a.rslot_bits, q[j], n_new, n_overflow);
+						kc_insert(base, a.region_bits, a.rslot_bits, q[j], kc_bloom_of(base, a.n_slots, a.list_cap, a.region_bits), a.ctl,
+						          n_new, n_overflow);
 					}
 				}
 			} else if (MODE == KC_PUSH) {
@@ -228,13 +263,16 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 						kc_lists_of(base, a.n_slots)[pos] = q[j];
 					} else { /* inbox full: straight to the owner's table */
 						++n_direct;
-						kc_insert(base, a.region_bits, a.rslot_bits, q[j], n_new, n_overflow);
+						kc_insert(base, a.region_bits, a.rslot_bits, q[j], kc_bloom_of(base, a.n_slots, a.list_cap, a.region_bits), a.ctl,
+						          n_new, n_overflow);
 					}
 				}
 			} else if (MODE == KC_DIRECT) {
 #pragma unroll
 				for (int j = 0; j < 4; ++j)
-					if (ok[j]) kc_insert(a.tables[owner[j]], a.region_bits, a.rslot_bits, q[j], n_new, n_overflow);
+					if (ok[j])
+						kc_insert(a.tables[owner[j]], a.region_bits, a.rslot_bits, q[j],
+						          kc_bloom_of(a.tables[owner[j]], a.n_slots, a.list_cap, a.region_bits), a.ctl, n_new, n_overflow);
 			} else {
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
@@ -274,7 +312,8 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 __global__ void __launch_bounds__(KC_THREADS) kc_flush_kernel(uint64_t *base, const uint64_t *lists, const unsigned long long *cursors,
                                                                const uint64_t list_cap, const uint32_t region_bits,
                                                                const uint32_t rslot_bits, const uint32_t tiles_per_region,
-                                                               const uint32_t tile_entries, unsigned long long *stats)
+                                                               const uint32_t tile_entries, uint32_t *bloom, const InsertCtl ctl,
+                                                               unsigned long long *stats)
 {
 	const uint32_t region = blockIdx.x / tiles_per_region, tile = blockIdx.x % tiles_per_region;
 	const uint64_t filled = cursors[(uint64_t)region * KC_CURSOR_STRIDE];
@@ -284,13 +323,14 @@ __global__ void __launch_bounds__(KC_THREADS) kc_flush_kernel(uint64_t *base, co
 	const uint64_t hi = lo + tile_entries < n ? lo + tile_entries : n;
 	const uint64_t *list = lists + (uint64_t)region * list_cap;
 	uint64_t *slice = base + ((uint64_t)region << rslot_bits);
+	uint32_t *const bloom_slice = kc_bloom_slice(bloom, ctl, region_bits, region); /* stays in L2 beside the table slice */
 	uint32_t n_new = 0, n_overflow = 0;
 	/* one entry per thread and step: more entries in flight per thread (four home slots
 	 * requested at once) measured slower -- the compare-and-swap chain, not the first load, is
 	 * what a thread waits for, and the registers halve the resident threads */
 	for (uint64_t i = lo + threadIdx.x; i < hi; i += KC_THREADS) {
 		const uint64_t q = __ldcs(reinterpret_cast<const unsigned long long *>(list + i));
-		kc_insert_region(slice, rslot_bits, q >> region_bits, n_new, n_overflow);
+		kc_insert_region(slice, rslot_bits, q >> region_bits, bloom_slice, ctl, ctl.bloom_bits - region_bits, n_new, n_overflow);
 	}
 	for (int o = 16; o; o >>= 1) {
 		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
@@ -311,7 +351,7 @@ __global__ void __launch_bounds__(KC_THREADS) kc_insert_kernel(const InsertArgs 
 		uint32_t owner;
 		kc_owner(q, a.n_parts, part_shift, owner, q);
 		++n_kmers;
-		kc_insert(a.table, a.region_bits, a.rslot_bits, q, n_new, n_overflow);
+		kc_insert(a.table, a.region_bits, a.rslot_bits, q, kc_bloom_of(a.table, a.n_slots, a.list_cap, a.region_bits), a.ctl, n_new, n_overflow);
 	}
 	for (int o = 16; o; o >>= 1) {
 		n_kmers += __shfl_xor_sync(KC_FULL, n_kmers, o);
@@ -340,7 +380,7 @@ __global__ void __launch_bounds__(KC_THREADS) kc_route_kernel(const RouteArgs a)
 			a.lists[region * a.cap + at] = q;
 		} else {
 			++n_direct;
-			kc_insert(a.table, a.region_bits, a.rslot_bits, q, n_new, n_overflow);
+			kc_insert(a.table, a.region_bits, a.rslot_bits, q, a.bloom, a.ctl, n_new, n_overflow);
 		}
 	}
 	for (int o = 16; o; o >>= 1) {
@@ -399,6 +439,29 @@ __global__ void __launch_bounds__(KC_THREADS) kc_hist_kernel(const uint64_t *tab
 	}
 }
 
+/* yak-count.c:205-239: one bin per count, 0..1023, over the used slots.  Private histograms
+ * per warp would take 32 KB of shared memory: one per CTA, lanes that hit the same bin merged
+ * first (most used slots of a read set share a handful of counts). */
+__global__ void __launch_bounds__(KC_THREADS) kc_hist1024_kernel(const uint64_t *table, const uint64_t n_slots,
+                                                                  unsigned long long *hist)
+{
+	__shared__ unsigned long long sh[1024];
+	for (int i = threadIdx.x; i < 1024; i += KC_THREADS) sh[i] = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const uint64_t stride = (uint64_t)gridDim.x * KC_THREADS;
+	for (uint64_t i0 = (uint64_t)blockIdx.x * KC_THREADS; i0 < n_slots; i0 += stride) {
+		const uint64_t i = i0 + threadIdx.x;
+		const uint64_t s = i < n_slots ? __ldcs(reinterpret_cast<const unsigned long long *>(table + i)) : 0ull;
+		const uint32_t bin = s ? (uint32_t)s & KC_COUNT_MAX : 0xFFFFFFFFu; /* free slots are not entries */
+		const uint32_t peers = __match_any_sync(KC_FULL, bin);
+		if (s && lane == __ffs(peers) - 1) atomicAdd(&sh[bin], (unsigned long long)__popc(peers));
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 1024; i += KC_THREADS)
+		if (sh[i]) atomicAdd(hist + i, sh[i]);
+}
+
 int shift_of(uint32_t n_parts)
 {
 	if (n_parts & (n_parts - 1)) return -1;
@@ -425,14 +488,16 @@ cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream) { return lau
 cudaError_t launch_push(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_PUSH>(a, stream); }
 
 cudaError_t launch_flush(uint64_t *base, const uint64_t *lists, const unsigned long long *cursors, uint64_t list_cap,
-                         uint32_t region_bits, uint32_t rslot_bits, unsigned long long *stats, cudaStream_t stream)
+                         uint32_t region_bits, uint32_t rslot_bits, uint32_t *bloom, const InsertCtl &ctl,
+                         unsigned long long *stats, cudaStream_t stream)
 {
 	if (!list_cap) return cudaSuccess;
 	const uint32_t tile = KC_FLUSH_TILE;
 	const uint64_t tiles = (list_cap + tile - 1) / tile;
 	const uint64_t blocks = tiles << region_bits;
 	if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-	kc_flush_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(base, lists, cursors, list_cap, region_bits, rslot_bits, (uint32_t)tiles, tile, stats);
+	kc_flush_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(base, lists, cursors, list_cap, region_bits, rslot_bits, (uint32_t)tiles, tile, bloom,
+	                                                             ctl, stats);
 	return cudaGetLastError();
 }
 
@@ -460,6 +525,16 @@ cudaError_t launch_histogram(const uint64_t *table, uint64_t n_slots, unsigned l
 	if (blocks > resident) blocks = resident;
 	if (blocks < 1) blocks = 1;
 	kc_hist_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(table, n_slots, hist256);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_histogram1024(const uint64_t *table, uint64_t n_slots, unsigned long long *hist1024, int n_sm, cudaStream_t stream)
+{
+	uint64_t blocks = (n_slots + KC_THREADS - 1) / KC_THREADS;
+	const uint64_t resident = (uint64_t)(n_sm > 0 ? n_sm : 1) * 8;
+	if (blocks > resident) blocks = resident;
+	if (blocks < 1) blocks = 1;
+	kc_hist1024_kernel<<<(unsigned)blocks, KC_THREADS, 0, stream>>>(table, n_slots, hist1024);
 	return cudaGetLastError();
 }
 

@@ -5,10 +5,12 @@
  * Table: n_slots 64-bit words, cut into 2^region_bits regions of 2^rslot_bits slots.  A k-mer
  * with hash h = hash64(canonical k-mer) (kc-c4.c:40-50) belongs to owner h mod n_parts; with
  * q = h div n_parts its region is the low region_bits of q (the reference's partition by hash
- * suffix, kc-c4.c:66) and the slot holds (q >> region_bits) << 10 | count, the reference's
- * "key << KC_BITS | count" word (kc-c4.c:11-15,124-125).  0 is a free slot (a used slot has a
- * count of at least 1).  Linear probing inside the region from a multiplicative hash of the
- * tag.  Nothing is lost: (owner, region, tag) give h back, and hash64 is invertible.
+ * suffix, kc-c4.c:66) and the slot holds ((q >> region_bits) + 1) << 10 | count, the reference's
+ * "key << KC_BITS | count" word (kc-c4.c:11-15,124-125) with the key moved up by one, so that
+ * 0 is a free slot and nothing else: an entry may carry a count of 0 (yak-count's second pass
+ * starts from entries without counts, yak-count.c:451-452).  Linear probing inside the region
+ * from a multiplicative hash of the tag.  Nothing is lost: (owner, region, tag) give h back,
+ * and hash64 is invertible.
  *
  * Region lists: like the reference (count_seq_buf files k-mers per partition, worker_for then
  * fills one partition's table at a time, kc-c4.c:64-72,116-128), the scan does not touch the
@@ -19,7 +21,7 @@
  * share of one pass over the table.
  *
  * One allocation per owner, so that one pointer (one CUDA IPC handle) names it all:
- *   [ table: n_slots x 8 B ][ lists: n_regions x list_cap x 8 B ][ cursors: n_regions x 256 B, one 64-bit count each ]
+ *   [ table: n_slots x 8 B ][ lists: n_regions x list_cap x 8 B ][ cursors: n_regions x 256 B, one 64-bit count each ][ Bloom filter: 2^bloom_bits / 8 B ]
  * With several owners the first half of the list area is the owner's inbox (its cursor follows
  * the regions'): whoever finds a k-mer appends it there in sector-sized runs; at a flush the
  * owner files what arrived under its region in the second half and empties that region by region.
@@ -44,7 +46,24 @@ enum { KC_MAX_PROBES = 8192 }; /* a region this crowded is reported as overflow,
 enum { KC_REGION_SLOT_BITS = 21 }; /* slots per region at most: 16 MiB of table, a few of them fit L2 */
 enum { KC_CURSOR_STRIDE = 32 };    /* 64-bit words between two regions' cursors: one 256-byte line each */
 enum { KC_FLUSH_TILE = 2048 };     /* list entries per CTA of the list-insert kernel */
-enum { KC_TAG_BITS = 64 - KC_COUNT_BITS };
+enum { KC_TAG_BITS = 64 - KC_COUNT_BITS - 1 }; /* the stored key is tag + 1 */
+enum { KC_BLOOM_BLOCK_BITS = 9 };                /* a Bloom block is 512 bits = 64 bytes (yak-count.c:14-15) */
+
+/* what the insert step does with a k-mer (yak-count.c:150-177) */
+enum {
+	KC_INS_COUNT = 0,  /* make an entry if there is none, count up to 1023: kc-c4, yak-count without -b      */
+	KC_INS_CLAIM = 1,  /* yak-count's first pass with -b: an entry with a count of 0 for every k-mer the
+	                      Bloom filter has seen before; the counts of this pass are thrown away anyway   */
+	KC_INS_LOOKUP = 2, /* yak-count's second pass: count the k-mers that have an entry, skip the others  */
+};
+
+/* the insert step's mode and the owner-independent part of the Bloom geometry; the filter
+ * itself lies behind the cursors of every owner's allocation */
+struct InsertCtl {
+	int mode;
+	uint32_t bloom_bits;   /* log2 of the bits of one owner's filter; 0 = no filter */
+	uint32_t bloom_hashes;
+};
 
 /* per-context counters the kernels add to (unsigned long long each) */
 enum { KC_ST_KMERS = 0, KC_ST_NEW = 1, KC_ST_OVERFLOW = 2, KC_ST_DROPPED = 3, KC_ST_DIRECT = 4, KC_ST_N = 8 };
@@ -74,6 +93,7 @@ struct CountArgs {
 	uint32_t region_bits, rslot_bits;
 	uint64_t *tables[KC_MAX_PARTS]; /* table of every owner (peer memory over NVLink for the others) */
 	unsigned long long *stats;
+	InsertCtl ctl;
 	/* extract-only form */
 	uint64_t *out_keys;   /* [part * cap_per_part + i] */
 	uint64_t cap_per_part;
@@ -86,6 +106,8 @@ struct InsertArgs {
 	uint32_t n_parts;
 	uint32_t region_bits, rslot_bits;
 	uint64_t *table;
+	uint64_t n_slots, list_cap; /* where the Bloom filter lies */
+	InsertCtl ctl;
 	unsigned long long *stats;
 };
 
@@ -96,7 +118,8 @@ cudaError_t launch_push(const CountArgs &a, cudaStream_t stream);      /* extrac
 /* insert what the region lists hold (`cap` entries per region at most, one cursor per region)
  * into the table; the cursors are left as they are */
 cudaError_t launch_flush(uint64_t *table, const uint64_t *lists, const unsigned long long *cursors, uint64_t cap,
-                         uint32_t region_bits, uint32_t rslot_bits, unsigned long long *stats, cudaStream_t stream);
+                         uint32_t region_bits, uint32_t rslot_bits, uint32_t *bloom, const InsertCtl &ctl,
+                         unsigned long long *stats, cudaStream_t stream);
 
 /* several owners: what arrived in the inbox, filed under its region (straight to the table
  * where a region list is full) */
@@ -109,6 +132,8 @@ struct RouteArgs {
 	uint64_t cap;
 	uint64_t *table;
 	uint32_t region_bits, rslot_bits;
+	uint32_t *bloom;
+	InsertCtl ctl;
 	unsigned long long *stats;
 };
 cudaError_t launch_route(const RouteArgs &a, int n_sm, cudaStream_t stream);
@@ -116,6 +141,9 @@ cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream); /* extract 
 cudaError_t launch_insert(const InsertArgs &a, int n_sm, cudaStream_t stream);
 cudaError_t launch_histogram(const uint64_t *table, uint64_t n_slots, unsigned long long *hist256, int n_sm,
                              cudaStream_t stream);
+/* yak-count's histogram (yak-count.c:205-239): 1024 bins, entries with a count of 0 in bin 0 */
+cudaError_t launch_histogram1024(const uint64_t *table, uint64_t n_slots, unsigned long long *hist1024, int n_sm,
+                                 cudaStream_t stream);
 
 KC_HD uint64_t *kc_lists_of(uint64_t *base, uint64_t n_slots) { return base + n_slots; }
 KC_HD unsigned long long *kc_cursors_of(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits)
@@ -124,9 +152,15 @@ KC_HD unsigned long long *kc_cursors_of(uint64_t *base, uint64_t n_slots, uint64
 }
 /* one cursor per region and one more, the inbox's */
 KC_HD uint64_t kc_cursor_bytes(uint32_t region_bits) { return (((uint64_t)1 << region_bits) + 1) * KC_CURSOR_STRIDE * 8; }
-KC_HD uint64_t kc_alloc_bytes(uint64_t n_slots, uint64_t list_cap, uint32_t region_bits)
+KC_HD uint64_t kc_bloom_bytes(uint32_t bloom_bits) { return bloom_bits ? (uint64_t)1 << (bloom_bits - 3) : 0; }
+KC_HD uint64_t kc_alloc_bytes(uint64_t n_slots, uint64_t list_cap, uint32_t region_bits, uint32_t bloom_bits = 0)
 {
-	return (n_slots + (list_cap << region_bits)) * 8 + kc_cursor_bytes(region_bits);
+	return (n_slots + (list_cap << region_bits)) * 8 + kc_cursor_bytes(region_bits) + kc_bloom_bytes(bloom_bits);
+}
+/* the Bloom filter of an allocation: behind the cursors */
+KC_HD uint32_t *kc_bloom_of(uint64_t *base, uint64_t n_slots, uint64_t list_cap, uint32_t region_bits)
+{
+	return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base + n_slots + (list_cap << region_bits)) + kc_cursor_bytes(region_bits));
 }
 /* several owners: the first half of the list area is the inbox, the second half the region lists */
 KC_HD uint64_t kc_inbox_cap(uint64_t list_cap, uint32_t region_bits) { return (list_cap << region_bits) / 2; }

@@ -1,0 +1,227 @@
+/*
+ * yak_count.c -- the yak-count command line on top of libvafgpu's counting mode (include/kcgpu.h).
+ *
+ * Same options, input and output as the reference tool (yak-count.c:460-507):
+ *   yak-count [-k INT] [-p INT] [-b INT] [-H INT] [-t INT] [-K INT] <in.fa> [in.fa]
+ * prints the 1023 lines "count<TAB>number of distinct canonical k-mers seen that often" on
+ * stdout.  Without -b every k-mer is counted in one pass.  With -b the first file is read once
+ * to find the k-mers worth an entry -- those a Bloom filter of 2^b bits has seen before -- the
+ * second file (or the first one again) is read to count them, and entries seen fewer than twice
+ * are dropped (yak-count.c:445-456).  The host keeps option parsing, FASTA/FASTQ parsing and the
+ * printing; extraction, filter, tables and the histogram scan run on the GPUs.
+ *   -p  only checked (>= 10, yak-count.c:492-495): the partition into 2^p tables is an internal of
+ *       the reference; here the hash space is split over the visible GPUs instead
+ *   -K  bases per turn when reads are dealt to several GPUs (the reference's chunk size)
+ *   -t  number of host reader threads
+ *   -b  the filter gets 2^b bits on every GPU (cut down to a quarter of its memory)
+ * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: all visible);
+ *              KCGPU_TABLE_SLOTS=n slots per GPU to start with (default: from the file size);
+ *              either way a table that fills up is doubled and the files counted again.
+ * Deviations: k outside 1..31 is rejected; a file that cannot be opened is an error (the
+ * reference dereferences NULL); with -b AND a second file the entries kept can differ from the
+ * reference's by false positives of the filter (include/kcgpu.h), as they do between two values
+ * of -b in the reference itself.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/kcgpu.h"
+#include "fastx.h"
+#include "ingest.h"
+
+typedef struct {
+	kcgpu_ctx **ctx;
+	int n_dev, chunk;
+} engine_t;
+
+typedef struct {
+	engine_t *e;
+	kcgpu_producer *prod[KCGPU_MAX_OWNERS];
+	int turn;
+	uint64_t in_turn;
+} reader_t;
+
+static int reader_destroy(void *producer)
+{
+	reader_t *r = (reader_t *)producer;
+	int rc = 0;
+	for (int i = 0; i < r->e->n_dev; ++i)
+		if (r->prod[i] && kcgpu_producer_destroy(r->prod[i]) != VAFGPU_OK) rc = -1;
+	free(r);
+	return rc;
+}
+
+static int reader_create(void *engine, void **producer)
+{
+	static int next_turn = 0;
+	engine_t *e = (engine_t *)engine;
+	reader_t *r = (reader_t *)calloc(1, sizeof *r);
+	if (!r) return -1;
+	r->e = e;
+	r->turn = __atomic_fetch_add(&next_turn, 1, __ATOMIC_RELAXED) % e->n_dev;
+	for (int i = 0; i < e->n_dev; ++i)
+		if (kcgpu_producer_create(e->ctx[i], &r->prod[i]) != VAFGPU_OK) {
+			reader_destroy(r);
+			return -1;
+		}
+	*producer = r;
+	return 0;
+}
+
+static int reader_add_read(void *producer, const char *seq, size_t len)
+{
+	reader_t *r = (reader_t *)producer;
+	if (kcgpu_producer_add_read(r->prod[r->turn], seq, len) != VAFGPU_OK) return -1;
+	r->in_turn += len;
+	if (r->in_turn >= (uint64_t)r->e->chunk) {
+		r->in_turn = 0;
+		r->turn = (r->turn + 1) % r->e->n_dev;
+	}
+	return 0;
+}
+
+static const char *engine_error(void *engine)
+{
+	engine_t *e = (engine_t *)engine;
+	for (int i = 0; i < e->n_dev; ++i)
+		if (kcgpu_strerror(e->ctx[i])[0]) return kcgpu_strerror(e->ctx[i]);
+	return "unknown error";
+}
+
+static uint64_t guess_slots(const char *fn, int n_dev)
+{
+	struct stat sb;
+	uint64_t est;
+	FILE *fp;
+	unsigned char magic[2] = {0, 0};
+	if (stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode)) return 0; /* a pipe: as large as fits */
+	est = (uint64_t)sb.st_size;
+	if ((fp = fopen(fn, "rb")) != NULL) {
+		if (fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) est *= 4; /* gzip */
+		fclose(fp);
+	}
+	est /= (uint64_t)n_dev;
+	return est < (1u << 20) ? 1u << 20 : est;
+}
+
+/* one pass over one file; 0, or 1 after printing what went wrong */
+static int count_file(engine_t *eng, const char *fn, int k, int n_thread)
+{
+	ingest_sink_t sink = {eng, reader_create, reader_add_read, reader_destroy, engine_error};
+	ingest_file_t info;
+	char *files[1] = {(char *)fn};
+	if (ingest_files_to(&sink, 1, files, k, eng->chunk, n_thread, &info) != 0) return 1;
+	if (!info.opened) {
+		fprintf(stderr, "ERROR: cannot open %s\n", fn);
+		return 1;
+	}
+	fprintf(stderr, "[M] processed %llu sequences of %s\n", (unsigned long long)info.seqs, fn);
+	return 0;
+}
+
+int main(int argc, char *argv[])
+{
+	int c, k = 31, pre = 10, bf_shift = 0, bf_n_hash = 4, n_thread = 4, chunk = 10000000, n_dev, i; /* yak-count.c:312-321 */
+	while ((c = getopt(argc, argv, "k:p:K:t:b:H:")) >= 0) {
+		if (c == 'k') k = atoi(optarg);
+		else if (c == 'p') pre = atoi(optarg);
+		else if (c == 'K') chunk = atoi(optarg);
+		else if (c == 't') n_thread = atoi(optarg);
+		else if (c == 'b') bf_shift = atoi(optarg);
+		else if (c == 'H') bf_n_hash = atoi(optarg);
+	}
+	if (argc - optind < 1) { /* yak-count.c:481-491 */
+		fprintf(stderr, "Usage: yak-count [options] <in.fa> [in.fa]\n");
+		fprintf(stderr, "Options:\n");
+		fprintf(stderr, "  -k INT     k-mer size [%d]\n", k);
+		fprintf(stderr, "  -p INT     prefix length [%d]\n", pre);
+		fprintf(stderr, "  -b INT     set Bloom filter size to 2**INT bits; 0 to disable [%d]\n", bf_shift);
+		fprintf(stderr, "  -H INT     use INT hash functions for Bloom filter [%d]\n", bf_n_hash);
+		fprintf(stderr, "  -t INT     number of worker threads [%d]\n", n_thread);
+		fprintf(stderr, "  -K INT     chunk size [100m]\n");
+		fprintf(stderr, "Note: -b37 is recommended for human reads\n");
+		return 1;
+	}
+	if (pre < 10) { /* yak-count.c:492-495 */
+		fprintf(stderr, "ERROR: -p should be at least %d\n", 10);
+		return 1;
+	}
+	if (k < 1 || k > 31) {
+		fprintf(stderr, "ERROR: -k should be between 1 and 31\n");
+		return 1;
+	}
+	if (chunk < 1) chunk = 1;
+	const char *fn1 = argv[optind], *fn2 = argc - optind >= 2 ? argv[optind + 1] : fn1;
+	const int two_pass = bf_shift > 0; /* yak-count.c:449: decided by -b alone, whether or not a filter comes of it */
+	/* the reference builds a filter when -H > 0 and -b > -p, one per partition of at least one block (yak-count.c:75,117) */
+	const int filter = bf_n_hash > 0 && bf_shift > pre && bf_shift - pre >= 9;
+
+	n_dev = kcgpu_device_count();
+	if (n_dev < 1) {
+		fprintf(stderr, "ERROR: no CUDA device (this build has no CPU path)\n");
+		return 1;
+	}
+	if (getenv("KCGPU_DEVICES") && atoi(getenv("KCGPU_DEVICES")) > 0 && atoi(getenv("KCGPU_DEVICES")) < n_dev)
+		n_dev = atoi(getenv("KCGPU_DEVICES"));
+	if (n_dev > KCGPU_MAX_OWNERS) n_dev = KCGPU_MAX_OWNERS;
+
+	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn1, n_dev);
+	uint64_t got_before = 0;
+	for (int attempt = 0;; ++attempt) {
+		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
+		uint64_t hist[1024], part[1024], overflow = 0, tot = 0;
+		kcgpu_stats st;
+		for (i = 0; i < n_dev; ++i)
+			if (kcgpu_create_filtered(&ctx[i], k, slots, 0, 0, i, filter ? (bf_shift > 40 ? 40 : bf_shift) : 0, bf_n_hash > 64 ? 64 : bf_n_hash) != VAFGPU_OK) {
+				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
+				return 1;
+			}
+		if (n_dev > 1 && kcgpu_link(ctx, n_dev) != VAFGPU_OK) {
+			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
+			return 1;
+		}
+		engine_t eng = {ctx, n_dev, chunk};
+		/* yak_count_file, yak-count.c:445-456 */
+		/* with -b the counts of the first pass are thrown away (yak-count.c:452): it only makes the
+		 * entries -- for the k-mers the filter has seen before or, where no filter comes of -b
+		 * (yak-count.c:75,117), for all of them */
+		if (kcgpu_set_pass(ctx[0], two_pass ? KCGPU_PASS_CLAIM : KCGPU_PASS_COUNT) != VAFGPU_OK || count_file(&eng, fn1, k, n_thread)) {
+			if (kcgpu_strerror(ctx[0])[0]) fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
+			return 1;
+		}
+		if (two_pass && (kcgpu_set_pass(ctx[0], KCGPU_PASS_LOOKUP) != VAFGPU_OK || count_file(&eng, fn2, k, n_thread))) {
+			if (kcgpu_strerror(ctx[0])[0]) fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
+			return 1;
+		}
+		memset(hist, 0, sizeof hist);
+		for (i = 0; i < n_dev; ++i) {
+			if (kcgpu_histogram1024(ctx[i], part, two_pass ? 2 : 0, 1023, &st) != VAFGPU_OK) { /* the shrink, yak-count.c:453 */
+				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[i]));
+				return 1;
+			}
+			for (int j = 0; j < 1024; ++j) hist[j] += part[j], tot += part[j];
+			overflow += st.n_overflow;
+			slots = st.table_slots;
+		}
+		for (i = 0; i < n_dev; ++i) kcgpu_destroy(ctx[i]);
+		if (overflow) { /* never print a histogram with k-mers missing */
+			struct stat sb;
+			if (attempt >= 12 || stat(fn1, &sb) != 0 || !S_ISREG(sb.st_mode) || stat(fn2, &sb) != 0 || !S_ISREG(sb.st_mode) ||
+			    (attempt && slots <= got_before)) {
+				fprintf(stderr, "ERROR: the k-mer table (%llu slots per GPU) is full\n", (unsigned long long)slots);
+				return 1;
+			}
+			got_before = slots;
+			slots *= 2;
+			fprintf(stderr, "[yak-count] table full, counting again with %llu slots per GPU\n", (unsigned long long)slots);
+			continue;
+		}
+		fprintf(stderr, "[M::%s] %ld distinct k-mers after shrinking\n", __func__, (long)tot); /* yak-count.c:499 */
+		for (i = 1; i < 1024; ++i) printf("%d\t%lld\n", i, (long long)hist[i]);                    /* yak-count.c:503 */
+		return 0;
+	}
+}

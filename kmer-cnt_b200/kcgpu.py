@@ -29,8 +29,9 @@ EXPORTS = (
     "kcgpu_producer_flush", "kcgpu_producer_destroy", "kcgpu_submit_stream", "kcgpu_count_device", "kcgpu_extract_device",
     "kcgpu_insert_device", "kcgpu_table", "kcgpu_ipc_export", "kcgpu_ipc_open", "kcgpu_set_owners",
     "kcgpu_link", "kcgpu_sync", "kcgpu_flush", "kcgpu_histogram", "kcgpu_reset", "kcgpu_destroy", "kcgpu_strerror",
-    "kcgpu_hash64",
+    "kcgpu_hash64", "kcgpu_create_filtered", "kcgpu_set_pass", "kcgpu_histogram1024",
 )
+PASS_COUNT, PASS_CLAIM, PASS_LOOKUP = 0, 1, 2
 
 
 class Stats(C.Structure):
@@ -75,6 +76,9 @@ def load_library() -> C.CDLL:
     lib.kcgpu_flush.argtypes = [vp]
     lib.kcgpu_histogram.argtypes = [vp, u64p, C.POINTER(Stats)]
     lib.kcgpu_reset.argtypes = [vp]
+    lib.kcgpu_create_filtered.argtypes = [C.POINTER(vp), C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int]
+    lib.kcgpu_set_pass.argtypes = [vp, C.c_int]
+    lib.kcgpu_histogram1024.argtypes = [vp, u64p, C.c_int, C.c_int, C.POINTER(Stats)]
     for name in EXPORTS:
         if name not in ("kcgpu_destroy", "kcgpu_strerror", "kcgpu_hash64"):
             getattr(lib, name).restype = C.c_int
@@ -102,13 +106,20 @@ def format_histogram(hist: Sequence[int]) -> str:
     return "".join(f"{i}\t{int(hist[i])}\n" for i in range(1, 256))
 
 
+def format_histogram1024(hist: Sequence[int]) -> str:
+    """The 1023 lines yak-count prints (yak-count.c:503)."""
+    return "".join(f"{i}\t{int(hist[i])}\n" for i in range(1, 1024))
+
+
 class Counter:
     """One k-mer table with its region lists on one device."""
 
-    def __init__(self, k: int, table_slots: int = 0, block_bytes: int = 0, device: int = 0, list_slots: int = 0):
+    def __init__(self, k: int, table_slots: int = 0, block_bytes: int = 0, device: int = 0, list_slots: int = 0,
+                 bloom_bits: int = 0, bloom_hashes: int = 0):
         self._lib = load_library()
         self._ctx = C.c_void_p()
-        rc = self._lib.kcgpu_create(C.byref(self._ctx), k, table_slots, list_slots, block_bytes, device)
+        rc = self._lib.kcgpu_create_filtered(C.byref(self._ctx), k, table_slots, list_slots, block_bytes, device,
+                                             bloom_bits, bloom_hashes)
         if rc:
             raise VafGpuError(rc, self._lib.kcgpu_strerror(None).decode())
         self.k = k
@@ -165,6 +176,17 @@ class Counter:
         hist = np.zeros(256, dtype=np.uint64)
         st = Stats()
         self._check(self._lib.kcgpu_histogram(self._ctx, hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(st)))
+        return hist, st.as_dict()
+
+    def set_pass(self, which: int) -> None:
+        """PASS_COUNT / PASS_CLAIM / PASS_LOOKUP: what the insert step does from now on (yak-count's passes)"""
+        self._check(self._lib.kcgpu_set_pass(self._ctx, which))
+
+    def histogram1024(self, min_count: int = 1, max_count: int = 1023) -> Tuple[np.ndarray, dict]:
+        hist = np.zeros(1024, dtype=np.uint64)
+        st = Stats()
+        self._check(self._lib.kcgpu_histogram1024(self._ctx, hist.ctypes.data_as(C.POINTER(C.c_uint64)), min_count, max_count,
+                                                  C.byref(st)))
         return hist, st.as_dict()
 
     def reset(self) -> None:

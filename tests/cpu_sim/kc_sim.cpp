@@ -42,10 +42,10 @@ bool insert(Owner &o, uint64_t q)
 	for (uint64_t tries = 0; tries <= rmask; ++tries, pos = (pos + 1) & rmask) {
 		uint64_t &v = slice[pos];
 		if (v == 0) {
-			v = tag << KC_COUNT_BITS | 1;
+			v = (tag + 1) << KC_COUNT_BITS | 1;
 			return true;
 		}
-		if (v >> KC_COUNT_BITS == tag) {
+		if (v >> KC_COUNT_BITS == tag + 1) {
 			if ((v & KC_COUNT_MAX) < KC_COUNT_MAX) ++v;
 			return true;
 		}

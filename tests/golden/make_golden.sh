@@ -41,4 +41,27 @@ for name in k21 k15 k31 exotic; do
 		"$ref/kc-c4" -k "$k" -t 2 "$here/e2e_$name/reads.fq.gz" > "$here/kc/$name.k$k.hist"
 	done
 done
-ls -la "$here" "$here"/e2e_* "$here"/kc
+# yak-count: what the reference prints for the same read sets, without and with the Bloom filter
+# (one file: the result does not depend on the filter; -b 12 is too small for a filter to come of
+# it, the second pass still runs), and with two files that share reads (there the filter's
+# false positives show: -b 30 has none, -b 19 many)
+rm -rf "$here/yak"; mkdir -p "$here/yak"
+yak() { # out-name args...
+	local out=$1; shift
+	"$ref/yak-count" -t 2 "$@" > "$here/yak/$out.hist" 2>/dev/null
+}
+tmp=$(mktemp -d)
+for name in k21 exotic; do
+	fq="$here/e2e_$name/reads.fq.gz"
+	yak "$name.k31" -k 31 "$fq"
+	yak "$name.k21" -k 21 "$fq"
+	yak "$name.k21.b24" -k 21 -b 24 "$fq"
+	yak "$name.k15.b19.H3" -k 15 -b 19 -H 3 "$fq"
+	yak "$name.k27.b12" -k 27 -b 12 "$fq"
+	zcat "$fq" | head -n 12000 > "$tmp/a.fq"; zcat "$fq" | tail -n 12000 > "$tmp/b.fq"
+	yak "$name.k21.b30.two" -k 21 -b 30 "$tmp/a.fq" "$tmp/b.fq"
+	yak "$name.k21.b19.two" -k 21 -b 19 "$tmp/a.fq" "$tmp/b.fq"
+	yak "$name.k21.b0.two" -k 21 "$tmp/a.fq" "$tmp/b.fq"
+done
+rm -rf "$tmp"
+ls -la "$here" "$here"/e2e_* "$here"/kc "$here"/yak

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 import subprocess
 import sys
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -23,7 +23,8 @@ import vafgpu  # noqa: E402
 
 
 def build_oracle() -> None:
-    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "liboracle.so", "vaf_oracle", "kc_oracle", "spg_oracle", "synth"], check=True)
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "liboracle.so", "vaf_oracle", "kc_oracle", "yak_oracle", "spg_oracle", "synth"],
+                   check=True)
 
 
 def build_sim() -> str:
@@ -350,6 +351,52 @@ class KcOracle:
         for h in np.asarray(hashed, dtype=np.uint64).tolist():
             self.lib.kco_add_hashed(o, h)
         return self._finish(o)
+
+
+class YakOracle:
+    """liboracle.so's restatement of yak-count (oracle/yak_oracle.h)."""
+
+    def __init__(self):
+        build_oracle()
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "liboracle.so"))
+        lib.yko_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.yko_create.restype = C.c_void_p
+        lib.yko_destroy.argtypes = [C.c_void_p]
+        lib.yko_add_read.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_int]
+        lib.yko_second_pass.argtypes = [C.c_void_p]
+        lib.yko_shrink.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.yko_shrink.restype = C.c_uint64
+        lib.yko_count_files.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_long]
+        lib.yko_hist.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.yko_distinct.argtypes = [C.c_void_p]
+        lib.yko_distinct.restype = C.c_uint64
+        lib.yko_bf_insert.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint64]
+        self.lib = lib
+
+    def _hist(self, o) -> np.ndarray:
+        hist = np.zeros(1024, dtype=np.uint64)
+        self.lib.yko_hist(o, hist.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self.lib.yko_destroy(o)
+        return hist
+
+    def count_reads(self, reads: Sequence[bytes], k: int, *, bf_shift: int = 0, n_hash: int = 4, pre: int = 10,
+                    reads2: Optional[Sequence[bytes]] = None) -> np.ndarray:
+        """hist[1024] of yak_count_file (yak-count.c:445-456) over in-memory reads"""
+        o = self.lib.yko_create(k, pre, bf_shift, n_hash)
+        for r in reads:
+            self.lib.yko_add_read(o, r, len(r), 1)
+        if bf_shift > 0:
+            self.lib.yko_second_pass(o)
+            for r in (reads if reads2 is None else reads2):
+                self.lib.yko_add_read(o, r, len(r), 0)
+            self.lib.yko_shrink(o, 2, 1023)
+        return self._hist(o)
+
+    def count_files(self, fn1: str, fn2: Optional[str], k: int, *, bf_shift: int = 0, n_hash: int = 4, pre: int = 10,
+                    chunk: int = 10_000_000) -> np.ndarray:
+        o = self.lib.yko_create(k, pre, bf_shift, n_hash)
+        assert self.lib.yko_count_files(o, fn1.encode(), fn2.encode() if fn2 else None, chunk) == 0
+        return self._hist(o)
 
 
 def build_kc_sim() -> str:

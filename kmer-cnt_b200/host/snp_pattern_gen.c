@@ -24,56 +24,49 @@
 #include "../../include/vafgpu.h"
 #include "fastx.h"
 
+/* the genome in memory: every record of the FASTA file, named by its header up to the first
+ * white space (what snp-pattern-gen.c:70-104 keeps) */
 typedef struct {
-	char *name, *seq;
-	long len;
-} fasta_seq_t;
+	char *name, *bases;
+	long n_bases;
+} contig_t;
 
 typedef struct {
-	int n, m;
-	fasta_seq_t *a;
-} fasta_db_t;
+	contig_t *contig;
+	int n_contigs, room;
+} genome_t;
 
-typedef struct { /* one BED row, snp-pattern-gen.c:60-67 */
-	char chr[256];
-	int start, end;
-	char rsid[256];
-	char ref, alt;
-} snp_t;
-
-/* snp-pattern-gen.c:70-104: every record of the file, name up to the first white space */
-static fasta_db_t *load_fasta(const char *fn)
+static genome_t *genome_load(const char *fn)
 {
 	fastx_t *fx = fastx_open(fn);
-	fasta_db_t *db;
-	const char *s;
-	long l;
 	if (!fx) return NULL;
-	db = (fasta_db_t *)calloc(1, sizeof *db);
-	while ((l = fastx_next(fx, &s)) >= 0) {
-		if (db->n == db->m) {
-			db->m = db->m ? db->m << 1 : 16;
-			db->a = (fasta_seq_t *)realloc(db->a, (size_t)db->m * sizeof *db->a);
+	genome_t *g = (genome_t *)calloc(1, sizeof *g);
+	const char *s;
+	for (long l; (l = fastx_next(fx, &s)) >= 0;) {
+		if (g->n_contigs == g->room) {
+			g->room = g->room ? g->room * 2 : 16;
+			g->contig = (contig_t *)realloc(g->contig, (size_t)g->room * sizeof *g->contig);
 		}
-		fasta_seq_t *q = &db->a[db->n++];
-		q->name = strdup(fastx_name(fx));
-		q->seq = (char *)malloc((size_t)l + 1);
-		memcpy(q->seq, s, (size_t)l);
-		q->seq[l] = 0;
-		q->len = l;
+		contig_t *c = &g->contig[g->n_contigs++];
+		c->name = strdup(fastx_name(fx));
+		c->bases = (char *)malloc((size_t)l + 1);
+		memcpy(c->bases, s, (size_t)l);
+		c->bases[l] = 0;
+		c->n_bases = l;
 	}
 	fastx_close(fx);
-	return db;
+	return g;
 }
 
-static fasta_seq_t *find_seq(fasta_db_t *db, const char *chr) /* snp-pattern-gen.c:118-126: the first of that name */
+/* the first contig of that name (snp-pattern-gen.c:118-126), NULL if there is none */
+static const contig_t *genome_find(const genome_t *g, const char *name)
 {
-	for (int i = 0; i < db->n; ++i)
-		if (strcmp(db->a[i].name, chr) == 0) return &db->a[i];
+	for (int i = 0; i < g->n_contigs; ++i)
+		if (strcmp(g->contig[i].name, name) == 0) return &g->contig[i];
 	return NULL;
 }
 
-static int base_code(unsigned char b) /* snp-pattern-gen.c:30-47 */
+static int base_code(unsigned char b) /* the strict table, snp-pattern-gen.c:30-47 */
 {
 	if (b < 4) return b;
 	switch (b | 0x20) {
@@ -85,33 +78,71 @@ static int base_code(unsigned char b) /* snp-pattern-gen.c:30-47 */
 	return -1;
 }
 
-/* canonical k-mer of k characters, UINT64_MAX if one is not a base (snp-pattern-gen.c:129-159) */
+/* canonical k-mer of k characters that are all bases (snp-pattern-gen.c:129-159) */
 static uint64_t canonical_of(const char *s, int k)
 {
 	uint64_t f = 0, r = 0;
 	for (int i = 0; i < k; ++i) {
-		int c = base_code((unsigned char)s[i]);
-		if (c < 0) return UINT64_MAX;
-		f = f << 2 | (uint64_t)c;
-		r = r >> 2 | (uint64_t)(3 - c) << 2 * (k - 1);
+		const uint64_t c = (uint64_t)base_code((unsigned char)s[i]);
+		f = f << 2 | c;
+		r = r >> 2 | (3 - c) << 2 * (k - 1);
 	}
 	return f < r ? f : r;
 }
 
-/* snp-pattern-gen.c:193-216: the k characters around the SNP, as they stand in the genome */
-static int extract_snp_kmer(const fasta_seq_t *seq, int pos, char alt, int k, char *ref_kmer, char *alt_kmer)
+/* One row of the BED file (snp-pattern-gen.c:60-67) with everything both host passes need of it,
+ * worked out once: where it lies, the k characters around it as they stand in the genome
+ * (snp-pattern-gen.c:193-216: the window must lie inside the contig and hold bases only) with
+ * the reference and with the alternative allele in the middle, and their canonical words. */
+typedef struct {
+	char chr[256], rsid[256];
+	int start, end;
+	char ref, alt;
+	int on_genome;   /* its contig exists */
+	int usable;      /* ... and the window is whole and free of non-bases, the alternative allele a base */
+	char ref_kmer[32], alt_kmer[32];
+	uint64_t ref_key, alt_key;
+} site_t;
+
+static void site_resolve(site_t *s, const genome_t *g, int k)
 {
-	const int flank = k / 2;
-	const long start = (long)pos - flank;
-	if (start < 0 || start + k > seq->len) return 0;
+	const contig_t *c = genome_find(g, s->chr);
+	const long first = (long)s->start - k / 2;
+	s->on_genome = c != NULL;
+	s->usable = 0;
+	if (!c || first < 0 || first + k > c->n_bases) return;
 	for (int i = 0; i < k; ++i)
-		if (base_code((unsigned char)seq->seq[start + i]) < 0) return 0;
-	memcpy(ref_kmer, seq->seq + start, (size_t)k);
-	ref_kmer[k] = 0;
-	memcpy(alt_kmer, seq->seq + start, (size_t)k);
-	alt_kmer[flank] = alt;
-	alt_kmer[k] = 0;
-	return 1;
+		if (base_code((unsigned char)c->bases[first + i]) < 0) return;
+	if (base_code((unsigned char)s->alt) < 0) return; /* the reference finds this out when it encodes the k-mer (:283,335) */
+	memcpy(s->ref_kmer, c->bases + first, (size_t)k);
+	memcpy(s->alt_kmer, c->bases + first, (size_t)k);
+	s->alt_kmer[k / 2] = s->alt;
+	s->ref_kmer[k] = s->alt_kmer[k] = 0;
+	s->ref_key = canonical_of(s->ref_kmer, k);
+	s->alt_key = canonical_of(s->alt_kmer, k);
+	s->usable = 1;
+}
+
+/* every row of the BED file the reference's fscanf loop would read (snp-pattern-gen.c:270,327) */
+static site_t *sites_load(const char *fn, const genome_t *g, int k, int *n_out)
+{
+	FILE *fp = fopen(fn, "r");
+	site_t *sites = NULL, row;
+	int n = 0, room = 0;
+	if (!fp) return NULL;
+	memset(&row, 0, sizeof row);
+	while (fscanf(fp, "%254s%d%d%254s %c %c", row.chr, &row.start, &row.end, row.rsid, &row.ref, &row.alt) == 6) {
+		if (n == room) {
+			room = room ? room * 2 : 1024;
+			sites = (site_t *)realloc(sites, (size_t)room * sizeof *sites);
+		}
+		site_resolve(&row, g, k);
+		sites[n++] = row;
+	}
+	fclose(fp);
+	if (!sites) sites = (site_t *)calloc(1, sizeof *sites);
+	*n_out = n;
+	return sites;
 }
 
 /* the candidate set: canonical k-mer -> index, in order of first appearance */
@@ -171,7 +202,7 @@ static long cand_get(const cand_t *c, uint64_t key) /* index or -1 */
 /* pass 2: the chromosomes to the engine, longest first, a few reader threads */
 typedef struct {
 	vafgpu_ctx *ctx;
-	fasta_db_t *db;
+	const genome_t *genome;
 	int *order, next, failed;
 	pthread_mutex_t mu;
 } feed_t;
@@ -186,34 +217,27 @@ static void *feeder(void *arg)
 	}
 	for (;;) {
 		pthread_mutex_lock(&f->mu);
-		int i = f->failed ? f->db->n : f->next++;
+		int i = f->failed ? f->genome->n_contigs : f->next++;
 		pthread_mutex_unlock(&f->mu);
-		if (i >= f->db->n) break;
-		const fasta_seq_t *q = &f->db->a[f->order[i]];
-		if (vafgpu_producer_add_read(p, q->seq, (size_t)q->len) != VAFGPU_OK) f->failed = 1;
+		if (i >= f->genome->n_contigs) break;
+		const contig_t *q = &f->genome->contig[f->order[i]];
+		if (vafgpu_producer_add_read(p, q->bases, (size_t)q->n_bases) != VAFGPU_OK) f->failed = 1;
 	}
 	if (vafgpu_producer_destroy(p) != VAFGPU_OK) f->failed = 1;
 	return NULL;
 }
 
-static fasta_db_t *g_sort_db;
-static int by_len_desc(const void *a, const void *b)
+static const genome_t *g_sort_genome;
+static int longest_first(const void *a, const void *b)
 {
-	long la = g_sort_db->a[*(const int *)a].len, lb = g_sort_db->a[*(const int *)b].len;
+	long la = g_sort_genome->contig[*(const int *)a].n_bases, lb = g_sort_genome->contig[*(const int *)b].n_bases;
 	return la < lb ? 1 : la > lb ? -1 : *(const int *)a - *(const int *)b;
 }
 
 int main(int argc, char *argv[])
 {
 	int c, k = 21;
-	char *bed_fn = 0, *fasta_fn = 0, *out_fn = 0;
-	FILE *bed_fp, *out_fp;
-	snp_t snp;
-	char ref_kmer[128], alt_kmer[128];
-	int n_total = 0, n_unique = 0, n_candidate = 0;
-	cand_t cand;
-	memset(&cand, 0, sizeof cand);
-
+	const char *bed_fn = NULL, *fasta_fn = NULL, *out_fn = NULL;
 	while ((c = getopt(argc, argv, "k:b:f:o:")) >= 0) {
 		if (c == 'k') k = atoi(optarg);
 		else if (c == 'b') bed_fn = optarg;
@@ -239,34 +263,31 @@ int main(int argc, char *argv[])
 	}
 
 	fprintf(stderr, "[M::%s] Loading reference genome...\n", __func__);
-	fasta_db_t *db = load_fasta(fasta_fn);
-	if (!db) {
+	genome_t *genome = genome_load(fasta_fn);
+	if (!genome) {
 		fprintf(stderr, "Error: failed to load FASTA file\n");
 		return 1;
 	}
-	fprintf(stderr, "[M::%s] Loaded %d sequences\n", __func__, db->n);
+	fprintf(stderr, "[M::%s] Loaded %d sequences\n", __func__, genome->n_contigs);
 
-	/* pass 1: candidate k-mers of the BED rows (snp-pattern-gen.c:262-301) */
+	/* the BED rows, read once and resolved against the genome; the reference reads the file twice
+	 * (snp-pattern-gen.c:262-301 and :318-356) and resolves every row in both passes */
 	fprintf(stderr, "[M::%s] Generating candidate k-mers from BED file...\n", __func__);
-	bed_fp = fopen(bed_fn, "r");
-	if (!bed_fp) {
+	int n_sites = 0;
+	site_t *sites = sites_load(bed_fn, genome, k, &n_sites);
+	if (!sites) {
 		fprintf(stderr, "Error: failed to open BED file\n");
 		return 1;
 	}
-	while (fscanf(bed_fp, "%254s%d%d%254s %c %c", snp.chr, &snp.start, &snp.end, snp.rsid, &snp.ref, &snp.alt) == 6) {
-		fasta_seq_t *seq = find_seq(db, snp.chr);
-		if (!seq) continue;
-		if (extract_snp_kmer(seq, snp.start, snp.alt, k, ref_kmer, alt_kmer)) {
-			uint64_t ref_can = canonical_of(ref_kmer, k), alt_can = canonical_of(alt_kmer, k);
-			if (ref_can == UINT64_MAX || alt_can == UINT64_MAX) continue;
-			n_candidate += cand_put(&cand, ref_can);
-			n_candidate += cand_put(&cand, alt_can);
-		}
-	}
-	fclose(bed_fp);
+	/* the candidate set: both k-mers of every usable row */
+	cand_t cand;
+	memset(&cand, 0, sizeof cand);
+	int n_candidate = 0;
+	for (int i = 0; i < n_sites; ++i)
+		if (sites[i].usable) n_candidate += cand_put(&cand, sites[i].ref_key) + cand_put(&cand, sites[i].alt_key);
 	fprintf(stderr, "[M::%s] Generated %d candidate k-mers\n", __func__, n_candidate);
 
-	/* pass 2 on the GPU: candidate i is "allele i & 1 of pattern i >> 1" of a vaf-counter panel */
+	/* the genome scan on the GPU: candidate i is "allele i & 1 of pattern i >> 1" of a vaf-counter panel */
 	fprintf(stderr, "[M::%s] Counting candidate k-mers in genome...\n", __func__);
 	uint32_t *vals = (uint32_t *)malloc(((size_t)cand.n + 1) * 4);
 	uint32_t n_pairs = (cand.n + 1) / 2 ? (cand.n + 1) / 2 : 1;
@@ -275,7 +296,7 @@ int main(int argc, char *argv[])
 	vafgpu_ctx *ctx = NULL;
 	int n_feed = (int)sysconf(_SC_NPROCESSORS_ONLN);
 	if (n_feed > 8) n_feed = 8;
-	if (n_feed > db->n) n_feed = db->n;
+	if (n_feed > genome->n_contigs) n_feed = genome->n_contigs;
 	if (n_feed < 1) n_feed = 1;
 	/* one GPU: a human genome is a second of kernel time, more devices only add start-up */
 	if (vafgpu_create(&ctx, k, cand.keys, vals, cand.n, n_pairs, 0, n_feed + 2, 1, VAFGPU_F_STRICT_BYTES) != VAFGPU_OK) {
@@ -284,11 +305,11 @@ int main(int argc, char *argv[])
 	}
 	feed_t feed;
 	memset(&feed, 0, sizeof feed);
-	feed.ctx = ctx, feed.db = db;
-	feed.order = (int *)malloc(((size_t)db->n + 1) * sizeof(int));
-	for (int i = 0; i < db->n; ++i) feed.order[i] = i;
-	g_sort_db = db;
-	qsort(feed.order, (size_t)db->n, sizeof(int), by_len_desc);
+	feed.ctx = ctx, feed.genome = genome;
+	feed.order = (int *)malloc(((size_t)genome->n_contigs + 1) * sizeof(int));
+	for (int i = 0; i < genome->n_contigs; ++i) feed.order[i] = i;
+	g_sort_genome = genome;
+	qsort(feed.order, (size_t)genome->n_contigs, sizeof(int), longest_first);
 	pthread_mutex_init(&feed.mu, NULL);
 	pthread_t th[8];
 	for (int i = 1; i < n_feed; ++i) pthread_create(&th[i], NULL, feeder, &feed);
@@ -301,38 +322,28 @@ int main(int argc, char *argv[])
 	vafgpu_destroy(ctx);
 	fprintf(stderr, "[M::%s] Finished counting k-mers\n", __func__);
 
-	/* pass 3: the rows whose pair is unique (snp-pattern-gen.c:303-356) */
-	bed_fp = fopen(bed_fn, "r");
-	if (!bed_fp) {
-		fprintf(stderr, "Error: failed to open BED file\n");
-		return 1;
-	}
-	out_fp = fopen(out_fn, "w");
+	/* the selection: rows whose reference k-mer occurs exactly once in the genome and whose
+	 * alternative k-mer never does (snp-pattern-gen.c:1-16,338-356), in the order of the BED file */
+	FILE *out_fp = fopen(out_fn, "w");
 	if (!out_fp) {
 		fprintf(stderr, "Error: failed to open output file\n");
 		return 1;
 	}
 	fprintf(stderr, "[M::%s] Processing SNPs...\n", __func__);
-	while (fscanf(bed_fp, "%254s%d%d%254s %c %c", snp.chr, &snp.start, &snp.end, snp.rsid, &snp.ref, &snp.alt) == 6) {
-		fasta_seq_t *seq = find_seq(db, snp.chr);
-		++n_total;
-		if (!seq) {
-			fprintf(stderr, "Warning: chromosome %s not found\n", snp.chr);
+	int n_unique = 0;
+	for (int i = 0; i < n_sites; ++i) {
+		const site_t *s = &sites[i];
+		if (!s->on_genome) {
+			fprintf(stderr, "Warning: chromosome %s not found\n", s->chr);
 			continue;
 		}
-		if (extract_snp_kmer(seq, snp.start, snp.alt, k, ref_kmer, alt_kmer)) {
-			uint64_t ref_can = canonical_of(ref_kmer, k), alt_can = canonical_of(alt_kmer, k);
-			if (ref_can == UINT64_MAX || alt_can == UINT64_MAX) continue;
-			long ri = cand_get(&cand, ref_can), ai = cand_get(&cand, alt_can);
-			if (ri >= 0 && counts[ri] == 1 && ai >= 0 && counts[ai] == 0) {
-				fprintf(out_fp, "%s\t%d\t%d\t%s\t%c\t%c\t%s\t%s\n", snp.chr, snp.start, snp.end, snp.rsid, snp.ref, snp.alt,
-				        ref_kmer, alt_kmer);
-				++n_unique;
-			}
-		}
+		if (!s->usable) continue;
+		const long ri = cand_get(&cand, s->ref_key), ai = cand_get(&cand, s->alt_key);
+		if (ri < 0 || ai < 0 || counts[ri] != 1 || counts[ai] != 0) continue;
+		fprintf(out_fp, "%s\t%d\t%d\t%s\t%c\t%c\t%s\t%s\n", s->chr, s->start, s->end, s->rsid, s->ref, s->alt, s->ref_kmer, s->alt_kmer);
+		++n_unique;
 	}
-	fprintf(stderr, "[M::%s] Total SNPs: %d, Unique k-mer pairs: %d\n", __func__, n_total, n_unique);
-	fclose(bed_fp);
+	fprintf(stderr, "[M::%s] Total SNPs: %d, Unique k-mer pairs: %d\n", __func__, n_sites, n_unique);
 	fclose(out_fp);
 	return 0;
 }

@@ -170,7 +170,9 @@ def test_full_table_is_reported_not_walked_forever(torch_cuda):
     with kcgpu.Counter(31, 4096) as c:
         c.count_device(d.data_ptr(), d.numel())
         hist, st = c.histogram()
-    assert st["n_overflow"] > 0 and st["n_distinct"] <= 4096 and int(hist.sum()) == st["n_distinct"]
+    # (4096 slots asked for; k = 31 needs 2^9 regions of at least 16 slots for the tag to fit: 8192)
+    assert st["table_slots"] == 8192
+    assert st["n_overflow"] > 0 and st["n_distinct"] <= st["table_slots"] and int(hist.sum()) == st["n_distinct"]
 
 
 @pytest.mark.parametrize("n_parts", [1, 2, 3, 8])

@@ -128,7 +128,9 @@ int kcgpu_producer_destroy(kcgpu_producer *producer);
  * other than A C G T U (either case) end a k-mer (no byte translation is done: hand parsed reads
  * to kcgpu_add_read if they may hold the bytes 0..3).  Page-locked memory is copied to the
  * device as it is, block by block, each copy overlapping the previous block's kernel; pageable
- * memory goes through the pinned staging blocks.  Returns when everything is submitted.
+ * memory goes through the pinned staging blocks.  Returns when everything is submitted: a
+ * page-locked buffer is still being read by the copy engines then, and must stay valid and
+ * unmodified until kcgpu_sync, kcgpu_flush or kcgpu_histogram has returned.
  */
 int kcgpu_submit_stream(kcgpu_ctx *ctx, const char *bytes, size_t n_bytes);
 

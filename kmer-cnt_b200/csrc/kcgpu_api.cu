@@ -61,7 +61,7 @@ struct kcgpu_ctx {
 	cudaStream_t main_stream = nullptr;
 	size_t block_bytes = 0;
 	std::vector<KcBlock *> blocks;
-	size_t next_block = 0;
+	size_t next_block = 0, n_producers = 0; /* n_producers: those made by kcgpu_producer_create and still alive */
 	kcgpu_producer *def = nullptr; /* the producer behind kcgpu_add_read / kcgpu_submit_stream */
 	uint32_t n_parts = 1, my_part = 0;
 	uint64_t *tables[KC_MAX_PARTS] = {};
@@ -514,11 +514,16 @@ int kcgpu_producer_create(kcgpu_ctx *c, kcgpu_producer **out)
 	if (!p) return kfail(c, VAFGPU_ENOMEM, "out of memory");
 	p->c = c;
 	std::lock_guard<std::mutex> lk(g_kc_mu);
-	int rc = kc_add_block(c); /* one block per reader to fill, on top of those in flight */
-	if (rc) {
-		delete p;
-		return rc;
+	/* one block per live reader to fill, on top of the three in flight; the blocks of readers that
+	 * are gone (the first pass of a two-pass count) are taken over */
+	if (c->blocks.size() < 3 + c->n_producers + 1) {
+		int rc = kc_add_block(c);
+		if (rc) {
+			delete p;
+			return rc;
+		}
 	}
+	c->n_producers++;
 	*out = p;
 	return VAFGPU_OK;
 }
@@ -568,6 +573,10 @@ int kcgpu_producer_destroy(kcgpu_producer *p)
 {
 	if (!p) return VAFGPU_OK;
 	int rc = kcgpu_producer_flush(p);
+	{
+		std::lock_guard<std::mutex> lk(g_kc_mu);
+		if (p->c->n_producers) p->c->n_producers--;
+	}
 	delete p;
 	return rc;
 }

@@ -16,7 +16,8 @@
  *   -b  the filter gets 2^b bits on every GPU (cut down to a quarter of its memory)
  * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: all visible);
  *              KCGPU_TABLE_SLOTS=n slots per GPU to start with (default: from the file size);
- *              either way a table that fills up is doubled and the files counted again.
+ *              either way a table that fills up is doubled and the files counted again;
+ *              KCGPU_TIMING: phase times on stderr.
  * Deviations: k outside 1..31 is rejected; a file that cannot be opened is an error (the
  * reference dereferences NULL); with -b AND a second file the entries kept can differ from the
  * reference's by false positives of the filter (include/kcgpu.h), as they do between two values
@@ -27,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include "../../include/kcgpu.h"
@@ -37,6 +39,13 @@ typedef struct {
 	kcgpu_ctx **ctx;
 	int n_dev, chunk;
 } engine_t;
+
+static double now(void)
+{
+	struct timeval tv;
+	gettimeofday(&tv, NULL);
+	return tv.tv_sec + tv.tv_usec * 1e-6;
+}
 
 typedef struct {
 	engine_t *e;
@@ -171,7 +180,9 @@ int main(int argc, char *argv[])
 
 	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn1, n_dev);
 	uint64_t got_before = 0;
+	const int timing = getenv("KCGPU_TIMING") != NULL;
 	for (int attempt = 0;; ++attempt) {
+		double t0 = now(), t1;
 		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
 		uint64_t hist[1024], part[1024], overflow = 0, tot = 0;
 		kcgpu_stats st;
@@ -185,6 +196,7 @@ int main(int argc, char *argv[])
 			return 1;
 		}
 		engine_t eng = {ctx, n_dev, chunk};
+		if (timing) fprintf(stderr, "[yak-count] contexts (%llu slots per GPU)  %8.1f ms\n", (unsigned long long)slots, ((t1 = now()) - t0) * 1e3), t0 = t1;
 		/* yak_count_file, yak-count.c:445-456 */
 		/* with -b the counts of the first pass are thrown away (yak-count.c:452): it only makes the
 		 * entries -- for the k-mers the filter has seen before or, where no filter comes of -b
@@ -193,10 +205,12 @@ int main(int argc, char *argv[])
 			if (kcgpu_strerror(ctx[0])[0]) fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
 			return 1;
 		}
+		if (timing) fprintf(stderr, "[yak-count] first pass                      %8.1f ms\n", ((t1 = now()) - t0) * 1e3), t0 = t1;
 		if (two_pass && (kcgpu_set_pass(ctx[0], KCGPU_PASS_LOOKUP) != VAFGPU_OK || count_file(&eng, fn2, k, n_thread))) {
 			if (kcgpu_strerror(ctx[0])[0]) fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
 			return 1;
 		}
+		if (timing && two_pass) fprintf(stderr, "[yak-count] second pass                     %8.1f ms\n", ((t1 = now()) - t0) * 1e3), t0 = t1;
 		memset(hist, 0, sizeof hist);
 		for (i = 0; i < n_dev; ++i) {
 			if (kcgpu_histogram1024(ctx[i], part, two_pass ? 2 : 0, 1023, &st) != VAFGPU_OK) { /* the shrink, yak-count.c:453 */
@@ -207,7 +221,9 @@ int main(int argc, char *argv[])
 			overflow += st.n_overflow;
 			slots = st.table_slots;
 		}
+		if (timing) fprintf(stderr, "[yak-count] flush + histogram               %8.1f ms (kernels %.1f ms, copies %.1f ms)\n", ((t1 = now()) - t0) * 1e3, st.kernel_ms, st.h2d_ms), t0 = t1;
 		for (i = 0; i < n_dev; ++i) kcgpu_destroy(ctx[i]);
+		if (timing) fprintf(stderr, "[yak-count] destroy                         %8.1f ms\n", (now() - t0) * 1e3);
 		if (overflow) { /* never print a histogram with k-mers missing */
 			struct stat sb;
 			if (attempt >= 12 || stat(fn1, &sb) != 0 || !S_ISREG(sb.st_mode) || stat(fn2, &sb) != 0 || !S_ISREG(sb.st_mode) ||

@@ -5,6 +5,11 @@
 //   cursor     one 64-bit atomicAdd with return on R cursors, 256 bytes apart
 //   l2cas      load + compare-and-swap per key into a table slice of S MiB (L2-resident for S <= 64)
 //   smemcas    the same into a shared-memory table of 16 K slots per CTA
+//   l2red      load + reduction (no return value) per key into an L2-resident slice: the cost of an increment
+//              when the entry is known to exist
+//   part       one radix-partition pass with shared-memory staging: a CTA ranks a tile of keys by a digit of
+//              RB bits (shared-memory atomics), sorts the tile in shared memory, reserves one run per digit
+//              with one cursor atomic and writes the runs out -- whole sectors instead of 8-byte stores
 // Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/exp/kc_store_exp tools/exp/kc_store_exp.cu
 // Run:   tools/exp/kc_store_exp [keys in millions = 512]
 #include <cstdio>
@@ -87,6 +92,99 @@ __global__ void __launch_bounds__(1024, 1) smemcas(uint64_t per_cta, unsigned lo
 	if (tab[threadIdx.x] == 12345) *sink = 1;
 }
 
+__global__ void l2red(unsigned long long *table, uint64_t slice_slots, uint32_t n_slices, uint32_t ctas_per_slice, uint64_t per_cta,
+                      unsigned long long *sink)
+{
+	const uint32_t s = blockIdx.x / ctas_per_slice;
+	if (s >= n_slices) return;
+	unsigned long long *slice = table + (uint64_t)s * slice_slots;
+	const uint64_t base = (uint64_t)blockIdx.x * per_cta, mask = slice_slots - 1;
+	unsigned long long acc = 0;
+	for (uint64_t i = threadIdx.x; i < per_cta; i += blockDim.x) {
+		const uint64_t pos = mix(base + i) >> 20 & mask;
+		acc += slice[pos];
+		atomicAdd(slice + pos, 1ull); /* result unused: RED */
+	}
+	if (acc == 12345) *sink = acc;
+}
+
+// T threads, IPT keys per thread; lists[r * cap + ...], cursors 256 bytes apart as in the library
+template <int RB, int T, int IPT>
+__global__ void __launch_bounds__(T, 1) part(const uint64_t *__restrict__ in, uint64_t n, uint64_t *lists, unsigned long long *cur, uint64_t cap, int shift)
+{
+	constexpr int R = 1 << RB, TILE = T * IPT;
+	extern __shared__ unsigned long long smem[];
+	unsigned long long *stage = smem;
+	uint32_t *cnt = reinterpret_cast<uint32_t *>(stage + TILE); /* R counts, then R local bases */
+	uint32_t *lbase = cnt + R;
+	unsigned long long *gbase = reinterpret_cast<unsigned long long *>(lbase + R);
+	const int tid = threadIdx.x;
+	const uint64_t n_tiles = n / TILE;
+	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		for (int r = tid; r < R; r += T) cnt[r] = 0;
+		__syncthreads();
+		uint64_t key[IPT];
+		uint16_t rank[IPT];
+		const uint64_t *src = in + tile * TILE;
+#pragma unroll
+		for (int j = 0; j < IPT; ++j) key[j] = __ldcs(src + j * T + tid);
+#pragma unroll
+		for (int j = 0; j < IPT; ++j) rank[j] = (uint16_t)atomicAdd(cnt + (key[j] >> shift & (R - 1)), 1u);
+		__syncthreads();
+		/* exclusive prefix over the R counts: PER per thread, warp scan, one scan over the warp totals */
+		{
+			constexpr int PER = R / T > 0 ? R / T : 1;
+			__shared__ uint32_t wsum[32];
+			uint32_t sum = 0, c[PER];
+#pragma unroll
+			for (int i = 0; i < PER; ++i) c[i] = tid * PER + i < R ? cnt[tid * PER + i] : 0, sum += c[i];
+			uint32_t incl = sum;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+				if ((tid & 31) >= d) incl += v;
+			}
+			if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+			__syncthreads();
+			if (tid < 32) {
+				const uint32_t w = tid < T / 32 ? wsum[tid] : 0;
+				uint32_t wi = w;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+					if (tid >= d) wi += v;
+				}
+				wsum[tid] = wi - w;
+			}
+			__syncthreads();
+			uint32_t at = wsum[tid >> 5] + incl - sum;
+#pragma unroll
+			for (int i = 0; i < PER; ++i)
+				if (tid * PER + i < R) lbase[tid * PER + i] = at, at += c[i];
+		}
+		__syncthreads();
+		for (int r = tid; r < R; r += T) {
+			const uint32_t c = cnt[r];
+			gbase[r] = (c ? atomicAdd(cur + r * 32, (unsigned long long)c) : 0ull) + (unsigned long long)r * cap - lbase[r];
+		}
+#pragma unroll
+		for (int j = 0; j < IPT; ++j) stage[lbase[key[j] >> shift & (R - 1)] + rank[j]] = key[j];
+		__syncthreads();
+#pragma unroll 4
+		for (int i = tid; i < TILE; i += T) {
+			const unsigned long long k = stage[i];
+			lists[(gbase[k >> shift & (R - 1)] + i) % (cap << RB)] = k; /* the modulo only keeps a repeated run of the benchmark in bounds */
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void fill_keys(uint64_t *keys, uint64_t n)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) keys[i] = mix(i);
+}
+
 template <typename F> static float timed(F f)
 {
 	cudaEvent_t a, b;
@@ -143,6 +241,42 @@ int main(int argc, char **argv)
 		cudaEventElapsedTime(&ms, a, b);
 		printf("l2cas      slice %3u MiB  %7.2f ms  %6.1f G inserts/s\n", mib, ms, total / ms / 1e6);
 		cudaFree(table);
+	}
+	for (uint32_t mib : {16u, 64u}) {
+		const uint64_t slice_slots = (uint64_t)mib << 17;
+		const uint32_t n_slices = 64, ctas_per_slice = 1024;
+		const uint64_t per_cta = slice_slots / 4 / ctas_per_slice;
+		unsigned long long *table;
+		cudaMalloc(&table, slice_slots * n_slices * 8);
+		cudaMemset(table, 0, slice_slots * n_slices * 8);
+		const uint64_t total = per_cta * ctas_per_slice * n_slices;
+		float ms = timed([&] { l2red<<<n_slices * ctas_per_slice, block>>>(table, slice_slots, n_slices, ctas_per_slice, per_cta, sink); });
+		printf("l2red      slice %3u MiB  %7.2f ms  %6.1f G updates/s\n", mib, ms, total / ms / 1e6);
+		cudaFree(table);
+	}
+	{
+		uint64_t *keys, *lists;
+		unsigned long long *cur;
+		cudaMalloc(&keys, n * 8);
+		fill_keys<<<grid, block>>>(keys, n);
+		auto run = [&](auto kernel, int rb, int threads, int ipt, const char *name) {
+			const uint64_t cap = ((n >> rb) * 2 + 31) & ~31ull;
+			cudaMalloc(&lists, (cap << rb) * 8);
+			cudaMalloc(&cur, 256ull << rb);
+			cudaMemset(cur, 0, 256ull << rb);
+			const size_t smem = (size_t)threads * ipt * 8 + ((size_t)8 << rb) + ((size_t)8 << rb);
+			cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			float ms = timed([&] { kernel<<<148, threads, smem>>>(keys, n, lists, cur, cap, 20); });
+			printf("part       %-22s smem %3zu KB  %7.2f ms  %6.1f G keys/s  (%.0f GB/s read + written)\n", name, smem >> 10, ms, n / ms / 1e6, n * 16 / ms / 1e6);
+			cudaFree(lists), cudaFree(cur);
+		};
+		run(part<6, 512, 16>, 6, 512, 16, "R=64 512x16");
+		run(part<8, 512, 16>, 8, 512, 16, "R=256 512x16");
+		run(part<8, 512, 32>, 8, 512, 32, "R=256 512x32");
+		run(part<10, 512, 32>, 10, 512, 32, "R=1024 512x32");
+		run(part<10, 1024, 16>, 10, 1024, 16, "R=1024 1024x16");
+		run(part<12, 512, 40>, 12, 512, 40, "R=4096 512x40");
+		cudaFree(keys);
 	}
 	{
 		cudaFuncSetAttribute(smemcas, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);

@@ -446,7 +446,7 @@ int kcgpu_create_filtered(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t
 			c->n_slots = n;
 			uint32_t bits = 0;
 			while ((1ull << bits) < n) ++bits;
-			/* regions: what the slot word needs, and small enough (16 MiB) to stay in L2 while the
+			/* regions: what the slot word needs, and small enough (64 MiB) to stay in L2 while the
 			 * lists of one region are emptied into it */
 			c->region_bits = need_bits;
 			if (lists && bits > KC_REGION_SLOT_BITS && bits - KC_REGION_SLOT_BITS > c->region_bits) c->region_bits = bits - KC_REGION_SLOT_BITS;

@@ -19,7 +19,13 @@
  *                          In the first two the owner's memory may be a peer's: the same
  *                          instructions then travel over NVLink, which is the all-to-all of
  *                          the partition step fused into the producer.
+ *  kc_scan_tile_kernel     KC_PARTITION as it runs when the regions are few enough (<= 2^12) for a CTA to sort
+ *                          by: the 16 k-mers of a chunk come out of one packed 48-byte window without a byte
+ *                          loop, a CTA sorts its tile of 512 chunks by region in shared memory and every
+ *                          region gets its share as ONE run (one cursor atomic, neighbouring stores) -- 2.3 x
+ *                          the rate of one cursor atomic and one 8-byte store per k-mer
  *  kc_route_kernel         several owners: what arrived in the inbox, filed under its region
+ *  kc_route_tile_kernel    the same through shared-memory tiles (regions <= 2^12)
  *  kc_flush_kernel         worker_for (kc-c4.c:116-128): the region lists into the table, region
  *                          by region so that the slice being filled stays in L2
  *  kc_insert_kernel        the same for lists that came from an exchange
@@ -129,6 +135,8 @@ __device__ __forceinline__ void kc_insert_region(uint64_t *base, uint32_t rslot_
 {
 	if (ctl.mode == KC_INS_CLAIM && bloom_slice && !kc_bloom_seen(bloom_slice, slice_bits, ctl.bloom_hashes, tag)) return;
 	const uint64_t pos = kc_home(tag, rslot_bits);
+	/* (claiming first and looking afterwards -- one L2 operation for a new k-mer instead of two -- is slower: the
+	 * k-mers that are there already then cost two atomics instead of a load and one; profiles/r2_kc_ablation.txt) */
 	kc_insert_from(base, rslot_bits, tag, pos, ld_slot(base + pos), ctl.mode, n_new, n_overflow);
 }
 
@@ -306,9 +314,295 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 	}
 }
 
+/* ---- extraction without a byte loop (the tile kernel) ----
+ * The rolling words of count_seq_buf (kc-c4.c:74-90) for the 16 positions of a chunk are windows of
+ * one packed word: 48 bytes -- the chunk and the 32 before it -- are packed to 2 bits per base once
+ * (codes A0 C1 G2 T3, kc-c4.c:21-38), the forward word of the k-mer that ends at byte e is a
+ * window of the pair-reversed packing, the reverse word a window of the complemented packing, and
+ * "a run of k bases ends here" is a test on a 48-bit mask of the bytes that are not bases. */
+
+/* 16 bytes -> 16 two-bit codes, byte i in bits 2i..2i+1; (b >> 1) & 3 gives A0 C1 T2 G3, the fix-up
+ * x ^ (x >> 1 & 0x5555...) turns that into A0 C1 G2 T3 */
+__device__ __forceinline__ uint32_t kc_pack16(uint4 w)
+{
+	const uint32_t M = 0x00820820u; /* 2^23 + 2^17 + 2^11 + 2^5: gathers the four codes of a word in its top byte */
+	const uint32_t p0 = (w.x & 0x06060606u) * M, p1 = (w.y & 0x06060606u) * M;
+	const uint32_t p2 = (w.z & 0x06060606u) * M, p3 = (w.w & 0x06060606u) * M;
+	const uint32_t x = __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);
+	return x ^ (x >> 1 & 0x55555555u);
+}
+
+/* the order of the 16 two-bit fields reversed */
+__device__ __forceinline__ uint32_t kc_rev16(uint32_t x)
+{
+	const uint32_t y = __brev(x);
+	return (y >> 1 & 0x55555555u) | (y & 0x55555555u) << 1;
+}
+
+/* four bytes -> four bits: bit i set when byte i is none of A C G T U a c g t u (the strict
+ * table, kc-c4.c:21-38).  With c = bits 2..1 of the byte: bit 7 clear, bit 6 set, bit 3 clear,
+ * bit 4 set exactly for T / U (c = 2), bit 0 set unless c = 2; bit 5 is the case. */
+__device__ __forceinline__ uint32_t kc_not_base4(uint32_t w)
+{
+	const uint32_t is2 = (w >> 2) & ~(w >> 1) & 0x01010101u;
+	uint32_t bad = (w ^ 0x40404040u) & 0xC8C8C8C8u;       /* bits 7, 6, 3 */
+	bad |= ((w >> 4) ^ is2) & 0x01010101u;                 /* bit 4 against c == 2 */
+	bad |= ~(w | is2) & 0x01010101u;                       /* bit 0 */
+	bad |= bad >> 3;                                       /* bits 3, 6, 7 -> bits 0, 3, 4 */
+	bad |= bad >> 4;                                       /* bits 4, 7 (and what they took in) -> bits 0, 3 */
+	bad = (bad | bad >> 3) & 0x01010101u;                  /* everything in bit 0 of its byte */
+	return (bad * 0x00204081u) >> 21 & 0xFu;               /* bits 0, 8, 16, 24 -> 21, 22, 23, 24 */
+}
+
+__device__ __forceinline__ uint32_t kc_not_base16(uint4 w)
+{
+	return kc_not_base4(w.x) | kc_not_base4(w.y) << 4 | kc_not_base4(w.z) << 8 | kc_not_base4(w.w) << 12;
+}
+
+/* ---- filing a tile of k-mers under their regions through shared memory ----
+ *
+ * 8-byte stores scattered over thousands of region lists are what the first scan waited for
+ * (~30 G/s, tools/exp/kc_store_exp.cu: scatter8); whole runs leave at ~200 G/s (part).  So a CTA
+ * collects a tile of KC_TILE_THREADS x KC_TILE_N k-mers, ranks them by region with one
+ * shared-memory atomic each, sorts the tile by region in shared memory, reserves ONE run per
+ * region with one atomic on the region's cursor, and writes the sorted tile out: neighbouring
+ * threads write neighbouring entries of the same list.  What a full list cannot take goes
+ * straight to the table, as before. */
+#define KC_TILE_THREADS 512
+#define KC_TILE_N 16
+#ifndef KC_TILE_MIN_CTAS
+#define KC_TILE_MIN_CTAS 2
+#endif
+enum { KC_TILE_ENTRIES = KC_TILE_THREADS * KC_TILE_N };
+
+struct TileSmem {
+	unsigned long long *stage; /* KC_TILE_ENTRIES: the tile, sorted by region                          */
+	unsigned long long *gpos;  /* per region: where entry i of the sorted tile goes, minus i, plus KC_TILE_ENTRIES --
+	                              an index into the lists, or (bit 63 set) a position in the region's list, which
+	                              is about to run full                                                           */
+	uint32_t *cnt;             /* per region: entries in the tile, then (lbase) where its run starts   */
+};
+
+__device__ __forceinline__ TileSmem kc_tile_smem(unsigned long long *smem, uint32_t n_regions)
+{
+	TileSmem s;
+	s.stage = smem;
+	s.gpos = smem + KC_TILE_ENTRIES;
+	s.cnt = reinterpret_cast<uint32_t *>(s.gpos + n_regions);
+	return s;
+}
+
+struct TileDest {
+	uint64_t *table;             /* the owner's table */
+	uint32_t *bloom;             /* its Bloom filter */
+	uint64_t *lists;             /* region lists: `stride` entries apart, room for `cap` entries each */
+	unsigned long long *cursors;
+	uint64_t cap, stride;
+	uint32_t region_bits, rslot_bits;
+};
+
+/* the rare way out of a tile (a list that is full): kept out of line so that the tile kernels do not carry its registers */
+__device__ __noinline__ void kc_insert_slow(uint64_t *table, uint32_t region_bits, uint32_t rslot_bits, uint64_t q, uint32_t *bloom, int mode,
+                                            uint32_t bloom_bits, uint32_t bloom_hashes, uint32_t *n_new, uint32_t *n_overflow)
+{
+	const InsertCtl ctl{mode, bloom_bits, bloom_hashes};
+	kc_insert(table, region_bits, rslot_bits, q, bloom, ctl, *n_new, *n_overflow);
+}
+
+/* s.cnt must be zero (and that visible to the CTA) on entry; all threads of the CTA call. */
+__device__ __forceinline__ void kc_file_tile(const uint64_t (&q)[KC_TILE_N], const uint32_t ok, const TileSmem &s, const TileDest &d,
+                                             const InsertCtl &ctl, uint32_t &n_direct, uint32_t &n_new, uint32_t &n_overflow)
+{
+	__shared__ uint32_t s_warp[KC_TILE_THREADS / 32];
+	__shared__ uint32_t s_total;
+	const uint32_t n_regions = 1u << d.region_bits, rmask = n_regions - 1u;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
+	uint32_t rk[KC_TILE_N / 2];
+#pragma unroll
+	for (int j = 0; j < KC_TILE_N; ++j) {
+		uint32_t r = 0;
+		if (ok >> j & 1u) r = atomicAdd(s.cnt + ((uint32_t)q[j] & rmask), 1u);
+		rk[j >> 1] = (j & 1) ? rk[j >> 1] | r << 16 : r;
+	}
+	__syncthreads();
+	/* exclusive prefix over the regions' counts; every region with entries reserves its run */
+	{
+		const uint32_t per = (n_regions + KC_TILE_THREADS - 1) / KC_TILE_THREADS, lo = tid * per;
+		uint32_t sum = 0;
+		for (uint32_t i = 0; i < per; ++i)
+			if (lo + i < n_regions) sum += s.cnt[lo + i];
+		uint32_t incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t v = __shfl_up_sync(KC_FULL, incl, o);
+			if (lane >= (uint32_t)o) incl += v;
+		}
+		if (lane == 31u) s_warp[tid >> 5] = incl;
+		__syncthreads();
+		if (tid < 32u) {
+			const uint32_t w = tid < KC_TILE_THREADS / 32 ? s_warp[tid] : 0u;
+			uint32_t wi = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t v = __shfl_up_sync(KC_FULL, wi, o);
+				if (lane >= (uint32_t)o) wi += v;
+			}
+			if (tid < KC_TILE_THREADS / 32) s_warp[tid] = wi - w;
+		}
+		__syncthreads();
+		uint32_t at = s_warp[tid >> 5] + incl - sum;
+		for (uint32_t i = 0; i < per; ++i) {
+			const uint32_t r = lo + i;
+			if (r >= n_regions) break;
+			const uint32_t c = s.cnt[r];
+			s.cnt[r] = at;
+			if (c) {
+				const unsigned long long g = atomicAdd(d.cursors + (uint64_t)r * KC_CURSOR_STRIDE, (unsigned long long)c);
+				/* + KC_TILE_ENTRIES - at: never negative, so that bit 63 can flag the run that does not fit */
+				const unsigned long long rel = g + KC_TILE_ENTRIES - at;
+				s.gpos[r] = g + c <= d.cap ? (unsigned long long)r * d.stride + rel : rel | 1ull << 63;
+			}
+			at += c;
+		}
+		if (tid == KC_TILE_THREADS - 1) s_total = at;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int j = 0; j < KC_TILE_N; ++j)
+		if (ok >> j & 1u) s.stage[s.cnt[(uint32_t)q[j] & rmask] + (rk[j >> 1] >> (16 * (j & 1)) & 0xFFFFu)] = q[j];
+	__syncthreads();
+	const uint32_t total = s_total;
+	for (uint32_t i = tid; i < total; i += KC_TILE_THREADS) {
+		const uint64_t w = s.stage[i];
+		const uint32_t r = (uint32_t)w & rmask;
+		const uint64_t at = s.gpos[r] + i;
+		if (!(at >> 63)) {
+			__stcs(reinterpret_cast<unsigned long long *>(d.lists) + (at - KC_TILE_ENTRIES), (unsigned long long)w); /* read once, by the flush: no reason to stay in L2 */
+		} else { /* the run crosses the end of the list: what fits is filed, the rest goes straight to the table */
+			const uint64_t pos = (at & ~(1ull << 63)) - KC_TILE_ENTRIES;
+			if (pos < d.cap) {
+				d.lists[(uint64_t)r * d.stride + pos] = w;
+			} else {
+				++n_direct;
+				kc_insert_slow(d.table, d.region_bits, d.rslot_bits, w, d.bloom, ctl.mode, ctl.bloom_bits, ctl.bloom_hashes, &n_new, &n_overflow);
+			}
+		}
+	}
+}
+
+/* one owner: extract, hash and file, a tile of KC_TILE_THREADS chunks at a time */
+__global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_scan_tile_kernel(const CountArgs a)
+{
+	extern __shared__ unsigned long long kc_dyn_smem[];
+	const TileSmem s = kc_tile_smem(kc_dyn_smem, 1u << a.region_bits);
+	TileDest d;
+	d.table = a.tables[0];
+	d.bloom = kc_bloom_of(d.table, a.n_slots, a.list_cap, a.region_bits);
+	d.lists = kc_lists_of(d.table, a.n_slots);
+	d.cursors = kc_cursors_of(d.table, a.n_slots, a.list_cap, a.region_bits);
+	d.cap = a.list_cap;
+	d.stride = a.list_cap;
+	d.region_bits = a.region_bits;
+	d.rslot_bits = a.rslot_bits;
+	const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
+	const int k = a.k;
+	const uint64_t mask = (1ull << 2 * k) - 1ull;
+	const uint64_t lim = 1ull << (64 - k); /* the k bytes that end at byte e of the window are bases: (inv << (63 - e)) < lim */
+	const int down = 64 - 2 * k;
+	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_direct = 0;
+	for (uint64_t c0 = a.first_chunk + (uint64_t)blockIdx.x * KC_TILE_THREADS; c0 < a.end_chunk; c0 += (uint64_t)gridDim.x * KC_TILE_THREADS) {
+		/* the last tile's entries are on their way out of shared memory; its counts are not needed any more */
+		for (uint32_t r = threadIdx.x; r < (1u << a.region_bits); r += KC_TILE_THREADS) s.cnt[r] = 0;
+		__syncthreads();
+		const uint64_t c = c0 + threadIdx.x;
+		const bool live = c < a.end_chunk;
+		const uint4 sep = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+		const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
+		const uint4 w1 = live && c >= 1 ? __ldg(chunks + c - 1) : sep;
+		const uint4 own = live ? __ldg(chunks + c) : sep;
+		/* byte i of the 48-byte window (i = 32 + j for position j of the chunk): code in bits 2i of P,
+		 * in bits 2 (47 - i) of R; bit i of `inv` set when it is not a base */
+		const uint32_t P0 = kc_pack16(w0), P1 = kc_pack16(w1), P2 = kc_pack16(own);
+		const uint32_t R0 = kc_rev16(P2), R1 = kc_rev16(P1), R2 = kc_rev16(P0);
+		const uint64_t inv = (uint64_t)(kc_not_base16(w0) | kc_not_base16(w1) << 16) | (uint64_t)kc_not_base16(own) << 32;
+		uint64_t q[KC_TILE_N];
+		uint32_t ok = 0;
+#pragma unroll
+		for (int j = 0; j < KC_TILE_N; ++j) {
+			/* forward word: byte 32 + j in bits 0..1, older bases above it (kc-c4.c:83) */
+			const int sf = 2 * (15 - j);
+			const uint64_t fw = ((uint64_t)__funnelshift_r(R1, R2, sf) << 32 | __funnelshift_r(R0, R1, sf)) & mask;
+			/* reverse word: the complement of the 32 bases that end at byte 32 + j, the newest on top (kc-c4.c:84) */
+			const int sr = 2 * (j + 1);
+			const uint64_t y = sr < 32 ? (uint64_t)__funnelshift_r(P1, P2, sr) << 32 | __funnelshift_r(P0, P1, sr) : (uint64_t)P2 << 32 | P1;
+			const uint64_t rv = ~y >> down;
+			q[j] = kc_hash64(fw < rv ? fw : rv, mask);
+			if ((inv << (31 - j)) < lim) ok |= 1u << j;
+		}
+		n_kmers += __popc(ok);
+		kc_file_tile(q, ok, s, d, a.ctl, n_direct, n_new, n_overflow);
+	}
+	for (int o = 16; o; o >>= 1) {
+		n_kmers += __shfl_xor_sync(KC_FULL, n_kmers, o);
+		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
+		n_overflow += __shfl_xor_sync(KC_FULL, n_overflow, o);
+		n_direct += __shfl_xor_sync(KC_FULL, n_direct, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (n_kmers) atomicAdd(a.stats + KC_ST_KMERS, (unsigned long long)n_kmers);
+		if (n_new) atomicAdd(a.stats + KC_ST_NEW, (unsigned long long)n_new);
+		if (n_overflow) atomicAdd(a.stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
+		if (n_direct) atomicAdd(a.stats + KC_ST_DIRECT, (unsigned long long)n_direct);
+	}
+}
+
+/* several owners: the inbox into the region lists, tile by tile (c4x_insert_buf, kc-c4.c:64-72, on the owner's side) */
+__global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_route_tile_kernel(const RouteArgs a)
+{
+	extern __shared__ unsigned long long kc_dyn_smem[];
+	const uint32_t n_regions = 1u << a.region_bits;
+	const TileSmem s = kc_tile_smem(kc_dyn_smem, n_regions);
+	const uint64_t filled = *a.n_ptr;
+	const uint64_t n = filled < a.inbox_cap ? filled : a.inbox_cap;
+	uint32_t n_new = 0, n_overflow = 0, n_direct = 0;
+	TileDest d;
+	d.table = a.table;
+	d.bloom = a.bloom;
+	d.lists = a.lists;
+	d.cursors = a.cursors;
+	d.cap = a.cap;
+	d.stride = a.cap;
+	d.region_bits = a.region_bits;
+	d.rslot_bits = a.rslot_bits;
+	for (uint64_t t0 = (uint64_t)blockIdx.x * KC_TILE_ENTRIES; t0 < n; t0 += (uint64_t)gridDim.x * KC_TILE_ENTRIES) {
+		for (uint32_t r = threadIdx.x; r < n_regions; r += KC_TILE_THREADS) s.cnt[r] = 0;
+		__syncthreads();
+		uint64_t q[KC_TILE_N];
+		uint32_t ok = 0;
+#pragma unroll
+		for (int j = 0; j < KC_TILE_N; ++j) {
+			const uint64_t i = t0 + (uint64_t)j * KC_TILE_THREADS + threadIdx.x;
+			q[j] = 0;
+			if (i < n) q[j] = __ldcs(reinterpret_cast<const unsigned long long *>(a.inbox + i)), ok |= 1u << j;
+		}
+		kc_file_tile(q, ok, s, d, a.ctl, n_direct, n_new, n_overflow);
+		__syncthreads();
+	}
+	for (int o = 16; o; o >>= 1) {
+		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
+		n_overflow += __shfl_xor_sync(KC_FULL, n_overflow, o);
+		n_direct += __shfl_xor_sync(KC_FULL, n_direct, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (n_new) atomicAdd(a.stats + KC_ST_NEW, (unsigned long long)n_new);
+		if (n_overflow) atomicAdd(a.stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
+		if (n_direct) atomicAdd(a.stats + KC_ST_DIRECT, (unsigned long long)n_direct);
+	}
+}
+
 /* The region lists into the table.  CTA b takes tile b % tiles_per_region of region
  * b / tiles_per_region: CTAs are dispatched in order, so the resident ones work on two or
- * three neighbouring regions and their slices (<= 16 MiB each) stay in L2 while they fill. */
+ * three neighbouring regions (one or two when they are as large as they get, 64 MiB) and their slices stay in L2 while they fill. */
 __global__ void __launch_bounds__(KC_THREADS) kc_flush_kernel(uint64_t *base, const uint64_t *lists, const unsigned long long *cursors,
                                                                const uint64_t list_cap, const uint32_t region_bits,
                                                                const uint32_t rslot_bits, const uint32_t tiles_per_region,
@@ -483,7 +777,22 @@ static cudaError_t launch_scan(const CountArgs &a, cudaStream_t stream)
 }
 
 cudaError_t launch_count(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_DIRECT>(a, stream); }
-cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_PARTITION>(a, stream); }
+/* shared memory of the tile kernels: the tile, and 12 bytes per region */
+static size_t tile_smem_bytes(uint32_t region_bits) { return (size_t)KC_TILE_ENTRIES * 8 + ((size_t)12 << region_bits); }
+
+cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream)
+{
+	if (a.region_bits > KC_TILE_REGION_BITS) return launch_scan<KC_PARTITION>(a, stream); /* too many regions for a tile to sort */
+	if (a.end_chunk <= a.first_chunk) return cudaSuccess;
+	/* one tile per CTA as long as the grid allows; the kernel walks on from there */
+	uint64_t blocks = (a.end_chunk - a.first_chunk + KC_TILE_THREADS - 1) / KC_TILE_THREADS;
+	if (blocks > 0x7FFFFFFFull) blocks = 0x7FFFFFFFull;
+	const size_t smem = tile_smem_bytes(a.region_bits);
+	cudaError_t e = cudaFuncSetAttribute(kc_scan_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	kc_scan_tile_kernel<<<(unsigned)blocks, KC_TILE_THREADS, smem, stream>>>(a);
+	return cudaGetLastError();
+}
 cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_EXTRACT>(a, stream); }
 cudaError_t launch_push(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_PUSH>(a, stream); }
 
@@ -504,6 +813,13 @@ cudaError_t launch_flush(uint64_t *base, const uint64_t *lists, const unsigned l
 cudaError_t launch_route(const RouteArgs &a, int n_sm, cudaStream_t stream)
 {
 	if (!a.inbox_cap) return cudaSuccess;
+	if (a.region_bits <= KC_TILE_REGION_BITS) {
+		const size_t smem = tile_smem_bytes(a.region_bits);
+		cudaError_t e = cudaFuncSetAttribute(kc_route_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		kc_route_tile_kernel<<<(unsigned)(n_sm > 0 ? n_sm : 1) * KC_TILE_MIN_CTAS, KC_TILE_THREADS, smem, stream>>>(a);
+		return cudaGetLastError();
+	}
 	kc_route_kernel<<<(unsigned)(n_sm > 0 ? n_sm : 1) * 8, KC_THREADS, 0, stream>>>(a); /* 8 CTAs of 256 threads per SM */
 	return cudaGetLastError();
 }

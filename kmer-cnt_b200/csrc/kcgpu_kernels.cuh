@@ -15,7 +15,7 @@
  * Region lists: like the reference (count_seq_buf files k-mers per partition, worker_for then
  * fills one partition's table at a time, kc-c4.c:64-72,116-128), the scan does not touch the
  * table: it appends q to the list of its region, and a second kernel walks the lists region by
- * region, so that the slice of the table it fills (at most 16 MiB) stays in L2 while it is
+ * region, so that the slice of the table it fills (at most 64 MiB) stays in L2 while it is
  * filled.  Random 8-byte updates of a table far larger than L2 cost ~130 bytes of DRAM traffic
  * each (profiles/r1_kc_scan_v0); through the lists a k-mer costs 16 bytes of streaming plus its
  * share of one pass over the table.
@@ -43,7 +43,14 @@ namespace kcgpu {
 enum { KC_COUNT_BITS = 10, KC_COUNT_MAX = 1023 }; /* kc-c4.c:11-12 */
 enum { KC_MAX_PARTS = 16 };
 enum { KC_MAX_PROBES = 8192 }; /* a region this crowded is reported as overflow, not walked for ever */
-enum { KC_REGION_SLOT_BITS = 21 }; /* slots per region at most: 16 MiB of table, a few of them fit L2 */
+#ifndef KC_REGION_SLOT_BITS_DEFAULT
+#define KC_REGION_SLOT_BITS_DEFAULT 23
+#endif
+/* slots per region at most: 64 MiB of table, which stays in the 126 MB L2 while the region's list is emptied into it
+ * (compare-and-swap into slices of 4 / 16 / 64 / 256 MiB: 47 / 50 / 45 / 27 G per second, tools/exp/kc_store_exp.cu);
+ * the fewer regions, the longer the runs a tile of k-mers leaves in each list */
+enum { KC_REGION_SLOT_BITS = KC_REGION_SLOT_BITS_DEFAULT };
+enum { KC_TILE_REGION_BITS = 12 }; /* the most regions a CTA sorts a tile of k-mers by in shared memory */
 enum { KC_CURSOR_STRIDE = 32 };    /* 64-bit words between two regions' cursors: one 256-byte line each */
 enum { KC_FLUSH_TILE = 2048 };     /* list entries per CTA of the list-insert kernel */
 enum { KC_TAG_BITS = 64 - KC_COUNT_BITS - 1 }; /* the stored key is tag + 1 */

@@ -40,4 +40,5 @@ with kcgpu.Counter(31, 1 << bits, list_slots=kcgpu.NO_LISTS if direct else int(o
     tot = ms + flush_ms
     print(f"{n_reads} reads, 2^{bits} slots{' direct' if direct else ''}: scan {ms:.3f} ms + flush {flush_ms:.3f} ms, "
           f"{st['n_kmers'] / tot / 1e6:.2f} G k-mers/s, {n_reads * 150 / tot / 1e6:.2f} Gbases/s, distinct {st['n_distinct']}, "
-          f"load {st['n_distinct'] / (1 << bits):.3f}, direct {st['n_direct']}, flushes {st['n_flushes']}")
+          f"load {st['n_distinct'] / (1 << bits):.3f}, direct {st['n_direct']}, flushes {st['n_flushes']}, "
+          f"histogram crc {__import__('zlib').crc32(h.tobytes()):08x} ({os.path.basename(os.environ.get('VAFGPU_LIB', 'libvafgpu.so'))})")

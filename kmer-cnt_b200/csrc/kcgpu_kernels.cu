@@ -8,22 +8,18 @@
  *    KC_PARTITION          appends it to the list of its region in its owner's allocation
  *                          (count_seq_buf / c4x_insert_buf, kc-c4.c:64-90); a list that is full
  *                          sends the k-mer straight to the table instead;
- *    KC_PUSH               several owners: appends it to its owner's inbox (the owner's list area
- *                          used as one list).  The CTA counts its k-mers per owner in shared
- *                          memory and reserves one range per owner with one atomic on the
- *                          owner's cursor, so a warp's k-mers for one owner are neighbours and
- *                          leave as whole sectors -- over NVLink when the owner is a peer;
  *    KC_DIRECT             adds it to its owner's table with 64-bit compare-and-swap;
  *    KC_EXTRACT            appends it to one list per owner (warp-aggregated), for an exchange
  *                          by NCCL all-to-all.
- *                          In the first two the owner's memory may be a peer's: the same
- *                          instructions then travel over NVLink, which is the all-to-all of
- *                          the partition step fused into the producer.
  *  kc_scan_tile_kernel     KC_PARTITION as it runs when the regions are few enough (<= 2^12) for a CTA to sort
  *                          by: the 16 k-mers of a chunk come out of one packed 48-byte window without a byte
  *                          loop, a CTA sorts its tile of 512 chunks by region in shared memory and every
  *                          region gets its share as ONE run (one cursor atomic, neighbouring stores) -- 2.3 x
  *                          the rate of one cursor atomic and one 8-byte store per k-mer
+ *  kc_push_tile_kernel     several owners: the same extraction; the tile is sorted by owner and every owner's
+ *                          share appended to its inbox (the owner's list area used as one list) as one run
+ *                          with one atomic on the owner's cursor -- peer memory over NVLink for the other
+ *                          GPUs: the all-to-all of the partition step fused into the producer
  *  kc_route_kernel         several owners: what arrived in the inbox, filed under its region
  *  kc_route_tile_kernel    the same through shared-memory tiles (regions <= 2^12)
  *  kc_flush_kernel         worker_for (kc-c4.c:116-128): the region lists into the table, region
@@ -66,7 +62,7 @@ __device__ __forceinline__ uint64_t cas_slot(uint64_t *p, uint64_t expect, uint6
 	return atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)expect, (unsigned long long)want);
 }
 
-enum { KC_PARTITION = 0, KC_DIRECT = 1, KC_EXTRACT = 2, KC_PUSH = 3 };
+enum { KC_PARTITION = 0, KC_DIRECT = 1, KC_EXTRACT = 2 };
 
 __device__ __forceinline__ uint64_t kc_home(uint64_t tag, uint32_t rslot_bits) { return (tag * 0x9E3779B97F4A7C15ull) >> (64 - rslot_bits); }
 
@@ -170,13 +166,7 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 	const uint64_t c = a.first_chunk + (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x;
 	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_dropped = 0, n_direct = 0;
 	const bool live = c < a.end_chunk;
-	__shared__ uint32_t s_cnt[2][KC_MAX_PARTS];
-	__shared__ unsigned long long s_base[2][KC_MAX_PARTS];
-	if (MODE == KC_PUSH) {
-		if (threadIdx.x < KC_MAX_PARTS) s_cnt[0][threadIdx.x] = 0;
-		__syncthreads();
-	}
-	if (live || MODE == KC_PUSH) { /* KC_PUSH: the whole CTA walks in step (barriers below) */
+	if (live) {
 		const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
 		const uint4 sep = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
 		const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
@@ -200,10 +190,8 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 			rv = rv >> 2 | (3ull - code) << top;
 			run = kc_is_base(b) ? run + 1 : 0;
 		}
-		/* four positions at a time: the push form pays one pair of barriers and one cursor
-		 * atomic per owner for four positions of every thread; for the other forms four
-		 * independent round trips per thread measured the same as one (the list stores are
-		 * throughput-bound, profiles/r1_kc_ablation.txt) */
+		/* four positions at a time (four independent round trips per thread measured the same as
+		 * one: the list stores are throughput-bound, profiles/r1_kc_ablation.txt) */
 #pragma unroll 1
 		for (int g = 0; g < 4; ++g) {
 			uint32_t word = own.x;
@@ -243,33 +231,6 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 					if (at[j] < a.list_cap) {
 						kc_lists_of(base, a.n_slots)[region * a.list_cap + at[j]] = q[j];
 					} else {
-						++n_direct;
-						kc_insert(base, a.region_bits, a.rslot_bits, q[j], kc_bloom_of(base, a.n_slots, a.list_cap, a.region_bits), a.ctl,
-						          n_new, n_overflow);
-					}
-				}
-			} else if (MODE == KC_PUSH) {
-				const int buf = g & 1;
-				uint32_t idx[4];
-#pragma unroll
-				for (int j = 0; j < 4; ++j) idx[j] = ok[j] ? atomicAdd(&s_cnt[buf][owner[j]], 1u) : 0u;
-				__syncthreads();
-				if (threadIdx.x < a.n_parts) {
-					const uint32_t n = s_cnt[buf][threadIdx.x];
-					if (n) s_base[buf][threadIdx.x] =
-						atomicAdd(kc_inbox_cursor(a.tables[threadIdx.x], a.n_slots, a.list_cap, a.region_bits), (unsigned long long)n);
-					s_cnt[buf ^ 1][threadIdx.x] = 0;
-				}
-				__syncthreads();
-				const uint64_t cap = kc_inbox_cap(a.list_cap, a.region_bits);
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					if (!ok[j]) continue;
-					uint64_t *base = a.tables[owner[j]];
-					const uint64_t pos = s_base[buf][owner[j]] + idx[j];
-					if (pos < cap) {
-						kc_lists_of(base, a.n_slots)[pos] = q[j];
-					} else { /* inbox full: straight to the owner's table */
 						++n_direct;
 						kc_insert(base, a.region_bits, a.rslot_bits, q[j], kc_bloom_of(base, a.n_slots, a.list_cap, a.region_bits), a.ctl,
 						          n_new, n_overflow);
@@ -490,6 +451,44 @@ __device__ __forceinline__ void kc_file_tile(const uint64_t (&q)[KC_TILE_N], con
 	}
 }
 
+/* what the extraction needs of k */
+struct Extract {
+	uint64_t mask, lim; /* the k bytes that end at byte e of the window are bases: (inv << (63 - e)) < lim */
+	int down;
+	__device__ __forceinline__ explicit Extract(int k) : mask((1ull << 2 * k) - 1ull), lim(1ull << (64 - k)), down(64 - 2 * k) {}
+};
+
+/* hash64 of the canonical k-mer that ends at each of the 16 bytes of chunk c (kc-c4.c:74-90); returns
+ * the positions where one does (a run of k bases ends there).  A chunk at or behind `end` gives none. */
+__device__ __forceinline__ uint32_t kc_extract16(const uint4 *chunks, const uint64_t c, const uint64_t end, const Extract &x,
+                                                 uint64_t (&h)[KC_TILE_N])
+{
+	const bool live = c < end;
+	const uint4 sep = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+	const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
+	const uint4 w1 = live && c >= 1 ? __ldg(chunks + c - 1) : sep;
+	const uint4 own = live ? __ldg(chunks + c) : sep;
+	/* byte i of the 48-byte window (i = 32 + j for position j of the chunk): code in bits 2i of P,
+	 * in bits 2 (47 - i) of R; bit i of `inv` set when it is not a base */
+	const uint32_t P0 = kc_pack16(w0), P1 = kc_pack16(w1), P2 = kc_pack16(own);
+	const uint32_t R0 = kc_rev16(P2), R1 = kc_rev16(P1), R2 = kc_rev16(P0);
+	const uint64_t inv = (uint64_t)(kc_not_base16(w0) | kc_not_base16(w1) << 16) | (uint64_t)kc_not_base16(own) << 32;
+	uint32_t ok = 0;
+#pragma unroll
+	for (int j = 0; j < KC_TILE_N; ++j) {
+		/* forward word: byte 32 + j in bits 0..1, older bases above it (kc-c4.c:83) */
+		const int sf = 2 * (15 - j);
+		const uint64_t fw = ((uint64_t)__funnelshift_r(R1, R2, sf) << 32 | __funnelshift_r(R0, R1, sf)) & x.mask;
+		/* reverse word: the complement of the 32 bases that end at byte 32 + j, the newest on top (kc-c4.c:84) */
+		const int sr = 2 * (j + 1);
+		const uint64_t y = sr < 32 ? (uint64_t)__funnelshift_r(P1, P2, sr) << 32 | __funnelshift_r(P0, P1, sr) : (uint64_t)P2 << 32 | P1;
+		const uint64_t rv = ~y >> x.down;
+		h[j] = kc_hash64(fw < rv ? fw : rv, x.mask);
+		if ((inv << (31 - j)) < x.lim) ok |= 1u << j;
+	}
+	return ok;
+}
+
 /* one owner: extract, hash and file, a tile of KC_TILE_THREADS chunks at a time */
 __global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_scan_tile_kernel(const CountArgs a)
 {
@@ -505,42 +504,102 @@ __global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_scan_til
 	d.region_bits = a.region_bits;
 	d.rslot_bits = a.rslot_bits;
 	const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
-	const int k = a.k;
-	const uint64_t mask = (1ull << 2 * k) - 1ull;
-	const uint64_t lim = 1ull << (64 - k); /* the k bytes that end at byte e of the window are bases: (inv << (63 - e)) < lim */
-	const int down = 64 - 2 * k;
+	const Extract x(a.k);
 	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_direct = 0;
 	for (uint64_t c0 = a.first_chunk + (uint64_t)blockIdx.x * KC_TILE_THREADS; c0 < a.end_chunk; c0 += (uint64_t)gridDim.x * KC_TILE_THREADS) {
 		/* the last tile's entries are on their way out of shared memory; its counts are not needed any more */
 		for (uint32_t r = threadIdx.x; r < (1u << a.region_bits); r += KC_TILE_THREADS) s.cnt[r] = 0;
 		__syncthreads();
-		const uint64_t c = c0 + threadIdx.x;
-		const bool live = c < a.end_chunk;
-		const uint4 sep = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
-		const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
-		const uint4 w1 = live && c >= 1 ? __ldg(chunks + c - 1) : sep;
-		const uint4 own = live ? __ldg(chunks + c) : sep;
-		/* byte i of the 48-byte window (i = 32 + j for position j of the chunk): code in bits 2i of P,
-		 * in bits 2 (47 - i) of R; bit i of `inv` set when it is not a base */
-		const uint32_t P0 = kc_pack16(w0), P1 = kc_pack16(w1), P2 = kc_pack16(own);
-		const uint32_t R0 = kc_rev16(P2), R1 = kc_rev16(P1), R2 = kc_rev16(P0);
-		const uint64_t inv = (uint64_t)(kc_not_base16(w0) | kc_not_base16(w1) << 16) | (uint64_t)kc_not_base16(own) << 32;
 		uint64_t q[KC_TILE_N];
-		uint32_t ok = 0;
-#pragma unroll
-		for (int j = 0; j < KC_TILE_N; ++j) {
-			/* forward word: byte 32 + j in bits 0..1, older bases above it (kc-c4.c:83) */
-			const int sf = 2 * (15 - j);
-			const uint64_t fw = ((uint64_t)__funnelshift_r(R1, R2, sf) << 32 | __funnelshift_r(R0, R1, sf)) & mask;
-			/* reverse word: the complement of the 32 bases that end at byte 32 + j, the newest on top (kc-c4.c:84) */
-			const int sr = 2 * (j + 1);
-			const uint64_t y = sr < 32 ? (uint64_t)__funnelshift_r(P1, P2, sr) << 32 | __funnelshift_r(P0, P1, sr) : (uint64_t)P2 << 32 | P1;
-			const uint64_t rv = ~y >> down;
-			q[j] = kc_hash64(fw < rv ? fw : rv, mask);
-			if ((inv << (31 - j)) < lim) ok |= 1u << j;
-		}
+		const uint32_t ok = kc_extract16(chunks, c0 + threadIdx.x, a.end_chunk, x, q);
 		n_kmers += __popc(ok);
 		kc_file_tile(q, ok, s, d, a.ctl, n_direct, n_new, n_overflow);
+	}
+	for (int o = 16; o; o >>= 1) {
+		n_kmers += __shfl_xor_sync(KC_FULL, n_kmers, o);
+		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
+		n_overflow += __shfl_xor_sync(KC_FULL, n_overflow, o);
+		n_direct += __shfl_xor_sync(KC_FULL, n_direct, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (n_kmers) atomicAdd(a.stats + KC_ST_KMERS, (unsigned long long)n_kmers);
+		if (n_new) atomicAdd(a.stats + KC_ST_NEW, (unsigned long long)n_new);
+		if (n_overflow) atomicAdd(a.stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
+		if (n_direct) atomicAdd(a.stats + KC_ST_DIRECT, (unsigned long long)n_direct);
+	}
+}
+
+/* several owners: extract, hash, sort the tile by owner in shared memory, and push every owner's share
+ * into its inbox as ONE run (one atomic on the owner's cursor per tile, 8 KB or so of neighbouring
+ * stores) -- into peer memory over NVLink for the other GPUs: the all-to-all of the partition step
+ * inside the producer */
+__global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_push_tile_kernel(const CountArgs a, const int part_shift)
+{
+	extern __shared__ unsigned long long kc_dyn_smem[];
+	unsigned long long *stage = kc_dyn_smem; /* KC_TILE_ENTRIES */
+	__shared__ uint32_t s_cnt[KC_MAX_PARTS], s_lbase[KC_MAX_PARTS + 1];
+	__shared__ unsigned long long s_gbase[KC_MAX_PARTS];
+	const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
+	const Extract x(a.k);
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
+	const uint64_t cap = kc_inbox_cap(a.list_cap, a.region_bits);
+	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_direct = 0;
+	for (uint64_t c0 = a.first_chunk + (uint64_t)blockIdx.x * KC_TILE_THREADS; c0 < a.end_chunk; c0 += (uint64_t)gridDim.x * KC_TILE_THREADS) {
+		if (tid < KC_MAX_PARTS) s_cnt[tid] = 0;
+		__syncthreads(); /* also: the last tile has left shared memory */
+		uint64_t q[KC_TILE_N];
+		const uint32_t ok = kc_extract16(chunks, c0 + tid, a.end_chunk, x, q);
+		n_kmers += __popc(ok);
+		/* rank within the owner's share: the lanes of a warp that have a k-mer for the same owner take
+		 * neighbouring ranks with one shared-memory atomic between them */
+		uint64_t owners = 0; /* 4 bits per position */
+		uint32_t rk[KC_TILE_N / 2];
+#pragma unroll
+		for (int j = 0; j < KC_TILE_N; ++j) {
+			uint32_t owner;
+			kc_owner(q[j], a.n_parts, part_shift, owner, q[j]);
+			const bool mine = ok >> j & 1u;
+			const uint32_t peers = __match_any_sync(KC_FULL, mine ? owner : KC_MAX_PARTS);
+			uint32_t r = 0;
+			if (mine) {
+				const int leader = __ffs(peers) - 1;
+				if ((int)lane == leader) r = atomicAdd(&s_cnt[owner], (uint32_t)__popc(peers));
+				r = __shfl_sync(peers, r, leader) + __popc(peers & ((1u << lane) - 1u));
+			}
+			owners |= (uint64_t)owner << (4 * j);
+			rk[j >> 1] = (j & 1) ? rk[j >> 1] | r << 16 : r;
+		}
+		__syncthreads();
+		if (tid < a.n_parts) {
+			uint32_t at = 0;
+			for (uint32_t o = 0; o < tid; ++o) at += s_cnt[o];
+			s_lbase[tid] = at;
+			const uint32_t n = s_cnt[tid];
+			if (tid == a.n_parts - 1) s_lbase[a.n_parts] = at + n;
+			if (n) s_gbase[tid] = atomicAdd(kc_inbox_cursor(a.tables[tid], a.n_slots, a.list_cap, a.region_bits), (unsigned long long)n);
+		}
+		__syncthreads();
+#pragma unroll
+		for (int j = 0; j < KC_TILE_N; ++j)
+			if (ok >> j & 1u) stage[s_lbase[(uint32_t)(owners >> (4 * j)) & 15u] + (rk[j >> 1] >> (16 * (j & 1)) & 0xFFFFu)] = q[j];
+		__syncthreads();
+		for (uint32_t o = 0; o < a.n_parts; ++o) {
+			const uint32_t lo = s_lbase[o], n = s_lbase[o + 1] - lo;
+			if (!n) continue;
+			uint64_t *base = a.tables[o];
+			uint64_t *inbox = kc_lists_of(base, a.n_slots);
+			const unsigned long long g = s_gbase[o];
+			for (uint32_t t = tid; t < n; t += KC_TILE_THREADS) {
+				const uint64_t w = stage[lo + t];
+				if (g + t < cap) {
+					inbox[g + t] = w;
+				} else { /* inbox full: straight to the owner's table */
+					++n_direct;
+					kc_insert_slow(base, a.region_bits, a.rslot_bits, w, kc_bloom_of(base, a.n_slots, a.list_cap, a.region_bits), a.ctl.mode,
+					               a.ctl.bloom_bits, a.ctl.bloom_hashes, &n_new, &n_overflow);
+				}
+			}
+		}
 	}
 	for (int o = 16; o; o >>= 1) {
 		n_kmers += __shfl_xor_sync(KC_FULL, n_kmers, o);
@@ -794,7 +853,17 @@ cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream)
 	return cudaGetLastError();
 }
 cudaError_t launch_extract(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_EXTRACT>(a, stream); }
-cudaError_t launch_push(const CountArgs &a, cudaStream_t stream) { return launch_scan<KC_PUSH>(a, stream); }
+cudaError_t launch_push(const CountArgs &a, cudaStream_t stream)
+{
+	if (a.end_chunk <= a.first_chunk) return cudaSuccess;
+	uint64_t blocks = (a.end_chunk - a.first_chunk + KC_TILE_THREADS - 1) / KC_TILE_THREADS;
+	if (blocks > 0x7FFFFFFFull) blocks = 0x7FFFFFFFull;
+	const size_t smem = (size_t)KC_TILE_ENTRIES * 8;
+	cudaError_t e = cudaFuncSetAttribute(kc_push_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	kc_push_tile_kernel<<<(unsigned)blocks, KC_TILE_THREADS, smem, stream>>>(a, shift_of(a.n_parts));
+	return cudaGetLastError();
+}
 
 cudaError_t launch_flush(uint64_t *base, const uint64_t *lists, const unsigned long long *cursors, uint64_t list_cap,
                          uint32_t region_bits, uint32_t rslot_bits, uint32_t *bloom, const InsertCtl &ctl,

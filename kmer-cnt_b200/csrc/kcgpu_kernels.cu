@@ -275,51 +275,6 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 	}
 }
 
-/* ---- extraction without a byte loop (the tile kernel) ----
- * The rolling words of count_seq_buf (kc-c4.c:74-90) for the 16 positions of a chunk are windows of
- * one packed word: 48 bytes -- the chunk and the 32 before it -- are packed to 2 bits per base once
- * (codes A0 C1 G2 T3, kc-c4.c:21-38), the forward word of the k-mer that ends at byte e is a
- * window of the pair-reversed packing, the reverse word a window of the complemented packing, and
- * "a run of k bases ends here" is a test on a 48-bit mask of the bytes that are not bases. */
-
-/* 16 bytes -> 16 two-bit codes, byte i in bits 2i..2i+1; (b >> 1) & 3 gives A0 C1 T2 G3, the fix-up
- * x ^ (x >> 1 & 0x5555...) turns that into A0 C1 G2 T3 */
-__device__ __forceinline__ uint32_t kc_pack16(uint4 w)
-{
-	const uint32_t M = 0x00820820u; /* 2^23 + 2^17 + 2^11 + 2^5: gathers the four codes of a word in its top byte */
-	const uint32_t p0 = (w.x & 0x06060606u) * M, p1 = (w.y & 0x06060606u) * M;
-	const uint32_t p2 = (w.z & 0x06060606u) * M, p3 = (w.w & 0x06060606u) * M;
-	const uint32_t x = __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);
-	return x ^ (x >> 1 & 0x55555555u);
-}
-
-/* the order of the 16 two-bit fields reversed */
-__device__ __forceinline__ uint32_t kc_rev16(uint32_t x)
-{
-	const uint32_t y = __brev(x);
-	return (y >> 1 & 0x55555555u) | (y & 0x55555555u) << 1;
-}
-
-/* four bytes -> four bits: bit i set when byte i is none of A C G T U a c g t u (the strict
- * table, kc-c4.c:21-38).  With c = bits 2..1 of the byte: bit 7 clear, bit 6 set, bit 3 clear,
- * bit 4 set exactly for T / U (c = 2), bit 0 set unless c = 2; bit 5 is the case. */
-__device__ __forceinline__ uint32_t kc_not_base4(uint32_t w)
-{
-	const uint32_t is2 = (w >> 2) & ~(w >> 1) & 0x01010101u;
-	uint32_t bad = (w ^ 0x40404040u) & 0xC8C8C8C8u;       /* bits 7, 6, 3 */
-	bad |= ((w >> 4) ^ is2) & 0x01010101u;                 /* bit 4 against c == 2 */
-	bad |= ~(w | is2) & 0x01010101u;                       /* bit 0 */
-	bad |= bad >> 3;                                       /* bits 3, 6, 7 -> bits 0, 3, 4 */
-	bad |= bad >> 4;                                       /* bits 4, 7 (and what they took in) -> bits 0, 3 */
-	bad = (bad | bad >> 3) & 0x01010101u;                  /* everything in bit 0 of its byte */
-	return (bad * 0x00204081u) >> 21 & 0xFu;               /* bits 0, 8, 16, 24 -> 21, 22, 23, 24 */
-}
-
-__device__ __forceinline__ uint32_t kc_not_base16(uint4 w)
-{
-	return kc_not_base4(w.x) | kc_not_base4(w.y) << 4 | kc_not_base4(w.z) << 8 | kc_not_base4(w.w) << 12;
-}
-
 /* ---- filing a tile of k-mers under their regions through shared memory ----
  *
  * 8-byte stores scattered over thousands of region lists are what the first scan waited for
@@ -330,7 +285,6 @@ __device__ __forceinline__ uint32_t kc_not_base16(uint4 w)
  * threads write neighbouring entries of the same list.  What a full list cannot take goes
  * straight to the table, as before. */
 #define KC_TILE_THREADS 512
-#define KC_TILE_N 16
 #ifndef KC_TILE_MIN_CTAS
 #define KC_TILE_MIN_CTAS 2
 #endif
@@ -451,44 +405,6 @@ __device__ __forceinline__ void kc_file_tile(const uint64_t (&q)[KC_TILE_N], con
 	}
 }
 
-/* what the extraction needs of k */
-struct Extract {
-	uint64_t mask, lim; /* the k bytes that end at byte e of the window are bases: (inv << (63 - e)) < lim */
-	int down;
-	__device__ __forceinline__ explicit Extract(int k) : mask((1ull << 2 * k) - 1ull), lim(1ull << (64 - k)), down(64 - 2 * k) {}
-};
-
-/* hash64 of the canonical k-mer that ends at each of the 16 bytes of chunk c (kc-c4.c:74-90); returns
- * the positions where one does (a run of k bases ends there).  A chunk at or behind `end` gives none. */
-__device__ __forceinline__ uint32_t kc_extract16(const uint4 *chunks, const uint64_t c, const uint64_t end, const Extract &x,
-                                                 uint64_t (&h)[KC_TILE_N])
-{
-	const bool live = c < end;
-	const uint4 sep = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
-	const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
-	const uint4 w1 = live && c >= 1 ? __ldg(chunks + c - 1) : sep;
-	const uint4 own = live ? __ldg(chunks + c) : sep;
-	/* byte i of the 48-byte window (i = 32 + j for position j of the chunk): code in bits 2i of P,
-	 * in bits 2 (47 - i) of R; bit i of `inv` set when it is not a base */
-	const uint32_t P0 = kc_pack16(w0), P1 = kc_pack16(w1), P2 = kc_pack16(own);
-	const uint32_t R0 = kc_rev16(P2), R1 = kc_rev16(P1), R2 = kc_rev16(P0);
-	const uint64_t inv = (uint64_t)(kc_not_base16(w0) | kc_not_base16(w1) << 16) | (uint64_t)kc_not_base16(own) << 32;
-	uint32_t ok = 0;
-#pragma unroll
-	for (int j = 0; j < KC_TILE_N; ++j) {
-		/* forward word: byte 32 + j in bits 0..1, older bases above it (kc-c4.c:83) */
-		const int sf = 2 * (15 - j);
-		const uint64_t fw = ((uint64_t)__funnelshift_r(R1, R2, sf) << 32 | __funnelshift_r(R0, R1, sf)) & x.mask;
-		/* reverse word: the complement of the 32 bases that end at byte 32 + j, the newest on top (kc-c4.c:84) */
-		const int sr = 2 * (j + 1);
-		const uint64_t y = sr < 32 ? (uint64_t)__funnelshift_r(P1, P2, sr) << 32 | __funnelshift_r(P0, P1, sr) : (uint64_t)P2 << 32 | P1;
-		const uint64_t rv = ~y >> x.down;
-		h[j] = kc_hash64(fw < rv ? fw : rv, x.mask);
-		if ((inv << (31 - j)) < x.lim) ok |= 1u << j;
-	}
-	return ok;
-}
-
 /* one owner: extract, hash and file, a tile of KC_TILE_THREADS chunks at a time */
 __global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_scan_tile_kernel(const CountArgs a)
 {
@@ -504,7 +420,7 @@ __global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_scan_til
 	d.region_bits = a.region_bits;
 	d.rslot_bits = a.rslot_bits;
 	const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
-	const Extract x(a.k);
+	const Extract x = kc_extract_of(a.k);
 	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_direct = 0;
 	for (uint64_t c0 = a.first_chunk + (uint64_t)blockIdx.x * KC_TILE_THREADS; c0 < a.end_chunk; c0 += (uint64_t)gridDim.x * KC_TILE_THREADS) {
 		/* the last tile's entries are on their way out of shared memory; its counts are not needed any more */
@@ -540,7 +456,7 @@ __global__ void __launch_bounds__(KC_TILE_THREADS, KC_TILE_MIN_CTAS) kc_push_til
 	__shared__ uint32_t s_cnt[KC_MAX_PARTS], s_lbase[KC_MAX_PARTS + 1];
 	__shared__ unsigned long long s_gbase[KC_MAX_PARTS];
 	const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
-	const Extract x(a.k);
+	const Extract x = kc_extract_of(a.k);
 	const uint32_t tid = threadIdx.x, lane = tid & 31u;
 	const uint64_t cap = kc_inbox_cap(a.list_cap, a.region_bits);
 	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_direct = 0;

@@ -90,6 +90,140 @@ KC_HD uint64_t kc_hash64(uint64_t key, uint64_t mask) /* kc-c4.c:40-50 */
 	return key;
 }
 
+/* ---- extraction without a byte loop (the tile kernels; host + device so that tests/cpu_sim can run it) ----
+ * The rolling words of count_seq_buf (kc-c4.c:74-90) for the 16 positions of a chunk are windows of
+ * one packed word: 48 bytes -- the chunk and the 32 before it -- are packed to 2 bits per base once
+ * (codes A0 C1 G2 T3, kc-c4.c:21-38), the forward word of the k-mer that ends at byte e is a
+ * window of the pair-reversed packing, the reverse word a window of the complemented packing, and
+ * "a run of k bases ends here" is a test on a 48-bit mask of the bytes that are not bases. */
+#define KC_TILE_N 16 /* positions per thread: one 16-byte chunk */
+
+KC_HD uint32_t kc_byte_perm(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(a, b, sel);
+#else
+	const uint64_t both = (uint64_t)b << 32 | a;
+	uint32_t r = 0;
+	for (int i = 0; i < 4; ++i) r |= (uint32_t)(both >> (8 * (sel >> (4 * i) & 7)) & 0xFF) << (8 * i);
+	return r;
+#endif
+}
+
+KC_HD uint32_t kc_brev(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return __brev(x);
+#else
+	x = (x >> 1 & 0x55555555u) | (x & 0x55555555u) << 1;
+	x = (x >> 2 & 0x33333333u) | (x & 0x33333333u) << 2;
+	x = (x >> 4 & 0x0F0F0F0Fu) | (x & 0x0F0F0F0Fu) << 4;
+	x = (x >> 8 & 0x00FF00FFu) | (x & 0x00FF00FFu) << 8;
+	return x >> 16 | x << 16;
+#endif
+}
+
+/* bits s .. s+31 of hi:lo, 0 <= s <= 31 */
+KC_HD uint32_t kc_funnel_r(uint32_t lo, uint32_t hi, int s)
+{
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_r(lo, hi, s);
+#else
+	return (uint32_t)(((uint64_t)hi << 32 | lo) >> s);
+#endif
+}
+
+/* 16 bytes -> 16 two-bit codes, byte i in bits 2i..2i+1; (b >> 1) & 3 gives A0 C1 T2 G3, the fix-up
+ * x ^ (x >> 1 & 0x5555...) turns that into A0 C1 G2 T3 */
+KC_HD uint32_t kc_pack16(uint4 w)
+{
+	const uint32_t M = 0x00820820u; /* 2^23 + 2^17 + 2^11 + 2^5: gathers the four codes of a word in its top byte */
+	const uint32_t p0 = (w.x & 0x06060606u) * M, p1 = (w.y & 0x06060606u) * M;
+	const uint32_t p2 = (w.z & 0x06060606u) * M, p3 = (w.w & 0x06060606u) * M;
+	const uint32_t x = kc_byte_perm(kc_byte_perm(p0, p1, 0x0073), kc_byte_perm(p2, p3, 0x0073), 0x5410);
+	return x ^ (x >> 1 & 0x55555555u);
+}
+
+/* the order of the 16 two-bit fields reversed */
+KC_HD uint32_t kc_rev16(uint32_t x)
+{
+	const uint32_t y = kc_brev(x);
+	return (y >> 1 & 0x55555555u) | (y & 0x55555555u) << 1;
+}
+
+/* four bytes -> four bits: bit i set when byte i is none of A C G T U a c g t u (the strict
+ * table, kc-c4.c:21-38).  With c = bits 2..1 of the byte: bit 7 clear, bit 6 set, bit 3 clear,
+ * bit 4 set exactly for T / U (c = 2), bit 0 set unless c = 2; bit 5 is the case. */
+KC_HD uint32_t kc_not_base4(uint32_t w)
+{
+	const uint32_t is2 = (w >> 2) & ~(w >> 1) & 0x01010101u;
+	uint32_t bad = (w ^ 0x40404040u) & 0xC8C8C8C8u;       /* bits 7, 6, 3 */
+	bad |= ((w >> 4) ^ is2) & 0x01010101u;                 /* bit 4 against c == 2 */
+	bad |= ~(w | is2) & 0x01010101u;                       /* bit 0 */
+	bad |= bad >> 3;                                       /* bits 3, 6, 7 -> bits 0, 3, 4 */
+	bad |= bad >> 4;                                       /* bits 4, 7 (and what they took in) -> bits 0, 3 */
+	bad = (bad | bad >> 3) & 0x01010101u;                  /* everything in bit 0 of its byte */
+	return (bad * 0x00204081u) >> 21 & 0xFu;               /* bits 0, 8, 16, 24 -> 21, 22, 23, 24 */
+}
+
+KC_HD uint32_t kc_not_base16(uint4 w)
+{
+	return kc_not_base4(w.x) | kc_not_base4(w.y) << 4 | kc_not_base4(w.z) << 8 | kc_not_base4(w.w) << 12;
+}
+
+/* what the extraction needs of k */
+struct Extract {
+	uint64_t mask, lim; /* the k bytes that end at byte e of the window are bases: (inv << (63 - e)) < lim */
+	int down;
+};
+KC_HD Extract kc_extract_of(int k)
+{
+	Extract x;
+	x.mask = (1ull << 2 * k) - 1ull;
+	x.lim = 1ull << (64 - k);
+	x.down = 64 - 2 * k;
+	return x;
+}
+
+/* hash64 of the canonical k-mer that ends at each of the 16 bytes of chunk c (kc-c4.c:74-90); returns
+ * the positions where one does (a run of k bases ends there).  A chunk at or behind `end` gives none. */
+KC_HD uint32_t kc_extract16(const uint4 *chunks, const uint64_t c, const uint64_t end, const Extract &x, uint64_t (&h)[KC_TILE_N])
+{
+	const bool live = c < end;
+	uint4 sep;
+	sep.x = sep.y = sep.z = sep.w = 0x0A0A0A0Au;
+#if defined(__CUDA_ARCH__)
+	const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
+	const uint4 w1 = live && c >= 1 ? __ldg(chunks + c - 1) : sep;
+	const uint4 own = live ? __ldg(chunks + c) : sep;
+#else
+	const uint4 w0 = live && c >= 2 ? chunks[c - 2] : sep;
+	const uint4 w1 = live && c >= 1 ? chunks[c - 1] : sep;
+	const uint4 own = live ? chunks[c] : sep;
+#endif
+	/* byte i of the 48-byte window (i = 32 + j for position j of the chunk): code in bits 2i of P,
+	 * in bits 2 (47 - i) of R; bit i of `inv` set when it is not a base */
+	const uint32_t P0 = kc_pack16(w0), P1 = kc_pack16(w1), P2 = kc_pack16(own);
+	const uint32_t R0 = kc_rev16(P2), R1 = kc_rev16(P1), R2 = kc_rev16(P0);
+	const uint64_t inv = (uint64_t)(kc_not_base16(w0) | kc_not_base16(w1) << 16) | (uint64_t)kc_not_base16(own) << 32;
+	uint32_t ok = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int j = 0; j < KC_TILE_N; ++j) {
+		/* forward word: byte 32 + j in bits 0..1, older bases above it (kc-c4.c:83) */
+		const int sf = 2 * (15 - j);
+		const uint64_t fw = ((uint64_t)kc_funnel_r(R1, R2, sf) << 32 | kc_funnel_r(R0, R1, sf)) & x.mask;
+		/* reverse word: the complement of the 32 bases that end at byte 32 + j, the newest on top (kc-c4.c:84) */
+		const int sr = 2 * (j + 1);
+		const uint64_t y = sr < 32 ? (uint64_t)kc_funnel_r(P1, P2, sr) << 32 | kc_funnel_r(P0, P1, sr) : (uint64_t)P2 << 32 | P1;
+		const uint64_t rv = ~y >> x.down;
+		h[j] = kc_hash64(fw < rv ? fw : rv, x.mask);
+		if ((inv << (31 - j)) < x.lim) ok |= 1u << j;
+	}
+	return ok;
+}
+
 struct CountArgs {
 	const uint8_t *bytes; /* stream: reads separated by '\n', 16-byte aligned */
 	uint64_t n_bytes;     /* multiple of 16                                    */

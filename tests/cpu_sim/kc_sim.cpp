@@ -5,8 +5,11 @@
  * without a GPU: every k, 1..16 owners, tables from 2^12 to 2^36 slots.
  *
  * sim_kc_count runs a stream through push -> route -> flush with host loops that follow the
- * kernels step by step (kc_scan_kernel<KC_PUSH>, kc_route_kernel, kc_flush_kernel) and
- * returns the 256-bin histogram over all owners.
+ * kernels' bookkeeping step by step (inbox, region lists, table) and returns the 256-bin
+ * histogram over all owners.
+ *
+ * sim_kc_extract runs the tile kernels' own extraction (kc_extract16 of the header: packed
+ * 48-byte windows, no byte loop) over a stream, chunk by chunk as the threads do.
  */
 #include <cstdint>
 #include <cstring>
@@ -72,6 +75,27 @@ void sim_kc_geometry(int k, uint64_t n_slots, uint64_t list_cap, uint32_t region
 }
 
 uint64_t sim_kc_hash64(uint64_t key, int k) { return kc_hash64(key, (1ull << 2 * k) - 1); }
+
+/* hash64 of every canonical k-mer of the stream (n_bytes a multiple of 16), in stream order, as the
+ * threads of kc_scan_tile_kernel / kc_push_tile_kernel compute them; returns how many (out may be
+ * NULL to count only, else it takes up to cap of them) */
+uint64_t sim_kc_extract(int k, const uint8_t *bytes, uint64_t n_bytes, uint64_t *out, uint64_t cap)
+{
+	std::vector<uint4> chunks(n_bytes / 16);
+	memcpy(chunks.data(), bytes, chunks.size() * 16);
+	const Extract x = kc_extract_of(k);
+	uint64_t n = 0;
+	for (uint64_t c = 0; c < chunks.size(); ++c) {
+		uint64_t h[KC_TILE_N];
+		const uint32_t ok = kc_extract16(chunks.data(), c, chunks.size(), x, h);
+		for (int j = 0; j < KC_TILE_N; ++j)
+			if (ok >> j & 1) {
+				if (out && n < cap) out[n] = h[j];
+				++n;
+			}
+	}
+	return n;
+}
 
 /* push -> route -> flush over n_parts owners with tables of 2^table_bits slots and list_cap
  * entries per region; returns the number of k-mers that could not be placed (0 expected) */

@@ -212,6 +212,24 @@ def test_geometry_of_the_allocation(ksim):
                     assert g["lists2_end"] == g["cursors"]
 
 
+@pytest.mark.parametrize("k", [1, 2, 5, 15, 16, 17, 21, 27, 30, 31])
+def test_window_extraction_is_count_seq_buf(kco, ksim, k):
+    """the tile kernels' extraction (kc_extract16 of csrc/kcgpu_kernels.cuh: 48 bytes packed once, the two
+    words of every k-mer read as windows of the packing, validity from a mask of the non-bases) gives, chunk by
+    chunk, exactly the hashed canonical k-mers the oracle's byte loop gives, in order -- over reads of every
+    length and alignment, lower case, N, U, junk bytes and reads shorter than k"""
+    rng = np.random.default_rng(900 + k)
+    reads = util.make_genome_reads(rng, 6000, 300, jitter=149, lower_rate=0.1, n_rate=0.02, junk_rate=0.01, repeat=6)
+    reads += [b"", b"A", b"ACGTU" * 9, b"acgtn" * 20, b"T" * 64, bytes(range(32, 127)) * 2, b"ACGT" * 8 + b"\x00\xff" + b"TTGCA" * 10]
+    stream = util.pack_stream_strict(reads, k)
+    got = ksim.extract(k, stream)
+    want = np.concatenate([kco.hashed_kmers(r, k) for r in reads if len(r) >= k] or [np.zeros(0, np.uint64)])
+    assert got.size == want.size and np.array_equal(got, want)
+    # the stream itself, byte for byte: what the reference's table makes of it
+    want2 = kco.hashed_kmers(stream.tobytes().replace(b"\n", b"N"), k)
+    assert np.array_equal(got, want2)
+
+
 @pytest.mark.parametrize("n_parts", [1, 2, 3, 8, 16])
 def test_push_route_flush_on_the_host(kco, ksim, n_parts):
     """the several-owner form step by step on the host: inbox, region lists, table -- with lists

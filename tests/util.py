@@ -420,7 +420,16 @@ class KcSim:
         lib.sim_kc_count.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.sim_kc_count.restype = C.c_uint64
+        lib.sim_kc_extract.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        lib.sim_kc_extract.restype = C.c_uint64
         self.lib = lib
+
+    def extract(self, k, stream: np.ndarray) -> np.ndarray:
+        """hash64 of every canonical k-mer of a packed stream, by the tile kernels' own extraction"""
+        assert stream.size % 16 == 0
+        out = np.zeros(stream.size, dtype=np.uint64)
+        n = self.lib.sim_kc_extract(k, stream.ctypes.data, stream.size, out.ctypes.data, out.size)
+        return out[:n]
 
     def geometry(self, k, n_slots, list_cap, region_bits):
         out = (C.c_uint64 * 7)()

@@ -594,9 +594,10 @@ __global__ void __launch_bounds__(KC_THREADS) kc_flush_kernel(uint64_t *base, co
 	uint64_t *slice = base + ((uint64_t)region << rslot_bits);
 	uint32_t *const bloom_slice = kc_bloom_slice(bloom, ctl, region_bits, region); /* stays in L2 beside the table slice */
 	uint32_t n_new = 0, n_overflow = 0;
-	/* one entry per thread and step: more entries in flight per thread (four home slots
-	 * requested at once) measured slower -- the compare-and-swap chain, not the first load, is
-	 * what a thread waits for, and the registers halve the resident threads */
+	/* one entry per thread and step: more entries in flight per thread (four home slots requested
+	 * at once in round 1, two in round 2 -- 39 registers, or 32 forced) measured slower every time
+	 * (config 5: 427 / 377 ms against 353): the compare-and-swap chain, not the first load, is
+	 * what a thread waits for */
 	for (uint64_t i = lo + threadIdx.x; i < hi; i += KC_THREADS) {
 		const uint64_t q = __ldcs(reinterpret_cast<const unsigned long long *>(list + i));
 		kc_insert_region(slice, rslot_bits, q >> region_bits, bloom_slice, ctl, ctl.bloom_bits - region_bits, n_new, n_overflow);

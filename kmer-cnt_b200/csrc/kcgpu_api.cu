@@ -463,6 +463,8 @@ int kcgpu_create_filtered(kcgpu_ctx **out, int k, uint64_t table_slots, uint64_t
 				if (c->flush_bytes > ((uint64_t)1 << 40)) c->flush_bytes = (uint64_t)1 << 40;
 			}
 			alloc = kc_alloc_bytes(n, c->list_cap, c->region_bits, c->ctl.bloom_bits);
+			/* (a table with more regions than a tile is sorted by would not fit any device: 2^35 slots) */
+			if (lists && c->region_bits > KC_TILE_REGION_BITS && n > min_slots) continue;
 			if (alloc - kc_bloom_bytes(c->ctl.bloom_bits) + ((uint64_t)256 << 20) <= (uint64_t)free_b || n <= min_slots) break;
 		}
 		cudaError_t me = cudaMalloc(&c->d_table, alloc);

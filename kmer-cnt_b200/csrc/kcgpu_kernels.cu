@@ -1,27 +1,23 @@
 /*
  * kcgpu_kernels.cu -- sm_100a kernels of the full k-mer counting mode (the kc-c4 path).
  *
- *  kc_scan_kernel<MODE>    every thread owns the 16 stream positions of one 128-bit chunk, warms
- *                          its two rolling words up on the 32 bytes before them (k - 1 <= 30),
- *                          and for each position where a k-mer ends (kc-c4.c:80-87) hashes the
- *                          canonical word (kc-c4.c:40-50).  Then
- *    KC_PARTITION          appends it to the list of its region in its owner's allocation
- *                          (count_seq_buf / c4x_insert_buf, kc-c4.c:64-90); a list that is full
- *                          sends the k-mer straight to the table instead;
- *    KC_DIRECT             adds it to its owner's table with 64-bit compare-and-swap;
- *    KC_EXTRACT            appends it to one list per owner (warp-aggregated), for an exchange
- *                          by NCCL all-to-all.
- *  kc_scan_tile_kernel     KC_PARTITION as it runs when the regions are few enough (<= 2^12) for a CTA to sort
- *                          by: the 16 k-mers of a chunk come out of one packed 48-byte window without a byte
- *                          loop, a CTA sorts its tile of 512 chunks by region in shared memory and every
- *                          region gets its share as ONE run (one cursor atomic, neighbouring stores) -- 2.3 x
- *                          the rate of one cursor atomic and one 8-byte store per k-mer
- *  kc_push_tile_kernel     several owners: the same extraction; the tile is sorted by owner and every owner's
- *                          share appended to its inbox (the owner's list area used as one list) as one run
- *                          with one atomic on the owner's cursor -- peer memory over NVLink for the other
- *                          GPUs: the all-to-all of the partition step fused into the producer
- *  kc_route_kernel         several owners: what arrived in the inbox, filed under its region
- *  kc_route_tile_kernel    the same through shared-memory tiles (regions <= 2^12)
+ *  Every scanning thread owns the 16 stream positions of one 128-bit chunk and reads the k-mers that end
+ *  there (kc-c4.c:80-87) out of one packed 48-byte window -- the chunk and the 32 bytes before it, k - 1 <= 30 --
+ *  without a byte loop (kc_extract16, kcgpu_kernels.cuh); canonical word, hash64 (kc-c4.c:40-50).  Then
+ *
+ *  kc_scan_tile_kernel     one owner: a CTA sorts its tile of 512 chunks (up to 8 192 k-mers) by region in shared
+ *                          memory and appends every region's share to its list as ONE run -- one cursor atomic,
+ *                          neighbouring stores (count_seq_buf / c4x_insert_buf, kc-c4.c:64-90); a list that is
+ *                          full sends the k-mer straight to the table instead.  2.5 x the rate of one cursor
+ *                          atomic and one 8-byte store per k-mer (round 1)
+ *  kc_push_tile_kernel     several owners: the tile is sorted by owner and every owner's share appended to its
+ *                          inbox (the owner's list area used as one list) as one run with one atomic on the
+ *                          owner's cursor -- peer memory over NVLink for the other GPUs: the all-to-all of the
+ *                          partition step fused into the producer
+ *  kc_route_tile_kernel    several owners: what arrived in the inbox, filed under its region through the same tiles
+ *  kc_scan_kernel<MODE>    KC_DIRECT: no lists, every k-mer added to its owner's table with 64-bit
+ *                          compare-and-swap; KC_EXTRACT: appended to one list per owner (warp-aggregated), for
+ *                          an exchange by NCCL all-to-all
  *  kc_flush_kernel         worker_for (kc-c4.c:116-128): the region lists into the table, region
  *                          by region so that the slice being filled stays in L2
  *  kc_insert_kernel        the same for lists that came from an exchange
@@ -42,14 +38,6 @@ namespace {
 #define KC_FULL 0xFFFFFFFFu
 #define KC_THREADS 256
 
-/* A C G T U in either case: bit (b & 31) of this word, for bytes 0x40..0x7F */
-#define KC_BASE_BITS ((1u << 1) | (1u << 3) | (1u << 7) | (1u << 20) | (1u << 21))
-
-__device__ __forceinline__ bool kc_is_base(uint32_t b)
-{
-	return ((b & 0xC0u) == 0x40u) && ((KC_BASE_BITS >> (b & 31u)) & 1u);
-}
-
 __device__ __forceinline__ uint64_t ld_slot(const uint64_t *p)
 {
 	/* L2 is the point of coherence for the atomics; a stale value is harmless because the
@@ -62,7 +50,7 @@ __device__ __forceinline__ uint64_t cas_slot(uint64_t *p, uint64_t expect, uint6
 	return atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)expect, (unsigned long long)want);
 }
 
-enum { KC_PARTITION = 0, KC_DIRECT = 1, KC_EXTRACT = 2 };
+enum { KC_DIRECT = 1, KC_EXTRACT = 2 };
 
 __device__ __forceinline__ uint64_t kc_home(uint64_t tag, uint32_t rslot_bits) { return (tag * 0x9E3779B97F4A7C15ull) >> (64 - rslot_bits); }
 
@@ -144,6 +132,15 @@ __device__ __forceinline__ void kc_insert(uint64_t *table, uint32_t region_bits,
 	                 ctl.bloom_bits - region_bits, n_new, n_overflow);
 }
 
+/* kc_insert out of line: the rare way out of a tile (a list that is full), kept away from the tile kernels' registers,
+ * and the insert of the list-less form */
+__device__ __noinline__ void kc_insert_slow(uint64_t *table, uint32_t region_bits, uint32_t rslot_bits, uint64_t q, uint32_t *bloom, int mode,
+                                            uint32_t bloom_bits, uint32_t bloom_hashes, uint32_t *n_new, uint32_t *n_overflow)
+{
+	const InsertCtl ctl{mode, bloom_bits, bloom_hashes};
+	kc_insert(table, region_bits, rslot_bits, q, bloom, ctl, *n_new, *n_overflow);
+}
+
 __device__ __forceinline__ void kc_owner(uint64_t h, uint32_t n_parts, int part_shift, uint32_t &owner, uint64_t &q)
 {
 	if (part_shift >= 0) {
@@ -164,99 +161,29 @@ template <int MODE>
 __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, const int part_shift)
 {
 	const uint64_t c = a.first_chunk + (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x;
-	uint32_t n_kmers = 0, n_new = 0, n_overflow = 0, n_dropped = 0, n_direct = 0;
-	const bool live = c < a.end_chunk;
-	if (live) {
-		const uint4 *chunks = reinterpret_cast<const uint4 *>(a.bytes);
-		const uint4 sep = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
-		const uint4 w0 = live && c >= 2 ? __ldg(chunks + c - 2) : sep;
-		const uint4 w1 = live && c >= 1 ? __ldg(chunks + c - 1) : sep;
-		uint4 own = live ? __ldg(chunks + c) : sep;
-		const int k = a.k;
-		const uint64_t mask = (1ull << 2 * k) - 1ull;
-		const int top = 2 * (k - 1);
-		uint64_t fw = 0, rv = 0;
-		int run = 0;
-		/* warm up: after these 32 bytes run, fw and rv are what a scan from the start of the
-		 * read would hold wherever a k-mer can end inside the chunk (run is capped by the
-		 * window, and k - 1 <= 30 < 32) */
-		const uint32_t warm[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+	uint32_t n_new = 0, n_overflow = 0, n_dropped = 0, n_direct = 0;
+	uint64_t h[KC_TILE_N];
+	const uint32_t ok = kc_extract16(reinterpret_cast<const uint4 *>(a.bytes), c, a.end_chunk, kc_extract_of(a.k), h);
+	uint32_t n_kmers = __popc(ok);
 #pragma unroll
-		for (int i = 0; i < 32; ++i) {
-			const uint32_t b = (warm[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-			uint64_t code = (b >> 1) & 3u;
-			code ^= code >> 1; /* A0 C1 T2 G3 -> A0 C1 G2 T3 (kc-c4.c:21-38) */
-			fw = (fw << 2 | code) & mask;
-			rv = rv >> 2 | (3ull - code) << top;
-			run = kc_is_base(b) ? run + 1 : 0;
-		}
-		/* four positions at a time (four independent round trips per thread measured the same as
-		 * one: the list stores are throughput-bound, profiles/r1_kc_ablation.txt) */
-#pragma unroll 1
-		for (int g = 0; g < 4; ++g) {
-			uint32_t word = own.x;
-			own.x = own.y, own.y = own.z, own.z = own.w;
-			uint64_t q[4];
-			uint32_t owner[4];
-			bool ok[4];
-#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				const uint32_t b = word & 0xFFu;
-				word >>= 8;
-				uint64_t code = (b >> 1) & 3u;
-				code ^= code >> 1;
-				fw = (fw << 2 | code) & mask;
-				rv = rv >> 2 | (3ull - code) << top;
-				run = kc_is_base(b) ? run + 1 : 0;
-				ok[j] = run >= k;
-				kc_owner(kc_hash64(fw < rv ? fw : rv, mask), a.n_parts, part_shift, owner[j], q[j]);
-				n_kmers += ok[j];
-			}
-			if (MODE == KC_PARTITION) {
-				/* file q under its region in the owner's allocation; the cursor runs on past the
-				 * capacity so that the flush knows the list was full, the excess goes to the table */
-				uint64_t at[4];
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const uint64_t region = q[j] & ((1ull << a.region_bits) - 1ull);
-					unsigned long long *cursor =
-					    kc_cursors_of(a.tables[owner[j]], a.n_slots, a.list_cap, a.region_bits) + region * KC_CURSOR_STRIDE;
-					at[j] = ok[j] ? atomicAdd(cursor, 1ull) : 0ull;
-				}
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					if (!ok[j]) continue;
-					uint64_t *base = a.tables[owner[j]];
-					const uint64_t region = q[j] & ((1ull << a.region_bits) - 1ull);
-					if (at[j] < a.list_cap) {
-						kc_lists_of(base, a.n_slots)[region * a.list_cap + at[j]] = q[j];
-					} else {
-						++n_direct;
-						kc_insert(base, a.region_bits, a.rslot_bits, q[j], kc_bloom_of(base, a.n_slots, a.list_cap, a.region_bits), a.ctl,
-						          n_new, n_overflow);
-					}
-				}
-			} else if (MODE == KC_DIRECT) {
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-					if (ok[j])
-						kc_insert(a.tables[owner[j]], a.region_bits, a.rslot_bits, q[j],
-						          kc_bloom_of(a.tables[owner[j]], a.n_slots, a.list_cap, a.region_bits), a.ctl, n_new, n_overflow);
-			} else {
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					if (!ok[j]) continue;
-					/* one atomic per owner and warp: the lanes that have a k-mer for the same owner
-					 * reserve consecutive entries of its list */
-					cg::coalesced_group active = cg::coalesced_threads();
-					cg::coalesced_group same = cg::labeled_partition(active, owner[j]);
-					uint32_t at = 0;
-					if (same.thread_rank() == 0) at = atomicAdd(a.part_counts + owner[j], same.size());
-					at = same.shfl(at, 0) + same.thread_rank();
-					if (at < a.cap_per_part) a.out_keys[(uint64_t)owner[j] * a.cap_per_part + at] = kc_unsplit(q[j], owner[j], a.n_parts, part_shift);
-					else ++n_dropped;
-				}
-			}
+	for (int j = 0; j < KC_TILE_N; ++j) {
+		if (!(ok >> j & 1u)) continue;
+		uint32_t owner;
+		uint64_t q;
+		kc_owner(h[j], a.n_parts, part_shift, owner, q);
+		if (MODE == KC_DIRECT) {
+			uint64_t *base = a.tables[owner];
+			kc_insert(base, a.region_bits, a.rslot_bits, q, kc_bloom_of(base, a.n_slots, a.list_cap, a.region_bits), a.ctl, n_new, n_overflow);
+		} else {
+			/* one atomic per owner and warp: the lanes that have a k-mer for the same owner
+			 * reserve consecutive entries of its list */
+			cg::coalesced_group active = cg::coalesced_threads();
+			cg::coalesced_group same = cg::labeled_partition(active, owner);
+			uint32_t at = 0;
+			if (same.thread_rank() == 0) at = atomicAdd(a.part_counts + owner, same.size());
+			at = same.shfl(at, 0) + same.thread_rank();
+			if (at < a.cap_per_part) a.out_keys[(uint64_t)owner * a.cap_per_part + at] = kc_unsplit(q, owner, a.n_parts, part_shift);
+			else ++n_dropped;
 		}
 	}
 	for (int o = 16; o; o >>= 1) {
@@ -315,14 +242,6 @@ struct TileDest {
 	uint64_t cap, stride;
 	uint32_t region_bits, rslot_bits;
 };
-
-/* the rare way out of a tile (a list that is full): kept out of line so that the tile kernels do not carry its registers */
-__device__ __noinline__ void kc_insert_slow(uint64_t *table, uint32_t region_bits, uint32_t rslot_bits, uint64_t q, uint32_t *bloom, int mode,
-                                            uint32_t bloom_bits, uint32_t bloom_hashes, uint32_t *n_new, uint32_t *n_overflow)
-{
-	const InsertCtl ctl{mode, bloom_bits, bloom_hashes};
-	kc_insert(table, region_bits, rslot_bits, q, bloom, ctl, *n_new, *n_overflow);
-}
 
 /* s.cnt must be zero (and that visible to the CTA) on entry; all threads of the CTA call. */
 __device__ __forceinline__ void kc_file_tile(const uint64_t (&q)[KC_TILE_N], const uint32_t ok, const TileSmem &s, const TileDest &d,
@@ -635,36 +554,6 @@ __global__ void __launch_bounds__(KC_THREADS) kc_insert_kernel(const InsertArgs 
 	}
 }
 
-/* several owners: the inbox into the region lists (c4x_insert_buf, kc-c4.c:64-72, on the owner's side) */
-__global__ void __launch_bounds__(KC_THREADS) kc_route_kernel(const RouteArgs a)
-{
-	uint32_t n_new = 0, n_overflow = 0, n_direct = 0;
-	const uint64_t stride = (uint64_t)gridDim.x * KC_THREADS;
-	const uint64_t filled = *a.n_ptr;
-	const uint64_t n = filled < a.inbox_cap ? filled : a.inbox_cap;
-	for (uint64_t i = (uint64_t)blockIdx.x * KC_THREADS + threadIdx.x; i < n; i += stride) {
-		const uint64_t q = __ldcs(reinterpret_cast<const unsigned long long *>(a.inbox + i));
-		const uint64_t region = q & ((1ull << a.region_bits) - 1ull);
-		const uint64_t at = atomicAdd(a.cursors + region * KC_CURSOR_STRIDE, 1ull);
-		if (at < a.cap) {
-			a.lists[region * a.cap + at] = q;
-		} else {
-			++n_direct;
-			kc_insert(a.table, a.region_bits, a.rslot_bits, q, a.bloom, a.ctl, n_new, n_overflow);
-		}
-	}
-	for (int o = 16; o; o >>= 1) {
-		n_new += __shfl_xor_sync(KC_FULL, n_new, o);
-		n_overflow += __shfl_xor_sync(KC_FULL, n_overflow, o);
-		n_direct += __shfl_xor_sync(KC_FULL, n_direct, o);
-	}
-	if ((threadIdx.x & 31) == 0) {
-		if (n_new) atomicAdd(a.stats + KC_ST_NEW, (unsigned long long)n_new);
-		if (n_overflow) atomicAdd(a.stats + KC_ST_OVERFLOW, (unsigned long long)n_overflow);
-		if (n_direct) atomicAdd(a.stats + KC_ST_DIRECT, (unsigned long long)n_direct);
-	}
-}
-
 /* kc-c4.c:186-197: bin min(count, 255) of every used slot.  One private histogram per warp in
  * shared memory; lanes that hit the same bin are merged first (most used slots of a read set
  * share a handful of counts). */
@@ -758,7 +647,7 @@ static size_t tile_smem_bytes(uint32_t region_bits) { return (size_t)KC_TILE_ENT
 
 cudaError_t launch_partition(const CountArgs &a, cudaStream_t stream)
 {
-	if (a.region_bits > KC_TILE_REGION_BITS) return launch_scan<KC_PARTITION>(a, stream); /* too many regions for a tile to sort */
+	if (a.region_bits > KC_TILE_REGION_BITS) return cudaErrorInvalidValue; /* kcgpu_create never makes that many regions */
 	if (a.end_chunk <= a.first_chunk) return cudaSuccess;
 	/* one tile per CTA as long as the grid allows; the kernel walks on from there */
 	uint64_t blocks = (a.end_chunk - a.first_chunk + KC_TILE_THREADS - 1) / KC_TILE_THREADS;
@@ -799,14 +688,11 @@ cudaError_t launch_flush(uint64_t *base, const uint64_t *lists, const unsigned l
 cudaError_t launch_route(const RouteArgs &a, int n_sm, cudaStream_t stream)
 {
 	if (!a.inbox_cap) return cudaSuccess;
-	if (a.region_bits <= KC_TILE_REGION_BITS) {
-		const size_t smem = tile_smem_bytes(a.region_bits);
-		cudaError_t e = cudaFuncSetAttribute(kc_route_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return e;
-		kc_route_tile_kernel<<<(unsigned)(n_sm > 0 ? n_sm : 1) * KC_TILE_MIN_CTAS, KC_TILE_THREADS, smem, stream>>>(a);
-		return cudaGetLastError();
-	}
-	kc_route_kernel<<<(unsigned)(n_sm > 0 ? n_sm : 1) * 8, KC_THREADS, 0, stream>>>(a); /* 8 CTAs of 256 threads per SM */
+	if (a.region_bits > KC_TILE_REGION_BITS) return cudaErrorInvalidValue;
+	const size_t smem = tile_smem_bytes(a.region_bits);
+	cudaError_t e = cudaFuncSetAttribute(kc_route_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	kc_route_tile_kernel<<<(unsigned)(n_sm > 0 ? n_sm : 1) * KC_TILE_MIN_CTAS, KC_TILE_THREADS, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 

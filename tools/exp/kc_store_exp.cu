@@ -108,6 +108,47 @@ __global__ void l2red(unsigned long long *table, uint64_t slice_slots, uint32_t 
 	if (acc == 12345) *sink = acc;
 }
 
+// tags and counts in two arrays: a k-mer that has its entry costs one load of the tag and one 32-bit reduction on the
+// count (no return value, nothing to wait for); a new one a compare-and-swap on the tag as well.  `dup` of every 8 keys
+// repeat an earlier key of the thread's slice (entry exists), the rest are new.
+__global__ void l2split(unsigned long long *tags, uint32_t *counts, uint64_t slice_slots, uint32_t n_slices, uint32_t ctas_per_slice, uint64_t per_cta,
+                        uint32_t dup)
+{
+	const uint32_t s = blockIdx.x / ctas_per_slice;
+	if (s >= n_slices) return;
+	unsigned long long *slice = tags + (uint64_t)s * slice_slots;
+	uint32_t *cnt = counts + (uint64_t)s * slice_slots;
+	const uint64_t base = (uint64_t)blockIdx.x * per_cta, mask = slice_slots - 1;
+	for (uint64_t i = threadIdx.x; i < per_cta; i += blockDim.x) {
+		const uint64_t n = base + i;
+		const uint64_t key = (n & 7) < dup ? mix(base + (i & 1023)) : mix(n); /* a repeat of one of the CTA's first keys, or a new key */
+		const uint64_t tag = key >> 24 | 1;
+		uint64_t pos = (tag * 0x9E3779B97F4A7C15ull) >> 20 & mask;
+		for (int t = 0; t < 64; ++t, pos = (pos + 1) & mask) {
+			unsigned long long v = slice[pos];
+			if (v == 0) v = atomicCAS(slice + pos, 0ull, tag), v = v ? v : tag;
+			if (v == tag) {
+				atomicAdd(cnt + pos, 1u); /* RED */
+				break;
+			}
+		}
+	}
+}
+
+// the same key stream into the one-word slots the library uses (tag << 10 | count, compare-and-swap loop)
+__global__ void l2word(unsigned long long *table, uint64_t slice_slots, uint32_t n_slices, uint32_t ctas_per_slice, uint64_t per_cta, uint32_t dup)
+{
+	const uint32_t s = blockIdx.x / ctas_per_slice;
+	if (s >= n_slices) return;
+	unsigned long long *slice = table + (uint64_t)s * slice_slots;
+	const uint64_t base = (uint64_t)blockIdx.x * per_cta;
+	for (uint64_t i = threadIdx.x; i < per_cta; i += blockDim.x) {
+		const uint64_t n = base + i;
+		const uint64_t key = (n & 7) < dup ? mix(base + (i & 1023)) : mix(n);
+		insert(slice, slice_slots - 1, key >> 24 | 1);
+	}
+}
+
 // T threads, IPT keys per thread; lists[r * cap + ...], cursors 256 bytes apart as in the library
 template <int RB, int T, int IPT>
 __global__ void __launch_bounds__(T, 1) part(const uint64_t *__restrict__ in, uint64_t n, uint64_t *lists, unsigned long long *cur, uint64_t cap, int shift)
@@ -253,6 +294,38 @@ int main(int argc, char **argv)
 		float ms = timed([&] { l2red<<<n_slices * ctas_per_slice, block>>>(table, slice_slots, n_slices, ctas_per_slice, per_cta, sink); });
 		printf("l2red      slice %3u MiB  %7.2f ms  %6.1f G updates/s\n", mib, ms, total / ms / 1e6);
 		cudaFree(table);
+	}
+	for (uint32_t dup : {0u, 5u, 7u}) { /* 0, 5 or 7 of 8 keys have their entry already (config 5: 5 of 8) */
+		const uint32_t mib = 64;
+		const uint64_t slice_slots = (uint64_t)mib << 17;
+		const uint32_t n_slices = 32, ctas_per_slice = 1024;
+		const uint64_t per_cta = slice_slots / 4 / ctas_per_slice * 4; /* as many keys as a quarter-full slice of new keys would take, times 4 */
+		unsigned long long *table;
+		uint32_t *counts;
+		cudaMalloc(&table, slice_slots * n_slices * 8);
+		cudaMalloc(&counts, slice_slots * n_slices * 4);
+		const uint64_t total = per_cta * ctas_per_slice * n_slices;
+		cudaMemset(table, 0, slice_slots * n_slices * 8);
+		cudaDeviceSynchronize();
+		cudaEvent_t a, b;
+		cudaEventCreate(&a), cudaEventCreate(&b);
+		float ms = 0;
+		cudaEventRecord(a);
+		l2word<<<n_slices * ctas_per_slice, block>>>(table, slice_slots, n_slices, ctas_per_slice, per_cta, dup);
+		cudaEventRecord(b);
+		cudaEventSynchronize(b);
+		cudaEventElapsedTime(&ms, a, b);
+		printf("l2word     %u of 8 keys present, slice %u MiB  %7.2f ms  %6.1f G inserts/s\n", dup, mib, ms, total / ms / 1e6);
+		cudaMemset(table, 0, slice_slots * n_slices * 8);
+		cudaMemset(counts, 0, slice_slots * n_slices * 4);
+		cudaDeviceSynchronize();
+		cudaEventRecord(a);
+		l2split<<<n_slices * ctas_per_slice, block>>>(table, counts, slice_slots, n_slices, ctas_per_slice, per_cta, dup);
+		cudaEventRecord(b);
+		cudaEventSynchronize(b);
+		cudaEventElapsedTime(&ms, a, b);
+		printf("l2split    %u of 8 keys present, slice %u MiB  %7.2f ms  %6.1f G inserts/s  (tags + 32-bit counts apart)\n", dup, mib, ms, total / ms / 1e6);
+		cudaFree(table), cudaFree(counts);
 	}
 	{
 		uint64_t *keys, *lists;

@@ -201,7 +201,7 @@ def test_geometry_of_the_allocation(ksim):
         need = ksim.geometry(k, 4096, 64, 0)["need_bits"]
         assert 2 * k - need <= 53 and (need == 0 or 2 * k - need == 53)
         for table_bits in (12, 21, 27, 33, 36):
-            for rb in sorted({need, min(max(need, table_bits - 21), 20), 12} & set(range(need, table_bits - 3))):
+            for rb in sorted({need, min(max(need, table_bits - 23), 20), 12} & set(range(need, table_bits - 3))):
                 for cap in (64, 96, 1 << 20):
                     g = ksim.geometry(k, 1 << table_bits, cap, rb)
                     assert g["lists"] == 8 << table_bits

@@ -31,6 +31,9 @@
 #include "fastx.h"
 #include "ingest.h"
 
+/* staging blocks of 4 MiB: the readers set the pace, and page-locking one block per reader is start-up time */
+#define STAGING_BYTES ((size_t)4 << 20)
+
 static double now(void)
 {
 	struct timeval tv;
@@ -166,7 +169,7 @@ int main(int argc, char *argv[])
 		uint64_t hist[256], part[256], overflow = 0;
 		kcgpu_stats st;
 		for (i = 0; i < n_dev; ++i)
-			if (kcgpu_create(&ctx[i], k, slots, direct ? KCGPU_NO_LISTS : 0, 0, i) != VAFGPU_OK) {
+			if (kcgpu_create(&ctx[i], k, slots, direct ? KCGPU_NO_LISTS : 0, STAGING_BYTES, i) != VAFGPU_OK) {
 				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
 				return 1;
 			}

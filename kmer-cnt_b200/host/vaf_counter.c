@@ -189,7 +189,11 @@ int main(int argc, char *argv[])
 	/* staging blocks per device: one for every reader to fill plus two in flight */
 	int n_buffers = n_thread > 1 ? n_thread + 2 : 3;
 	if (n_buffers > 66) n_buffers = 66;
-	if (vafgpu_create(&ctx, k, keys, vals, n_keys, (uint32_t)db->n, block_size > 0 ? (size_t)block_size : 0, n_buffers, 0, flags) != VAFGPU_OK) {
+	/* -b bounds a staging block from above; more than 2 MiB buys nothing here (the readers, not the copies, set the
+	 * pace) and page-locking the blocks is start-up time: 18 blocks of 16 / 4 / 2 MiB take 280 / 110 / 30 ms */
+	size_t staging = block_size > 0 ? (size_t)block_size : 0;
+	if (staging == 0 || staging > ((size_t)2 << 20)) staging = (size_t)2 << 20;
+	if (vafgpu_create(&ctx, k, keys, vals, n_keys, (uint32_t)db->n, staging, n_buffers, 0, flags) != VAFGPU_OK) {
 		fprintf(stderr, "Error: failed to create k-mer map: %s\n", vafgpu_strerror(NULL));
 		return 1;
 	}
@@ -276,7 +280,9 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "  Threads:               %d readers\n", n_thread);
 		fprintf(stderr, "==============================\n");
 	}
+	t0 = now();
 	vafgpu_destroy(ctx);
+	if (getenv("VAFGPU_TIMING")) fprintf(stderr, "[vafgpu] %-28s %8.1f ms\n", "destroy", (now() - t0) * 1e3);
 	free(counts);
 	free(per_file);
 	free(keys);

@@ -40,6 +40,9 @@ typedef struct {
 	int n_dev, chunk;
 } engine_t;
 
+/* staging blocks of 4 MiB: the readers set the pace, and page-locking one block per reader is start-up time */
+#define STAGING_BYTES ((size_t)4 << 20)
+
 static double now(void)
 {
 	struct timeval tv;
@@ -187,7 +190,7 @@ int main(int argc, char *argv[])
 		uint64_t hist[1024], part[1024], overflow = 0, tot = 0;
 		kcgpu_stats st;
 		for (i = 0; i < n_dev; ++i)
-			if (kcgpu_create_filtered(&ctx[i], k, slots, 0, 0, i, filter ? (bf_shift > 40 ? 40 : bf_shift) : 0, bf_n_hash > 64 ? 64 : bf_n_hash) != VAFGPU_OK) {
+			if (kcgpu_create_filtered(&ctx[i], k, slots, 0, STAGING_BYTES, i, filter ? (bf_shift > 40 ? 40 : bf_shift) : 0, bf_n_hash > 64 ? 64 : bf_n_hash) != VAFGPU_OK) {
 				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
 				return 1;
 			}

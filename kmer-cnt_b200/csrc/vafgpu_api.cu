@@ -295,16 +295,6 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 		if (keys[i] > kmask) return fail(nullptr, VAFGPU_EINVAL, "key %u does not fit 2k bits", i);
 		if (vals[i] >= 2ull * n_patterns) return fail(nullptr, VAFGPU_EINVAL, "value %u names pattern %u of %u", i, vals[i] >> 1, n_patterns);
 	}
-	int visible = 0;
-	cudaError_t ce = cudaGetDeviceCount(&visible);
-	if (ce != cudaSuccess || visible < 1)
-		return fail(nullptr, VAFGPU_ENOGPU, "no CUDA device: %s", ce == cudaSuccess ? "count is 0" : cudaGetErrorString(ce));
-	if (n_devices <= 0 || n_devices > visible) n_devices = visible;
-	if (block_bytes == 0) block_bytes = (size_t)16 << 20;
-	if (block_bytes < 4096) block_bytes = 4096;
-	if (block_bytes > ((size_t)1 << 34)) return fail(nullptr, VAFGPU_EINVAL, "block_bytes too large");
-	if (n_buffers <= 0) n_buffers = 3;
-
 	const bool timing = getenv("VAFGPU_TIMING") != nullptr; /* start-up breakdown on stderr */
 	auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	double tt = tnow();
@@ -315,6 +305,17 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			tt = t;
 		}
 	};
+	int visible = 0;
+	cudaError_t ce = cudaGetDeviceCount(&visible); /* the first runtime call: cuInit */
+	lap("CUDA init (device count)");
+	if (ce != cudaSuccess || visible < 1)
+		return fail(nullptr, VAFGPU_ENOGPU, "no CUDA device: %s", ce == cudaSuccess ? "count is 0" : cudaGetErrorString(ce));
+	if (n_devices <= 0 || n_devices > visible) n_devices = visible;
+	if (block_bytes == 0) block_bytes = (size_t)16 << 20;
+	if (block_bytes < 4096) block_bytes = 4096;
+	if (block_bytes > ((size_t)1 << 34)) return fail(nullptr, VAFGPU_EINVAL, "block_bytes too large");
+	if (n_buffers <= 0) n_buffers = 3;
+
 	vafgpu_ctx *c = new (std::nothrow) vafgpu_ctx;
 	if (!c) return fail(nullptr, VAFGPU_ENOMEM, "out of memory");
 	c->k = k;
@@ -325,7 +326,6 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 
 	RecipeTable rt;
 	AnchorTables at;
-	lap("device count");
 	build_recipe_table(k, keys, vals, n_entries, n_patterns, rt);
 	build_anchor_tables(k, keys, vals, n_entries, at);
 	lap("host tables");

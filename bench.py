@@ -778,7 +778,9 @@ def main():
                 ctx_ms = sum(float(x) for x in re.findall(rb"\[vafgpu\] (?:CUDA init \(device count\)|context|module load \+ policy kernel)\s+([0-9.]+) ms", r.stderr))
                 ours["t%d" % th] = {"whole_process_s": wall, "whole_process_gbases_s": cli_bases / wall / 1e9,
                                     "counting_phase_gbases_s": cli_bases / max(float(m.group(1)), 1e-9) / 1e9 if m else None,
-                                    "cuda_init_context_module_s": ctx_ms / 1e3}
+                                    "cuda_init_context_module_s": ctx_ms / 1e3,
+                                    "phases_ms": {a.decode().strip(): float(b) for a, b in re.findall(rb"\[vafgpu\] (.+?)\s+([0-9.]+) ms", r.stderr)},
+                                    "main_total_s": (lambda t: float(t.group(1)) if t else None)(re.search(rb"Total runtime:\s+([0-9.]+) sec", r.stderr))}
             best_th = min(ours, key=lambda x: ours[x]["whole_process_s"])
             e2e_cli = {"workload": "%d reads x %d bp of this workload as one plain FASTQ file in %s (%.2f GB)"
                                    % (n_c, READ_LEN, os.path.dirname(big), os.path.getsize(big) / 1e9),

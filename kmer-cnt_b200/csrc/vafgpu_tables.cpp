@@ -90,8 +90,8 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	struct Item { uint64_t okey; uint32_t val, off, anchor; };
 	std::vector<Item> items;
 	std::unordered_set<uint64_t> seen;
-	std::unordered_set<uint32_t> canon, plain; /* filter keys with / without strand folding */
 	items.reserve((size_t)n * 2 * S);
+	seen.reserve((size_t)n * 2);
 	for (uint32_t i = 0; i < n; ++i) {
 		if (!seen.insert(keys[i]).second) continue; /* first insert wins */
 		uint64_t f = ref_to_stream(keys[i], k), r = stream_revcomp(f, k);
@@ -101,11 +101,26 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 			for (int t = 0; t < S; ++t) { /* anchor = bases [k-t-L, k-t) of the oriented k-mer */
 				uint32_t a = (uint32_t)(ok >> 2 * (k - t - L)) & amask;
 				items.push_back({ok, vals[i], (uint32_t)t, a});
-				canon.insert(vg_filter_key(a, L, 1));
-				plain.insert(a);
 			}
 		}
 	}
+	/* the distinct filter keys, without and with strand folding (sorted vectors: hash sets of 10^6
+	 * keys cost most of a second here, which is start-up time of every run of the command line) */
+	auto distinct = [&](int fold) {
+		std::vector<uint32_t> v(items.size());
+		for (size_t i = 0; i < items.size(); ++i) v[i] = fold ? vg_filter_key(items[i].anchor, L, 1) : items[i].anchor;
+		std::vector<uint32_t> tmp(v.size()); /* least-significant-digit radix sort, four passes of eight bits */
+		for (int shift = 0; shift < 32; shift += 8) {
+			size_t count[257] = {0};
+			for (uint32_t x : v) ++count[(x >> shift & 255u) + 1];
+			for (int d = 0; d < 256; ++d) count[d + 1] += count[d];
+			for (uint32_t x : v) tmp[count[x >> shift & 255u]++] = x;
+			v.swap(tmp);
+		}
+		v.erase(std::unique(v.begin(), v.end()), v.end());
+		return v;
+	};
+	const std::vector<uint32_t> plain = distinct(0);
 	out.n_entries = (uint32_t)items.size();
 
 	/* Filter: two bits per key in one 32-bit word.  A panel small enough to get >= 24 bits
@@ -117,7 +132,8 @@ void build_anchor_tables(int k, const uint64_t *keys, const uint32_t *vals, uint
 	out.defer = out.canon && VG_DEFER_OK(S);
 	out.threads = VG_THREADS(S, out.defer);
 	const uint32_t budget = VG_FILTER_BUDGET_WORDS(S, out.defer);
-	const std::unordered_set<uint32_t> &fkeys = out.canon ? canon : plain;
+	const std::vector<uint32_t> folded = out.canon ? distinct(1) : std::vector<uint32_t>();
+	const std::vector<uint32_t> &fkeys = out.canon ? folded : plain;
 	out.n_filter_keys = (uint32_t)fkeys.size();
 	uint64_t want = (uint64_t)out.n_filter_keys * 2;
 	uint32_t nw = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, VG_MIN_FILTER_WORDS), budget);

@@ -57,6 +57,8 @@ struct Device {
 	unsigned long long *d_stats = nullptr;
 	cudaStream_t main_stream = nullptr;
 	std::vector<Block> blocks;
+	char *h_slab = nullptr;    /* the blocks' page-locked host memory and their device copies: one allocation */
+	uint8_t *d_slab = nullptr; /* each (a driver call per block is start-up time of every run)                */
 };
 
 } // namespace
@@ -241,13 +243,13 @@ void destroy_device(Device &d)
 	cudaSetDevice(d.ordinal);
 	for (Block &b : d.blocks) {
 		if (b.stream) cudaStreamSynchronize(b.stream);
-		if (b.h) cudaFreeHost(b.h);
-		if (b.d) cudaFree(b.d);
 		if (b.e0) cudaEventDestroy(b.e0);
 		if (b.e1) cudaEventDestroy(b.e1);
 		if (b.e2) cudaEventDestroy(b.e2);
 		if (b.stream) cudaStreamDestroy(b.stream);
 	}
+	if (d.h_slab) cudaFreeHost(d.h_slab);
+	if (d.d_slab) cudaFree(d.d_slab);
 	if (d.main_stream) cudaStreamDestroy(d.main_stream);
 	if (d.attached) cudaIpcCloseMemHandle(d.attached);
 	cudaFree(d.d_filter);
@@ -377,9 +379,14 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			d.counts_to = d.d_counts;
 			lap("tables to device");
 			d.blocks.resize(n_buffers);
+			const size_t pitch = (block_bytes + 64 + 255) & ~(size_t)255;
+			CU(c, cudaHostAlloc(&d.h_slab, pitch * (size_t)n_buffers, cudaHostAllocPortable));
+			CU(c, cudaMalloc(&d.d_slab, pitch * (size_t)n_buffers));
+			size_t at = 0;
 			for (Block &b : d.blocks) {
-				CU(c, cudaHostAlloc(&b.h, block_bytes + 64, cudaHostAllocPortable));
-				CU(c, cudaMalloc(&b.d, block_bytes + 64));
+				b.h = d.h_slab + at;
+				b.d = d.d_slab + at;
+				at += pitch;
 				CU(c, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
 				CU(c, cudaEventCreate(&b.e0));
 				CU(c, cudaEventCreate(&b.e1));

@@ -721,6 +721,7 @@ def main():
     # ---- CPU baseline + byte parity of the .vaf on a sample (rank 0 only)
     cpu = None
     e2e_cli = None
+    cli_job = None
     if rank == 0 and not args.no_cpu_baseline:
         exe, kind = reference_binary()
         n_s = min(args.cpu_sample_reads, args.reads)
@@ -753,46 +754,18 @@ def main():
         except Exception as exc:  # the oracle is a checker; its absence is reported, not hidden
             parity["oracle_counts_on_sample"] = "not run: %r" % (exc,)
         del reads
-        # ---- whole process against whole process on one FASTQ file (N = 1): this repository's
-        #      vaf-counter and the reference's, same file in /dev/shm, same patterns, -t as given
+        # ---- whole process against whole process on one FASTQ file (N = 1): the file is written now, while the
+        #      stream is at hand; the two command lines run at the very end, when this process has let go of
+        #      its GPU and page-locked memory (a second process with 100 GB on the same GPU slows every driver
+        #      call of the command line: context 0.2 -> 1.6 s, teardown 8 ms -> 1 s)
+        cli_job = None
         if world == 1 and args.e2e_cli_reads > 0:
             n_c = min(args.e2e_cli_reads, args.reads)
             big = os.path.join(tmp, "e2e_cli.fq")
             t0 = time.perf_counter()
             write_fastq_fixed(big, stream[:n_c * rec].cpu().numpy(), n_c)
             log(f"e2e_cli: wrote {os.path.getsize(big) / 1e9:.2f} GB FASTQ in {time.perf_counter() - t0:.1f} s")
-            cli_bases = n_c * READ_LEN
-            t_ref = time_reference(exe, pattern_file, big, os.path.join(tmp, "big_ref.vaf"), threads)
-            cli_exe = os.path.join(PKG, "vaf-counter")
-            ours = {}
-            for th in sorted({1, ncpu}):
-                out_vaf = os.path.join(tmp, "big_cli%d.vaf" % th)
-                t0 = time.perf_counter()
-                r = subprocess.run([cli_exe, "-k", str(K), "-t", str(th), "-v", "-p", pattern_file, "-o", out_vaf, big],
-                                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
-                                   env=dict(os.environ, VAFGPU_TIMING="1"))  # start-up breakdown on stderr
-                wall = time.perf_counter() - t0
-                assert open(out_vaf, "rb").read() == open(os.path.join(tmp, "big_ref.vaf"), "rb").read(), \
-                    "CLI output differs from the reference's at -t %d" % th
-                m = re.search(rb"K-mer counting:\s+([0-9.]+) sec", r.stderr)
-                ctx_ms = sum(float(x) for x in re.findall(rb"\[vafgpu\] (?:CUDA init \(device count\)|context|module load \+ policy kernel)\s+([0-9.]+) ms", r.stderr))
-                ours["t%d" % th] = {"whole_process_s": wall, "whole_process_gbases_s": cli_bases / wall / 1e9,
-                                    "counting_phase_gbases_s": cli_bases / max(float(m.group(1)), 1e-9) / 1e9 if m else None,
-                                    "cuda_init_context_module_s": ctx_ms / 1e3,
-                                    "phases_ms": {a.decode().strip(): float(b) for a, b in re.findall(rb"\[vafgpu\] (.+?)\s+([0-9.]+) ms", r.stderr)},
-                                    "main_total_s": (lambda t: float(t.group(1)) if t else None)(re.search(rb"Total runtime:\s+([0-9.]+) sec", r.stderr))}
-            best_th = min(ours, key=lambda x: ours[x]["whole_process_s"])
-            e2e_cli = {"workload": "%d reads x %d bp of this workload as one plain FASTQ file in %s (%.2f GB)"
-                                   % (n_c, READ_LEN, os.path.dirname(big), os.path.getsize(big) / 1e9),
-                       "value": ours[best_th]["whole_process_gbases_s"], "unit": "Gbases/s",
-                       "reference": {"value": cli_bases / t_ref / 1e9, "unit": "Gbases/s", "threads": threads, "whole_process_s": t_ref,
-                                     "kind": kind},
-                       "speedup_whole_process": t_ref / ours[best_th]["whole_process_s"], "this_repo": ours,
-                       "vaf_bytes": "identical",
-                       "note": "process start (CUDA context creation, 0.5-3 s on these boxes without a persistence daemon: "
-                               "this_repo.*.cuda_init_context_module_s), pattern load, FASTQ parse, count and VAF write on both sides"}
-            os.unlink(big)
-            parity["cli_vaf_bytes_vs_%s_on_%d_reads" % (kind, n_c)] = "identical at -t 1 and -t %d" % ncpu
+            cli_job = (n_c, big, exe, kind, threads, ncpu)
 
     # ---- BASELINE config 4: k sweep on reads with N runs (N = 1 only)
     k_sweep = None
@@ -807,6 +780,46 @@ def main():
         eng = None
         torch.cuda.empty_cache()
         modes = {"kc": run_kc_mode(args.kc_reads)}
+
+    if rank == 0 and cli_job is not None:
+        if eng is not None:
+            eng.close()
+            eng = None
+        host = stream = scratch = None  # the page-locked buffer and the resident stream go too
+        torch.cuda.empty_cache()
+        n_c, big, exe, kind, threads, ncpu = cli_job
+        cli_bases = n_c * READ_LEN
+        t_ref = time_reference(exe, pattern_file, big, os.path.join(tmp, "big_ref.vaf"), threads)
+        cli_exe = os.path.join(PKG, "vaf-counter")
+        ours = {}
+        for th in sorted({1, ncpu}):
+            out_vaf = os.path.join(tmp, "big_cli%d.vaf" % th)
+            t0 = time.perf_counter()
+            r = subprocess.run([cli_exe, "-k", str(K), "-t", str(th), "-v", "-p", pattern_file, "-o", out_vaf, big],
+                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
+                               env=dict(os.environ, VAFGPU_TIMING="1"))  # start-up breakdown on stderr
+            wall = time.perf_counter() - t0
+            assert open(out_vaf, "rb").read() == open(os.path.join(tmp, "big_ref.vaf"), "rb").read(), \
+                "CLI output differs from the reference's at -t %d" % th
+            m = re.search(rb"K-mer counting:\s+([0-9.]+) sec", r.stderr)
+            ctx_ms = sum(float(x) for x in re.findall(rb"\[vafgpu\] (?:CUDA init \(device count\)|context|module load \+ policy kernel)\s+([0-9.]+) ms", r.stderr))
+            ours["t%d" % th] = {"whole_process_s": wall, "whole_process_gbases_s": cli_bases / wall / 1e9,
+                                "counting_phase_gbases_s": cli_bases / max(float(m.group(1)), 1e-9) / 1e9 if m else None,
+                                "cuda_init_context_module_s": ctx_ms / 1e3,
+                                "phases_ms": {a.decode().strip(): float(b) for a, b in re.findall(rb"\[vafgpu\] (.+?)\s+([0-9.]+) ms", r.stderr)},
+                                "main_total_s": (lambda t: float(t.group(1)) if t else None)(re.search(rb"Total runtime:\s+([0-9.]+) sec", r.stderr))}
+        best_th = min(ours, key=lambda x: ours[x]["whole_process_s"])
+        e2e_cli = {"workload": "%d reads x %d bp of this workload as one plain FASTQ file in %s (%.2f GB)"
+                               % (n_c, READ_LEN, os.path.dirname(big), os.path.getsize(big) / 1e9),
+                   "value": ours[best_th]["whole_process_gbases_s"], "unit": "Gbases/s",
+                   "reference": {"value": cli_bases / t_ref / 1e9, "unit": "Gbases/s", "threads": threads, "whole_process_s": t_ref,
+                                 "kind": kind},
+                   "speedup_whole_process": t_ref / ours[best_th]["whole_process_s"], "this_repo": ours,
+                   "vaf_bytes": "identical",
+                   "note": "process start (CUDA context creation, 0.5-3 s on these boxes without a persistence daemon: "
+                           "this_repo.*.cuda_init_context_module_s), pattern load, FASTQ parse, count and VAF write on both sides"}
+        os.unlink(big)
+        parity["cli_vaf_bytes_vs_%s_on_%d_reads" % (kind, n_c)] = "identical at -t 1 and -t %d" % ncpu
 
     if rank == 0:
         traffic, traffic_note = None, None

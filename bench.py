@@ -797,7 +797,8 @@ def main():
             t0 = time.perf_counter()
             r = subprocess.run([cli_exe, "-k", str(K), "-t", str(th), "-v", "-p", pattern_file, "-o", out_vaf, big],
                                check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
-                               env=dict(os.environ, VAFGPU_TIMING="1"))  # start-up breakdown on stderr
+                               env=dict(os.environ, VAFGPU_TIMING="1",  # start-up breakdown on stderr
+                                        CUDA_VISIBLE_DEVICES=(os.environ.get("CUDA_VISIBLE_DEVICES") or "0").split(",")[0]))  # N = 1
             wall = time.perf_counter() - t0
             assert open(out_vaf, "rb").read() == open(os.path.join(tmp, "big_ref.vaf"), "rb").read(), \
                 "CLI output differs from the reference's at -t %d" % th

@@ -341,10 +341,20 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 
 	int rc = VAFGPU_OK;
 	c->devs.resize(n_devices);
-	for (int i = 0; i < n_devices && rc == VAFGPU_OK; ++i) {
+	/* every device is set up by a thread of its own: creating a context takes 0.2-2 s, and eight of them one
+	 * after the other were most of the start-up of a run on eight GPUs (the breakdown is printed for device 0) */
+	auto setup = [&](int i) -> int {
 		Device &d = c->devs[i];
 		d.ordinal = i;
-		rc = [&]() -> int {
+		double tt = tnow(); /* shadows the caller's: laps of this device */
+		auto lap = [&](const char *what) {
+			if (timing && i == 0) {
+				double t = tnow();
+				fprintf(stderr, "[vafgpu] %-28s %8.1f ms\n", what, (t - tt) * 1e3);
+				tt = t;
+			}
+		};
+		return [&]() -> int {
 			cudaDeviceProp prop;
 			CU(c, cudaSetDevice(i));
 			CU(c, cudaGetDeviceProperties(&prop, i));
@@ -395,7 +405,17 @@ int vafgpu_create(vafgpu_ctx **out, int k, const uint64_t *keys, const uint32_t 
 			lap("staging blocks");
 			return VAFGPU_OK;
 		}();
+	};
+	if (n_devices == 1) {
+		rc = setup(0);
+	} else {
+		std::vector<int> rcs((size_t)n_devices, VAFGPU_OK);
+		std::vector<std::thread> th;
+		for (int i = 0; i < n_devices; ++i) th.emplace_back([&, i] { rcs[(size_t)i] = setup(i); });
+		for (std::thread &t : th) t.join();
+		for (int i = 0; i < n_devices && rc == VAFGPU_OK; ++i) rc = rcs[(size_t)i];
 	}
+	tt = tnow();
 	/* Several devices: every kernel adds into device 0's counter vector through NVLink peer
 	 * memory (hits are rare -- tens of thousands per 10^10 bases -- and RED.ADD needs no answer),
 	 * so the result is final when the streams have drained.  Without peer access between all

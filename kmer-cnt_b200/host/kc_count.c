@@ -13,12 +13,14 @@
  *   -t  number of host reader threads (the insert it used to parallelise runs on the GPU): a
  *       plain four-line FASTQ is cut into slices read in parallel (ingest.h), anything else
  *       goes through the one sequential reader
- * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: all visible);
+ * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: as many of the visible ones as
+ *              the table of a file this size needs -- one up to ~50 GB of input -- more if it fills up);
  *              KCGPU_TABLE_SLOTS=n slots per GPU to start with (default: from the file size);
  *              either way a table that fills up is doubled and the file counted again.
  * Deviations: k outside 1..31 is rejected (the reference shifts by >= 64 bits there), and a
  * file that cannot be opened is an error (the reference dereferences NULL, kc-c4.c:166,247-248).
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,6 +41,39 @@ static double now(void)
 	struct timeval tv;
 	gettimeofday(&tv, NULL);
 	return tv.tv_sec + tv.tv_usec * 1e-6;
+}
+
+/* one context per GPU, each made by a thread of its own: creating a CUDA context takes 0.2-2 s */
+typedef struct {
+	kcgpu_ctx **out;
+	int k, device, rc;
+	uint64_t slots, list_slots;
+} create_job_t;
+
+static void *create_one(void *arg)
+{
+	create_job_t *j = (create_job_t *)arg;
+	j->rc = kcgpu_create(j->out, j->k, j->slots, j->list_slots, STAGING_BYTES, j->device);
+	return NULL;
+}
+
+static int create_all(kcgpu_ctx **ctx, int n_dev, int k, uint64_t slots, uint64_t list_slots)
+{
+	create_job_t job[KCGPU_MAX_OWNERS];
+	pthread_t th[KCGPU_MAX_OWNERS];
+	int i, rc = VAFGPU_OK;
+	for (i = 0; i < n_dev; ++i) {
+		job[i].out = &ctx[i], job[i].k = k, job[i].device = i, job[i].rc = VAFGPU_OK, job[i].slots = slots, job[i].list_slots = list_slots;
+		if (n_dev == 1 || pthread_create(&th[i], NULL, create_one, &job[i]) != 0) {
+			create_one(&job[i]);
+			th[i] = 0;
+		}
+	}
+	for (i = 0; i < n_dev; ++i) {
+		if (n_dev > 1 && th[i]) pthread_join(th[i], NULL);
+		if (job[i].rc != VAFGPU_OK && rc == VAFGPU_OK) rc = job[i].rc;
+	}
+	return rc;
 }
 
 static uint64_t guess_slots(const char *fn, int n_dev)
@@ -155,9 +190,20 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "ERROR: no CUDA device (this build has no CPU path)\n");
 		return 1;
 	}
-	if (getenv("KCGPU_DEVICES") && atoi(getenv("KCGPU_DEVICES")) > 0 && atoi(getenv("KCGPU_DEVICES")) < n_dev)
-		n_dev = atoi(getenv("KCGPU_DEVICES"));
 	if (n_dev > KCGPU_MAX_OWNERS) n_dev = KCGPU_MAX_OWNERS;
+	const int n_visible = n_dev;
+	if (getenv("KCGPU_DEVICES") && atoi(getenv("KCGPU_DEVICES")) > 0) {
+		if (atoi(getenv("KCGPU_DEVICES")) < n_dev) n_dev = atoi(getenv("KCGPU_DEVICES"));
+	} else {
+		/* as many GPUs as the table needs, not as many as there are: one GPU counts faster than the readers
+		 * parse, and every further one costs a context and the peer mappings (seconds) before the first read */
+		const uint64_t est = guess_slots(fn, 1); /* 0: a pipe, size unknown */
+		const uint64_t per_gpu = (uint64_t)6 << 30; /* slots: 48 GB of table beside its lists and filter */
+		if (est) {
+			uint64_t need = (est + per_gpu - 1) / per_gpu;
+			if (need < (uint64_t)n_dev) n_dev = (int)(need > 0 ? need : 1);
+		}
+	}
 
 	const int direct = getenv("KCGPU_DIRECT") && atoi(getenv("KCGPU_DIRECT")); /* no region lists (development) */
 	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn, n_dev);
@@ -168,11 +214,10 @@ int main(int argc, char *argv[])
 		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
 		uint64_t hist[256], part[256], overflow = 0;
 		kcgpu_stats st;
-		for (i = 0; i < n_dev; ++i)
-			if (kcgpu_create(&ctx[i], k, slots, direct ? KCGPU_NO_LISTS : 0, STAGING_BYTES, i) != VAFGPU_OK) {
-				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
-				return 1;
-			}
+		if (create_all(ctx, n_dev, k, slots, direct ? KCGPU_NO_LISTS : 0) != VAFGPU_OK) {
+			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
+			return 1;
+		}
 		if (n_dev > 1 && kcgpu_link(ctx, n_dev) != VAFGPU_OK) {
 			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
 			return 1;
@@ -213,9 +258,19 @@ int main(int argc, char *argv[])
 			struct stat sb;
 			/* a pipe cannot be read twice; a request the device cannot hold is cut down by
 			 * kcgpu_create, so a table that did not grow is the largest one that fits */
-			if (attempt >= 12 || stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode) || (attempt && slots <= got_before)) {
+			if (attempt >= 12 || stat(fn, &sb) != 0 || !S_ISREG(sb.st_mode)) {
 				fprintf(stderr, "ERROR: the k-mer table (%llu slots per GPU) is full\n", (unsigned long long)slots);
 				return 1;
+			}
+			if (attempt && slots <= got_before) { /* the table cannot grow on this GPU: take more GPUs if there are any */
+				if (n_dev >= n_visible) {
+					fprintf(stderr, "ERROR: the k-mer table (%llu slots per GPU) is full\n", (unsigned long long)slots);
+					return 1;
+				}
+				n_dev = n_dev * 2 < n_visible ? n_dev * 2 : n_visible;
+				fprintf(stderr, "[kc-c4] table full, counting again on %d GPUs\n", n_dev);
+				got_before = 0;
+				continue;
 			}
 			got_before = slots;
 			slots *= 2;

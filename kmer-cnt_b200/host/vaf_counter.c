@@ -9,7 +9,8 @@
  *   -t  is the number of host reader threads (the lookup it used to parallelise runs on the
  *       GPU); -t 1 reads every file with the one sequential reader
  *   -b  is the staging block size in bases, as in the reference
- * Environment: CUDA_VISIBLE_DEVICES selects the GPUs (all visible ones are used);
+ * Environment: CUDA_VISIBLE_DEVICES selects the GPUs, VAFGPU_DEVICES=n how many of them are used (default 1: one GPU
+ *              scans hundreds of times faster than the readers parse; 0 = all visible);
  *              VAFGPU_RECIPE=1 runs the literal on-device recipe (verification mode).
  */
 #include <limits.h>
@@ -193,7 +194,10 @@ int main(int argc, char *argv[])
 	 * pace) and page-locking the blocks is start-up time: 18 blocks of 16 / 4 / 2 MiB take 280 / 110 / 30 ms */
 	size_t staging = block_size > 0 ? (size_t)block_size : 0;
 	if (staging == 0 || staging > ((size_t)2 << 20)) staging = (size_t)2 << 20;
-	if (vafgpu_create(&ctx, k, keys, vals, n_keys, (uint32_t)db->n, staging, n_buffers, 0, flags) != VAFGPU_OK) {
+	/* one GPU unless VAFGPU_DEVICES asks for more (0 = all): it scans 300 times faster than -t readers parse, and
+	 * every further GPU is a context (and its share of seconds) before the first read */
+	int n_gpus = getenv("VAFGPU_DEVICES") ? atoi(getenv("VAFGPU_DEVICES")) : 1;
+	if (vafgpu_create(&ctx, k, keys, vals, n_keys, (uint32_t)db->n, staging, n_buffers, n_gpus < 0 ? 1 : n_gpus, flags) != VAFGPU_OK) {
 		fprintf(stderr, "Error: failed to create k-mer map: %s\n", vafgpu_strerror(NULL));
 		return 1;
 	}

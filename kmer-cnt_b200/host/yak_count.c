@@ -14,7 +14,8 @@
  *   -K  bases per turn when reads are dealt to several GPUs (the reference's chunk size)
  *   -t  number of host reader threads
  *   -b  the filter gets 2^b bits on every GPU (cut down to a quarter of its memory)
- * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: all visible);
+ * Environment: CUDA_VISIBLE_DEVICES / KCGPU_DEVICES=n select the GPUs (default: as many of the visible ones as
+ *              the table of a file this size needs -- one up to ~50 GB of input -- more if it fills up);
  *              KCGPU_TABLE_SLOTS=n slots per GPU to start with (default: from the file size);
  *              either way a table that fills up is doubled and the files counted again;
  *              KCGPU_TIMING: phase times on stderr.
@@ -23,6 +24,7 @@
  * reference's by false positives of the filter (include/kcgpu.h), as they do between two values
  * of -b in the reference itself.
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -104,6 +106,40 @@ static const char *engine_error(void *engine)
 	return "unknown error";
 }
 
+/* one context per GPU, each made by a thread of its own: creating a CUDA context takes 0.2-2 s */
+typedef struct {
+	kcgpu_ctx **out;
+	int k, device, rc;
+	uint64_t slots;
+	int bloom_bits, bloom_hashes;
+} create_job_t;
+
+static void *create_one(void *arg)
+{
+	create_job_t *j = (create_job_t *)arg;
+	j->rc = kcgpu_create_filtered(j->out, j->k, j->slots, 0, STAGING_BYTES, j->device, j->bloom_bits, j->bloom_hashes);
+	return NULL;
+}
+
+static int create_all(kcgpu_ctx **ctx, int n_dev, int k, uint64_t slots, int bloom_bits, int bloom_hashes)
+{
+	create_job_t job[KCGPU_MAX_OWNERS];
+	pthread_t th[KCGPU_MAX_OWNERS];
+	int i, rc = VAFGPU_OK;
+	for (i = 0; i < n_dev; ++i) {
+		job[i].out = &ctx[i], job[i].k = k, job[i].device = i, job[i].rc = VAFGPU_OK, job[i].slots = slots, job[i].bloom_bits = bloom_bits, job[i].bloom_hashes = bloom_hashes;
+		if (n_dev == 1 || pthread_create(&th[i], NULL, create_one, &job[i]) != 0) {
+			create_one(&job[i]);
+			th[i] = 0;
+		}
+	}
+	for (i = 0; i < n_dev; ++i) {
+		if (n_dev > 1 && th[i]) pthread_join(th[i], NULL);
+		if (job[i].rc != VAFGPU_OK && rc == VAFGPU_OK) rc = job[i].rc;
+	}
+	return rc;
+}
+
 static uint64_t guess_slots(const char *fn, int n_dev)
 {
 	struct stat sb;
@@ -177,9 +213,20 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "ERROR: no CUDA device (this build has no CPU path)\n");
 		return 1;
 	}
-	if (getenv("KCGPU_DEVICES") && atoi(getenv("KCGPU_DEVICES")) > 0 && atoi(getenv("KCGPU_DEVICES")) < n_dev)
-		n_dev = atoi(getenv("KCGPU_DEVICES"));
 	if (n_dev > KCGPU_MAX_OWNERS) n_dev = KCGPU_MAX_OWNERS;
+	const int n_visible = n_dev;
+	if (getenv("KCGPU_DEVICES") && atoi(getenv("KCGPU_DEVICES")) > 0) {
+		if (atoi(getenv("KCGPU_DEVICES")) < n_dev) n_dev = atoi(getenv("KCGPU_DEVICES"));
+	} else {
+		/* as many GPUs as the table needs, not as many as there are: one GPU counts faster than the readers
+		 * parse, and every further one costs a context and the peer mappings (seconds) before the first read */
+		const uint64_t est = guess_slots(fn1, 1); /* 0: a pipe, size unknown */
+		const uint64_t per_gpu = (uint64_t)6 << 30; /* slots: 48 GB of table beside its lists and filter */
+		if (est) {
+			uint64_t need = (est + per_gpu - 1) / per_gpu;
+			if (need < (uint64_t)n_dev) n_dev = (int)(need > 0 ? need : 1);
+		}
+	}
 
 	uint64_t slots = getenv("KCGPU_TABLE_SLOTS") ? strtoull(getenv("KCGPU_TABLE_SLOTS"), NULL, 10) : guess_slots(fn1, n_dev);
 	uint64_t got_before = 0;
@@ -189,11 +236,10 @@ int main(int argc, char *argv[])
 		kcgpu_ctx *ctx[KCGPU_MAX_OWNERS] = {0};
 		uint64_t hist[1024], part[1024], overflow = 0, tot = 0;
 		kcgpu_stats st;
-		for (i = 0; i < n_dev; ++i)
-			if (kcgpu_create_filtered(&ctx[i], k, slots, 0, STAGING_BYTES, i, filter ? (bf_shift > 40 ? 40 : bf_shift) : 0, bf_n_hash > 64 ? 64 : bf_n_hash) != VAFGPU_OK) {
-				fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
-				return 1;
-			}
+		if (create_all(ctx, n_dev, k, slots, filter ? (bf_shift > 40 ? 40 : bf_shift) : 0, bf_n_hash > 64 ? 64 : bf_n_hash) != VAFGPU_OK) {
+			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(NULL));
+			return 1;
+		}
 		if (n_dev > 1 && kcgpu_link(ctx, n_dev) != VAFGPU_OK) {
 			fprintf(stderr, "ERROR: %s\n", kcgpu_strerror(ctx[0]));
 			return 1;
@@ -229,10 +275,19 @@ int main(int argc, char *argv[])
 		if (timing) fprintf(stderr, "[yak-count] destroy                         %8.1f ms\n", (now() - t0) * 1e3);
 		if (overflow) { /* never print a histogram with k-mers missing */
 			struct stat sb;
-			if (attempt >= 12 || stat(fn1, &sb) != 0 || !S_ISREG(sb.st_mode) || stat(fn2, &sb) != 0 || !S_ISREG(sb.st_mode) ||
-			    (attempt && slots <= got_before)) {
+			if (attempt >= 12 || stat(fn1, &sb) != 0 || !S_ISREG(sb.st_mode) || stat(fn2, &sb) != 0 || !S_ISREG(sb.st_mode)) {
 				fprintf(stderr, "ERROR: the k-mer table (%llu slots per GPU) is full\n", (unsigned long long)slots);
 				return 1;
+			}
+			if (attempt && slots <= got_before) { /* the table cannot grow on this GPU: take more GPUs if there are any */
+				if (n_dev >= n_visible) {
+					fprintf(stderr, "ERROR: the k-mer table (%llu slots per GPU) is full\n", (unsigned long long)slots);
+					return 1;
+				}
+				n_dev = n_dev * 2 < n_visible ? n_dev * 2 : n_visible;
+				fprintf(stderr, "[yak-count] table full, counting again on %d GPUs\n", n_dev);
+				got_before = 0;
+				continue;
 			}
 			got_before = slots;
 			slots *= 2;

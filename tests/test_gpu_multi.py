@@ -115,3 +115,29 @@ def test_one_process_per_gpu_shares_one_vector_over_ipc(tmp_path, oracle, lib):
         assert child.returncode == 0, err.decode()[-2000:]
         got, _ = eng.finish()          # after the child has drained (its exit is the barrier)
     assert np.array_equal(got, want)
+
+
+@needs2
+def test_command_lines_on_two_gpus_print_what_they_print_on_one(tmp_path, lib):
+    """the three command lines use one GPU unless told (or forced by the table size) to take more: with
+    VAFGPU_DEVICES / KCGPU_DEVICES = 2 the bytes they write are the ones they write on one GPU"""
+    rng = np.random.default_rng(77)
+    pats = util.make_patterns(rng, 300, 21)
+    reads = util.make_reads(rng, pats, 21, 30000, mean_len=150, jitter=30, junk_rate=0.003)
+    pf, fq = str(tmp_path / "p.txt"), str(tmp_path / "r.fq")
+    util.write_patterns(pf, pats)
+    with open(fq, "wb") as fh:
+        for i, r in enumerate(reads):
+            fh.write(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)))
+    outs = {}
+    for nd in ("1", "2"):
+        out = str(tmp_path / ("o%s.vaf" % nd))
+        r = subprocess.run([os.path.join(util.PKG, "vaf-counter"), "-k", "21", "-t", "4", "-v", "-p", pf, "-o", out, fq], check=True,
+                           capture_output=True, env=dict(os.environ, VAFGPU_DEVICES=nd))
+        assert ("Devices:               %s" % nd).encode() in r.stderr
+        outs["vaf" + nd] = open(out, "rb").read()
+        for exe, args in (("kc-c4", ["-k", "31", "-t", "4"]), ("yak-count", ["-k", "31", "-t", "4", "-b", "26"])):
+            outs[exe + nd] = subprocess.run([os.path.join(util.PKG, exe)] + args + [fq], check=True, capture_output=True,
+                                            env=dict(os.environ, KCGPU_DEVICES=nd)).stdout
+    for name in ("vaf", "kc-c4", "yak-count"):
+        assert outs[name + "1"] == outs[name + "2"] and len(outs[name + "1"]) > 100, name

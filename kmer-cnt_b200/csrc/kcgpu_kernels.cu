@@ -221,12 +221,11 @@ __global__ void __launch_bounds__(KC_THREADS) kc_scan_kernel(const CountArgs a, 
 #define KC_TILE_MIN_CTAS 2
 #endif
 enum { KC_TILE_ENTRIES = KC_TILE_THREADS * KC_TILE_N };
+static_assert(KC_TILE_ENTRIES == KC_TILE_BIAS, "the bias of kc_tile_word is the size of a tile");
 
 struct TileSmem {
 	unsigned long long *stage; /* KC_TILE_ENTRIES: the tile, sorted by region                          */
-	unsigned long long *gpos;  /* per region: where entry i of the sorted tile goes, minus i, plus KC_TILE_ENTRIES --
-	                              an index into the lists, or (bit 63 set) a position in the region's list, which
-	                              is about to run full                                                           */
+	unsigned long long *gpos;  /* per region: where its entries go (kc_tile_word, kcgpu_kernels.cuh)               */
 	uint32_t *cnt;             /* per region: entries in the tile, then (lbase) where its run starts   */
 };
 
@@ -297,9 +296,7 @@ __device__ __forceinline__ void kc_file_tile(const uint64_t (&q)[KC_TILE_N], con
 			s.cnt[r] = at;
 			if (c) {
 				const unsigned long long g = atomicAdd(d.cursors + (uint64_t)r * KC_CURSOR_STRIDE, (unsigned long long)c);
-				/* + KC_TILE_ENTRIES - at: never negative, so that bit 63 can flag the run that does not fit */
-				const unsigned long long rel = g + KC_TILE_ENTRIES - at;
-				s.gpos[r] = g + c <= d.cap ? (unsigned long long)r * d.stride + rel : rel | 1ull << 63;
+				s.gpos[r] = kc_tile_word(g, c, at, r, d.cap, d.stride);
 			}
 			at += c;
 		}
@@ -314,11 +311,10 @@ __device__ __forceinline__ void kc_file_tile(const uint64_t (&q)[KC_TILE_N], con
 	for (uint32_t i = tid; i < total; i += KC_TILE_THREADS) {
 		const uint64_t w = s.stage[i];
 		const uint32_t r = (uint32_t)w & rmask;
-		const uint64_t at = s.gpos[r] + i;
-		if (!(at >> 63)) {
-			__stcs(reinterpret_cast<unsigned long long *>(d.lists) + (at - KC_TILE_ENTRIES), (unsigned long long)w); /* read once, by the flush: no reason to stay in L2 */
+		uint64_t pos;
+		if (kc_tile_fits(s.gpos[r], i, &pos)) {
+			__stcs(reinterpret_cast<unsigned long long *>(d.lists) + pos, (unsigned long long)w); /* read once, by the flush: no reason to stay in L2 */
 		} else { /* the run crosses the end of the list: what fits is filed, the rest goes straight to the table */
-			const uint64_t pos = (at & ~(1ull << 63)) - KC_TILE_ENTRIES;
 			if (pos < d.cap) {
 				d.lists[(uint64_t)r * d.stride + pos] = w;
 			} else {

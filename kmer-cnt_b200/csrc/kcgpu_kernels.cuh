@@ -224,6 +224,28 @@ KC_HD uint32_t kc_extract16(const uint4 *chunks, const uint64_t c, const uint64_
 	return ok;
 }
 
+/* ---- where a tile's entries go (the tile kernels; host + device so that tests/cpu_sim can check the arithmetic) ----
+ * A region whose c entries stand at places lbase .. lbase + c - 1 of the sorted tile has reserved positions
+ * g .. g + c - 1 of its list (g = what its cursor held).  One 64-bit word per region tells entry i of the tile
+ * where to go: word + i is, if the whole run fits the list, KC_TILE_BIAS + its index in the list area
+ * (region * stride + g + i - lbase), else -- bit 63 set -- KC_TILE_BIAS + its position in the region's list
+ * (g + i - lbase), which the writer compares with the capacity itself.  The bias keeps word + i free of
+ * borrows into bit 63 (lbase <= KC_TILE_BIAS). */
+#define KC_TILE_BIAS 8192ull /* entries of a tile: 512 threads x 16 positions */
+
+KC_HD unsigned long long kc_tile_word(unsigned long long g, uint32_t c, uint32_t lbase, uint32_t region, uint64_t cap, uint64_t stride)
+{
+	const unsigned long long rel = g + KC_TILE_BIAS - lbase;
+	return g + c <= cap ? (unsigned long long)region * stride + rel : rel | 1ull << 63;
+}
+/* entry i: true and its index in the list area, or false and its position in its region's list */
+KC_HD bool kc_tile_fits(unsigned long long word, uint32_t i, uint64_t *where)
+{
+	const unsigned long long at = word + i;
+	*where = (at & ~(1ull << 63)) - KC_TILE_BIAS;
+	return !(at >> 63);
+}
+
 struct CountArgs {
 	const uint8_t *bytes; /* stream: reads separated by '\n', 16-byte aligned */
 	uint64_t n_bytes;     /* multiple of 16                                    */

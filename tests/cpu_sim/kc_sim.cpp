@@ -74,6 +74,24 @@ void sim_kc_geometry(int k, uint64_t n_slots, uint64_t list_cap, uint32_t region
 	out[6] = out[2] + (out[5] + (list_cap / 2 << region_bits)) * 8;
 }
 
+/* one region's run of a tile: entries lbase .. lbase + c - 1, cursor value g; returns 0 when every entry is sent where
+ * it belongs (kc_tile_word / kc_tile_fits), else 1 + the first entry that is not */
+uint64_t sim_kc_tile_run(uint64_t g, uint32_t c, uint32_t lbase, uint32_t region, uint64_t cap, uint64_t stride)
+{
+	const unsigned long long word = kc_tile_word(g, c, lbase, region, cap, stride);
+	for (uint32_t i = lbase; i < lbase + c; ++i) {
+		uint64_t where;
+		const bool fits = kc_tile_fits(word, i, &where);
+		const uint64_t pos = g + (i - lbase);
+		if (g + c <= cap) {
+			if (!fits || where != (uint64_t)region * stride + pos) return 1 + i;
+		} else {
+			if (fits || where != pos) return 1 + i;
+		}
+	}
+	return 0;
+}
+
 uint64_t sim_kc_hash64(uint64_t key, int k) { return kc_hash64(key, (1ull << 2 * k) - 1); }
 
 /* hash64 of every canonical k-mer of the stream (n_bytes a multiple of 16), in stream order, as the

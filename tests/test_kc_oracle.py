@@ -230,6 +230,25 @@ def test_window_extraction_is_count_seq_buf(kco, ksim, k):
     assert np.array_equal(got, want2)
 
 
+def test_tile_runs_land_where_their_cursor_says(ksim):
+    """the word a region of a sorted tile gets (kc_tile_word) sends entry i of the tile to index
+    region * stride + g + i - lbase of the list area when the whole run fits the list, and else flags it with its
+    position in the list, for every place of the run in the tile, first and last regions, empty and full lists,
+    cursors that ran on far past the capacity, halves of lists (stride > cap)"""
+    rng = np.random.default_rng(12)
+    cases = [(0, 1, 0, 0, 64, 64), (0, 8192, 0, 0, 8192, 8192), (63, 1, 8191, 4095, 64, 64), (64, 1, 0, 0, 64, 64),
+             (60, 8, 100, 7, 64, 128), (1 << 40, 5, 8000, 4095, 1 << 30, 1 << 31), (0, 3, 8189, 0, 2, 64)]
+    for _ in range(20000):
+        cap = int(rng.choice([64, 96, 4096, 1 << 22, 1 << 33]))
+        stride = cap * int(rng.choice([1, 2]))
+        c = int(rng.integers(1, 200))
+        lbase = int(rng.integers(0, 8192 - c + 1))
+        g = int(rng.choice([0, max(cap - c, 0), max(cap - c + 1, 0), cap, int(rng.integers(0, 2 * cap + 1))]))
+        cases.append((g, c, lbase, int(rng.integers(0, 4096)), cap, stride))
+    for g, c, lbase, region, cap, stride in cases:
+        assert ksim.lib.sim_kc_tile_run(g, c, lbase, region, cap, stride) == 0, (g, c, lbase, region, cap, stride)
+
+
 @pytest.mark.parametrize("n_parts", [1, 2, 3, 8, 16])
 def test_push_route_flush_on_the_host(kco, ksim, n_parts):
     """the several-owner form step by step on the host: inbox, region lists, table -- with lists

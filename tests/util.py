@@ -422,6 +422,8 @@ class KcSim:
         lib.sim_kc_count.restype = C.c_uint64
         lib.sim_kc_extract.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         lib.sim_kc_extract.restype = C.c_uint64
+        lib.sim_kc_tile_run.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]
+        lib.sim_kc_tile_run.restype = C.c_uint64
         self.lib = lib
 
     def extract(self, k, stream: np.ndarray) -> np.ndarray:

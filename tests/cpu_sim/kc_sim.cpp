@@ -8,6 +8,9 @@
  * kernels' bookkeeping step by step (inbox, region lists, table) and returns the 256-bin
  * histogram over all owners.
  *
+ * sim_kc_tile_run checks where the entries of one region's run of a sorted tile are sent
+ * (kc_tile_word / kc_tile_fits of the header) against the plain statement of it.
+ *
  * sim_kc_extract runs the tile kernels' own extraction (kc_extract16 of the header: packed
  * 48-byte windows, no byte loop) over a stream, chunk by chunk as the threads do.
  */
